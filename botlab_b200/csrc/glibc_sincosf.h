@@ -1,0 +1,99 @@
+// Bit-exact restatement of glibc 2.39's sincosf for |x| < 120, usable from host C/C++ and from CUDA device code.
+//
+// Why: the reference's sensor model truncates `range * cosf(theta) * cellsPerMeter + start` to a cell index
+// (src/slam/sensor_model.cpp:34-38), so a 1-ulp difference in cosf/sinf can move an endpoint to another cell and change
+// a particle's score by whole units.  g++ -O3 merges the reference's std::cos/std::sin(float) into one `sincosf` call,
+// and CUDA's sincosf is a different (also not correctly rounded) function.  Parity therefore needs glibc's algorithm:
+// third-party code, not in /root/reference: glibc 2.39 (Ubuntu 2.39-0ubuntu8.5), sysdeps/ieee754/flt-32/s_sincosf.c
+// with the x86-64 FMA ifunc variant (__sincosf_fma, sysdeps/x86_64/fpu/multiarch + sincosf_poly.h) -- the one every
+// FMA-capable x86-64 host selects.  The algorithm (Szabolcs Nagy's ARM optimized-routines sincosf): reduce
+// x to [-pi/4, pi/4] in double with n = round(x * 2/pi), evaluate degree-7/8 double polynomials, round once to float.
+// The operation order and fusion below were read off the disassembly of libm.so.6's __sincosf_fma and the constants
+// from its .rodata; tests/test_sincosf.py checks it against the live libm over every float in [-4, 4] (strided in CI).
+#ifndef BOTLAB_B200_GLIBC_SINCOSF_H
+#define BOTLAB_B200_GLIBC_SINCOSF_H
+
+#include <stdint.h>
+#if defined(__CUDA_ARCH__)
+#define GS_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define GS_MUL(a, b) __dmul_rn((a), (b))
+#define GS_HD __host__ __device__ __forceinline__
+#else
+#include <math.h>
+#include <string.h>
+#define GS_FMA(a, b, c) fma((a), (b), (c))
+#define GS_MUL(a, b) ((a) * (b))
+#if defined(__CUDACC__)
+#define GS_HD __host__ __device__ __forceinline__
+#else
+#define GS_HD static inline
+#endif
+#endif
+
+// Polynomial coefficients (__sincosf_table[0]; table[1] negates the cosine set).
+#define GS_C0 1.0
+#define GS_C1 (-0x1.ffffffd0c621cp-2)
+#define GS_C2 0x1.55553e1068f19p-5
+#define GS_C3 (-0x1.6c087e89a359dp-10)
+#define GS_C4 0x1.99343027bf8c3p-16
+#define GS_S1 (-0x1.555545995a603p-3)
+#define GS_S2 0x1.1107605230bc4p-7
+#define GS_S3 (-0x1.994eb3774cf24p-13)
+#define GS_HPI_INV 0x1.45F306DC9C883p+23 /* 2/pi * 2^24 */
+#define GS_HPI 0x1.921FB54442D18p0       /* pi/2 */
+
+GS_HD uint32_t gs_float_bits(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return u;
+#endif
+}
+
+// Valid for |x| < 120 (the engine only ever passes angles wrapped to [-pi, pi]); larger |x| would need glibc's
+// reduce_large table, which this path never reaches.
+GS_HD void glibc_sincosf(float xf, float* sinp, float* cosp)
+{
+    const uint32_t top = (gs_float_bits(xf) >> 20) & 0x7ff;
+    double x = (double)xf;
+    double xs, x2, csign;   // xs: reduced argument with the quadrant sign folded in; csign: +1/-1 on the cosine set
+    int swap;
+    if (top < 0x3f4) {                      // |x| < pi/4 (abstop12 compare)
+        if (top < 0x398) {                  // |x| < 2^-12
+            *sinp = xf;
+            *cosp = 1.0f;
+            return;
+        }
+        xs = x;
+        x2 = GS_MUL(x, x);
+        csign = 1.0;
+        swap = 0;
+    } else {
+        double r = GS_MUL(x, GS_HPI_INV);
+        int n = ((int32_t)r + 0x800000) >> 24;              // round to nearest quadrant
+        double xr = GS_FMA(-(double)n, GS_HPI, x);          // vfnmadd: x - n*hpi, fused
+        double sgn = ((n + 1) & 2) ? -1.0 : 1.0;            // sign[n & 3] = {1,-1,-1,1}
+        xs = GS_MUL(xr, sgn);
+        x2 = GS_MUL(xr, xr);
+        csign = (n & 2) ? -1.0 : 1.0;
+        swap = n & 1;
+    }
+    double x3 = GS_MUL(x2, xs);
+    double x4 = GS_MUL(x2, x2);
+    double s1 = GS_FMA(x2, GS_S3, GS_S2);
+    double c2 = GS_FMA(x2, csign * GS_C4, csign * GS_C3);
+    double c1 = GS_FMA(x2, csign * GS_C1, csign * GS_C0);
+    double x5 = GS_MUL(x2, x3);
+    double x6 = GS_MUL(x2, x4);
+    double s = GS_FMA(x3, GS_S1, xs);
+    double c = GS_FMA(x4, csign * GS_C2, c1);
+    float sv = (float)GS_FMA(x5, s1, s);
+    float cv = (float)GS_FMA(x6, c2, c);
+    if (swap) { *sinp = cv; *cosp = sv; }
+    else      { *sinp = sv; *cosp = cv; }
+}
+
+#endif  // BOTLAB_B200_GLIBC_SINCOSF_H
