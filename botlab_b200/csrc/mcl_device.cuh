@@ -1,0 +1,162 @@
+// Device-side arithmetic of the MCL hot path, written so that every rounding matches the reference's x86-64 SSE2
+// build (no FMA contraction, mixed float/double evaluation exactly as SURVEY.md Appendix A records it).
+// Compile with -fmad=false; the only fused operations are the explicit __fma_rn calls inside glibc_sincosf.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "glibc_sincosf.h"
+
+namespace mcl {
+
+constexpr double kPi = 3.14159265358979323846;       // M_PI
+constexpr double kTwoPi = 2.0 * kPi;                 // 2.0*M_PI, exact doubling
+constexpr float kPiF = 3.14159274101257324f;         // (float)M_PI: the smallest float > M_PI
+
+struct DevGrid {
+    const int8_t* cells;   // row-major, pitch bytes per row
+    int width, height, pitch;
+    float origin_x, origin_y, cells_per_meter;
+};
+
+// One valid beam of the current scan (range > min_range), prepared on the host once per scan:
+// ratio = (times[n] - t_begin) / (t_end - t_begin) in double (common/interpolation.hpp:36).
+struct __align__(16) Beam {
+    float range;
+    float theta;
+    double ratio;
+};
+
+// common/angle_functions.hpp:12-24.  For a float a: (double)a > M_PI  <=>  a >= (float)M_PI, because (float)M_PI is the
+// first float above M_PI; likewise on the negative side.  The 2*pi step is a double add rounded back to float.
+__device__ __forceinline__ float wrap_to_pi(float a)
+{
+    if (a <= -kPiF) {
+        do { a = (float)__dadd_rn((double)a, kTwoPi); } while (a <= -kPiF);
+    } else if (a >= kPiF) {
+        do { a = (float)__dadd_rn((double)a, -kTwoPi); } while (a >= kPiF);
+    }
+    return a;
+}
+
+// common/angle_functions.hpp:78-87 / :128-138 share this fold.
+__device__ __forceinline__ double fold_pi(double v)
+{
+    if (fabs(v) > kPi) v = __dadd_rn(v, (v > 0) ? -kTwoPi : kTwoPi);
+    return v;
+}
+
+// float -> int the way the x86-64 host does it (cvttss2si): truncate; out of range or NaN -> INT_MIN.
+__device__ __forceinline__ int f2i_x86(float v)
+{
+    return (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+}
+
+__device__ __forceinline__ int grid_read(const DevGrid& g, int x, int y)
+{
+    if ((unsigned)x < (unsigned)g.width && (unsigned)y < (unsigned)g.height)
+        return (int)__ldg(g.cells + (size_t)y * g.pitch + x);
+    return 0;   // occupancy_grid.cpp:65-70: outside the grid reads as 0
+}
+
+// slam/sensor_model.cpp:61-86: the cell one Bresenham step from (x1,y1) toward (x2,y2).  Wrapping differences and
+// 64-bit compares make INT_MIN inputs well defined and equal to the oracle's double compare.
+__device__ __forceinline__ void bresenham_step(int x1, int y1, int x2, int y2, int& xo, int& yo)
+{
+    int dx = (int)((unsigned)x2 - (unsigned)x1);
+    int dy = (int)((unsigned)y2 - (unsigned)y1);
+    dx = dx < 0 ? (int)(0u - (unsigned)dx) : dx;
+    dy = dy < 0 ? (int)(0u - (unsigned)dy) : dy;
+    const int sx = x1 < x2 ? 1 : -1;
+    const int sy = y1 < y2 ? 1 : -1;
+    const long long e2 = 2ll * (long long)(int)((unsigned)dx - (unsigned)dy);
+    xo = (e2 >= -(long long)dy) ? (int)((unsigned)x1 + (unsigned)sx) : x1;
+    yo = (e2 <= (long long)dx) ? (int)((unsigned)y1 + (unsigned)sy) : y1;
+}
+
+// Per-particle constants of the ray construction (common/interpolation.hpp:24-50).
+struct RayBase {
+    float xa, ya, tha;          // pose (scan end)
+    double xb, yb, thb;         // parent pose widened
+    double dx, dy, dth;         // (float)(xa-xb) widened; angle_diff(tha, thb)
+};
+
+__device__ __forceinline__ RayBase make_ray_base(float xa, float ya, float tha, float xb, float yb, float thb)
+{
+    RayBase r;
+    r.xa = xa; r.ya = ya; r.tha = tha;
+    r.xb = (double)xb; r.yb = (double)yb; r.thb = (double)thb;
+    r.dx = (double)__fsub_rn(xa, xb);                       // float subtraction, then widened (interpolation.hpp:39)
+    r.dy = (double)__fsub_rn(ya, yb);
+    r.dth = fold_pi(__dsub_rn((double)tha, (double)thb));   // angle_diff in double (:41)
+    return r;
+}
+
+// One particle-beam evaluation: moving_laser_scan.cpp:26-33 + sensor_model.cpp:28-59.  Returns the ray score in
+// HALF units (2*odds, or o1, or o2): exact integers.  READ(x, y) reads the map.
+template <bool INTERP, class Reader>
+__device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, float gx, float gy, float cpm,
+                                          const Reader& READ, int& gathers)
+{
+    float ox, oy, thr;
+    if (INTERP) {
+        ox = (float)__dadd_rn(p.xb, __dmul_rn(p.dx, b.ratio));                 // interpolation.hpp:45
+        oy = (float)__dadd_rn(p.yb, __dmul_rn(p.dy, b.ratio));                 // :46
+        thr = (float)fold_pi(__dadd_rn(p.thb, __dmul_rn(p.dth, b.ratio)));     // :47 angle_sum
+    } else {
+        ox = p.xa; oy = p.ya; thr = p.tha;                                      // :29-34 equal-utime early-out
+    }
+    const float th = wrap_to_pi(__fsub_rn(thr, b.theta));                      // moving_laser_scan.cpp:33
+    // grid_utils.hpp:50-55: double math, stored into Point<float>
+    const float sx = (float)__dmul_rn(__dsub_rn((double)ox, (double)gx), (double)cpm);
+    const float sy = (float)__dmul_rn(__dsub_rn((double)oy, (double)gy), (double)cpm);
+    float s, c;
+    glibc_sincosf(th, &s, &c);
+    const float px = __fmul_rn(__fmul_rn(b.range, c), cpm);                    // (range*cos)*cpm, float
+    const float py = __fmul_rn(__fmul_rn(b.range, s), cpm);
+    const int ex = f2i_x86(__fadd_rn(px, sx));                                 // sensor_model.cpp:34
+    const int ey = f2i_x86(__fadd_rn(py, sy));                                 // :35
+    // :37-38  ((2*range)*cos)*cpm == 2*px exactly (power-of-two scaling commutes with rounding)
+    const int xx = f2i_x86(__fadd_rn(__fmul_rn(2.0f, px), sx));
+    const int xy = f2i_x86(__fadd_rn(__fmul_rn(2.0f, py), sy));
+    const int odds = READ(ex, ey);                                             // :41
+    gathers += 1;
+    if (odds > 0) return 2 * odds;
+    int ax, ay, bx, by;
+    bresenham_step(ex, ey, f2i_x86(sx), f2i_x86(sy), ax, ay);                  // :48 toward the robot
+    bresenham_step(ex, ey, xx, xy, bx, by);                                    // :49 away from the robot
+    const int o1 = READ(ax, ay);
+    const int o2 = READ(bx, by);
+    gathers += 2;
+    return o1 > 0 ? o1 : (o2 > 0 ? o2 : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: counter = (global particle index, update number), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// Four uniform words -> up to four standard normals (Box-Muller, float).
+__device__ __forceinline__ void philox_normals(uint4 w, float& z0, float& z1, float& z2, float& z3)
+{
+    const float k = 2.3283064365386963e-10f;   // 2^-32
+    const float u0 = fmaf((float)w.x, k, 0.5f * k), u1 = (float)w.y * k;
+    const float u2 = fmaf((float)w.z, k, 0.5f * k), u3 = (float)w.w * k;
+    const float r0 = sqrtf(-2.0f * logf(fminf(u0, 0.99999994f)));
+    const float r1 = sqrtf(-2.0f * logf(fminf(u2, 0.99999994f)));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    z0 = r0 * c0; z1 = r0 * s0; z2 = r1 * c1; z3 = r1 * s1;
+}
+
+}  // namespace mcl

@@ -1,0 +1,1027 @@
+// libmcl_cuda.so -- engine object and the C ABI declared in include/mcl_cuda.h.
+// One engine = one GPU = one stream.  All particle state is SoA in HBM and never leaves the device on the fast path;
+// per update the host sends ~6 KB (prepared beams + scalars) and reads back one pose.
+#include "../../include/mcl_cuda.h"
+#include "mcl_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#ifdef MCL_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace mcl;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct PoseSoA {
+    float *x = nullptr, *y = nullptr, *th = nullptr;
+};
+
+}  // namespace
+
+struct mcl_engine {
+    mcl_params params;
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // partition
+    long long n = 0;            // global particle count
+    int rank = 0, world = 1;
+    long long lo = 0, hi = 0;   // slice scored / moved by this rank
+#ifdef MCL_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+
+    // particle state (global-sized arrays; every rank holds the full cloud, only [lo,hi) is computed locally)
+    PoseSoA pose[2], parent[2];
+    int cur = 0;
+    double* weight[2] = {nullptr, nullptr};
+    int wcur = 0;
+    int32_t* score2 = nullptr;
+    int32_t* idx = nullptr;
+    long long pose_utime = 0, parent_utime = 0;
+    bool have_particles = false, have_scores = false;
+
+    // sequential-sum workspace
+    long long n1 = 0, n2 = 0;
+    double *cum = nullptr, *sums = nullptr, *cin1 = nullptr, *cin2 = nullptr, *total = nullptr;
+    int *ebias = nullptr, *gebias = nullptr, *opened = nullptr;
+    long long *q0 = nullptr, *q1 = nullptr, *g0 = nullptr, *g1 = nullptr, *fallbacks = nullptr;
+    unsigned long long* overruns = nullptr;
+    unsigned long long* gather_counter = nullptr;
+    double* ess_acc = nullptr;
+    int* bbox = nullptr;
+
+    // estimate
+    double4* est_partials = nullptr;
+    int est_count = 0;
+    float* est_out = nullptr;          // device float4
+    float* est_host = nullptr;         // pinned float4
+    mcl_pose_t last_estimate{};
+
+    // map mirror
+    int8_t* map = nullptr;
+    DevGrid grid{};
+    float meters_per_cell = 0.05f;
+    bool have_map = false;
+
+    // scan
+    Beam* beams = nullptr;             // device
+    Beam* beams_host = nullptr;        // pinned
+    int beams_cap = 0, num_beams = 0;
+    float max_range = 0.0f;
+    bool scan_interp = false;
+    bool have_scan = false;
+
+    // staging
+    float* noise = nullptr;            // device, 3 floats per particle, allocated on first injection
+    void* staging = nullptr;           // device scratch for AoS / double vectors
+    size_t staging_bytes = 0;
+    int* host_bbox = nullptr;          // pinned 4 ints
+    unsigned long long* host_counters = nullptr;   // pinned: overruns, gathers, fallbacks, (double) total, ess
+
+    // stats
+    mcl_stats stats{};
+    bool count_gathers = false;
+    uint64_t seed = 0x5eedULL;
+    uint32_t update_no = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launches = 0;
+};
+
+namespace {
+
+int fail(mcl_engine* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                                     \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess)                                                                                      \
+            return fail(h, MCL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKL(h)                                                                                                       \
+    do {                                                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                                                        \
+        if (e__ != cudaSuccess)                                                                                      \
+            return fail(h, MCL_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__,      \
+                        __LINE__);                                                                                   \
+        ++(h)->launches;                                                                                             \
+    } while (0)
+
+template <class T>
+int dev_alloc(mcl_engine* h, T** p, size_t count)
+{
+    CK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return MCL_OK;
+}
+
+int grid_for(const mcl_engine* h, long long work, int block, int per_sm = 8)
+{
+    long long want = (work + block - 1) / block;
+    long long cap = (long long)h->sm_count * per_sm;
+    return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+int ensure_staging(mcl_engine* h, size_t bytes)
+{
+    if (bytes <= h->staging_bytes) return MCL_OK;
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    CK(cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return MCL_OK;
+}
+
+// ---- exact sequential running sum of a double vector on the device (S1..S7) --------------------------------------
+int seq_total(mcl_engine* h, const double* w, bool materialize)
+{
+    const long long n = h->n, n1 = h->n1, n2 = h->n2;
+    const int tiles = (int)((n1 + kSeqTileChunks - 1) / kSeqTileChunks);
+    seq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums);
+    CKL(h);
+    seq_scan_classify_kernel<<<1, 1024, 0, h->stream>>>(h->sums, n1, h->ebias);
+    CKL(h);
+    seq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->ebias, h->q0, h->q1);
+    CKL(h);
+    seq_group_maps_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->ebias, h->q0, h->q1, n1, n2, h->gebias,
+                                                                          h->g0, h->g1);
+    CKL(h);
+    seq_walk_kernel<<<1, 32, 0, h->stream>>>(w, n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2,
+                                             h->cin1, h->opened, h->total, h->fallbacks);
+    CKL(h);
+    if (materialize) {
+        seq_group_expand_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->q0, h->q1, n1, n2, h->cin2,
+                                                                            h->opened, h->cin1);
+        CKL(h);
+        seq_materialize_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->cin1, h->cum);
+        CKL(h);
+    }
+    return MCL_OK;
+}
+
+// ---- scan preparation (host): valid-beam compaction + interpolation ratios ------------------
+int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int nb,
+                 long long t_begin, long long t_end)
+{
+    if (nb < 0 || (nb > 0 && (!ranges || !thetas || !times))) return fail(h, MCL_ERR_INVALID, "bad scan arrays");
+    if (nb > h->beams_cap) {
+        if (h->beams) cudaFree(h->beams);
+        if (h->beams_host) cudaFreeHost(h->beams_host);
+        h->beams = nullptr; h->beams_host = nullptr;
+        const int cap = std::max(nb, 1024);
+        CK(cudaMalloc((void**)&h->beams, sizeof(Beam) * cap));
+        CK(cudaMallocHost((void**)&h->beams_host, sizeof(Beam) * cap));
+        h->beams_cap = cap;
+    }
+    // interpolation.hpp:29-36: equal utimes -> every ray from the end pose; else ratio in double, unclamped.
+    const bool interp = t_begin != t_end;
+    const double denom = (double)(t_end - t_begin);
+    int k = 0;
+    float mx = 0.0f;
+    for (int i = 0; i < nb; ++i) {
+        if (ranges[i] > h->params.min_range) {                 // moving_laser_scan.cpp:24
+            Beam b;
+            b.range = ranges[i];
+            b.theta = thetas[i];
+            b.ratio = interp ? (double)(times[i] - t_begin) / denom : 1.0;
+            h->beams_host[k++] = b;
+            if (std::isfinite(ranges[i])) mx = std::max(mx, ranges[i]);
+        }
+    }
+    h->num_beams = k;
+    h->max_range = mx;
+    h->scan_interp = interp;
+    if (k > 0) CK(cudaMemcpyAsync(h->beams, h->beams_host, sizeof(Beam) * k, cudaMemcpyHostToDevice, h->stream));
+    h->have_scan = true;
+    h->stats.valid_beams = k;
+    return MCL_OK;
+}
+
+// ---- sensor-model launch ---------------------------------------------------------------------------------------------
+template <int G, bool INTERP, bool TILE>
+int launch_score_g(mcl_engine* h, const ScoreArgs& a, size_t smem, int blocks)
+{
+    if (h->count_gathers) {
+        auto k = score_kernel<G, INTERP, TILE, true>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, 256, smem, h->stream>>>(a);
+    } else {
+        auto k = score_kernel<G, INTERP, TILE, false>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, 256, smem, h->stream>>>(a);
+    }
+    CKL(h);
+    return MCL_OK;
+}
+
+template <bool INTERP, bool TILE>
+int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, size_t smem, int blocks)
+{
+    switch (G) {
+        case 1: return launch_score_g<1, INTERP, TILE>(h, a, smem, blocks);
+        case 2: return launch_score_g<2, INTERP, TILE>(h, a, smem, blocks);
+        case 4: return launch_score_g<4, INTERP, TILE>(h, a, smem, blocks);
+        case 8: return launch_score_g<8, INTERP, TILE>(h, a, smem, blocks);
+        case 16: return launch_score_g<16, INTERP, TILE>(h, a, smem, blocks);
+        default: return launch_score_g<32, INTERP, TILE>(h, a, smem, blocks);
+    }
+}
+
+int run_score(mcl_engine* h)
+{
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles: call mcl_init_* or mcl_import_particles");
+    if (!h->have_scan) return fail(h, MCL_ERR_STATE, "no scan uploaded");
+    const long long local = h->hi - h->lo;
+    ScoreArgs a{};
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    a.x = p.x; a.y = p.y; a.th = p.th; a.px = q.x; a.py = q.y; a.pth = q.th;
+    a.score2 = h->score2;
+    a.lo = h->lo; a.hi = h->hi;
+    a.beams = h->beams; a.num_beams = h->num_beams;
+    a.grid = h->grid;
+    a.gather_counter = h->gather_counter;
+    if (h->count_gathers) CK(cudaMemsetAsync(h->gather_counter, 0, sizeof(unsigned long long), h->stream));
+
+    // lanes per particle: enough particle groups to fill the machine (148 SMs x 8 CTAs x (256/G) slots)
+    int G = h->params.lanes_per_particle;
+    if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) {
+        G = 32;
+        while (G > 1 && local * G / 2 >= (long long)h->sm_count * 2048 * 2) G >>= 1;
+    }
+
+    // shared-memory map tile: window = bounding box of the cloud (poses and parents) +- (max range + 2 cells)
+    size_t smem = (size_t)h->num_beams * sizeof(Beam);
+    bool tile = false;
+    if (h->params.map_tile != 1 && local > 0 && h->num_beams > 0) {
+        int* box = h->bbox;
+        const int init_box[4] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000};
+        std::memcpy(h->host_bbox, init_box, sizeof(init_box));
+        CK(cudaMemcpyAsync(box, h->host_bbox, sizeof(init_box), cudaMemcpyHostToDevice, h->stream));
+        bbox_kernel<<<grid_for(h, local, 256), 256, 0, h->stream>>>(p.x, p.y, q.x, q.y, h->lo, h->hi, box);
+        CKL(h);
+        CK(cudaMemcpyAsync(h->host_bbox, box, sizeof(init_box), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        auto unorder = [](int i) { int b = i >= 0 ? i : i ^ 0x7fffffff; float f; std::memcpy(&f, &b, 4); return f; };
+        const float mnx = unorder(h->host_bbox[0]), mny = unorder(h->host_bbox[1]);
+        const float mxx = unorder(h->host_bbox[2]), mxy = unorder(h->host_bbox[3]);
+        if (std::isfinite(mnx) && std::isfinite(mny) && std::isfinite(mxx) && std::isfinite(mxy)) {
+            const double cpm = h->grid.cells_per_meter;
+            const double reach = (double)h->max_range * cpm + 3.0;
+            const double cx0 = std::floor(((double)mnx - h->grid.origin_x) * cpm - reach);
+            const double cy0 = std::floor(((double)mny - h->grid.origin_y) * cpm - reach);
+            const double cx1 = std::ceil(((double)mxx - h->grid.origin_x) * cpm + reach);
+            const double cy1 = std::ceil(((double)mxy - h->grid.origin_y) * cpm + reach);
+            // clip to the grid (outside reads are 0 through the global fallback anyway)
+            long long x0 = (long long)std::max(cx0, 0.0), y0 = (long long)std::max(cy0, 0.0);
+            long long x1 = (long long)std::min(cx1, (double)h->grid.width - 1);
+            long long y1 = (long long)std::min(cy1, (double)h->grid.height - 1);
+            if (x1 >= x0 && y1 >= y0) {
+                x0 &= ~3ll;
+                const long long tw = x1 - x0 + 1, th = y1 - y0 + 1;
+                long long pitch = (tw + 3) & ~3ll;
+                if (((pitch >> 2) & 1) == 0) pitch += 4;     // odd number of 4-byte words per row: spreads rows over banks
+                const size_t bytes = (size_t)pitch * th;
+                const size_t budget = (size_t)h->max_smem_optin - smem - 1024;
+                if (bytes <= budget / (h->params.map_tile == 2 ? 1 : 2) || (h->params.map_tile == 2 && bytes <= budget)) {
+                    tile = true;
+                    a.tile_x0 = (int)x0; a.tile_y0 = (int)y0; a.tile_w = (int)tw; a.tile_h = (int)th;
+                    a.tile_pitch = (int)pitch;
+                    smem += bytes;
+                }
+            }
+        }
+        if (h->params.map_tile == 2 && !tile)
+            return fail(h, MCL_ERR_INVALID, "map_tile=2 forced but the cloud's window does not fit in shared memory");
+    }
+
+    // persistent CTAs: a multiple of the SM count, as many as the shared-memory footprint allows per SM
+    int per_sm = tile ? std::max(1, std::min(8, (int)((size_t)(h->max_smem_optin + 1024) / (smem + 1024)))) : 8;
+    const int ppb = 256 / G;
+    long long want = (local + ppb - 1) / ppb;
+    int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * per_sm));
+
+    int rc;
+    if (h->scan_interp)
+        rc = tile ? launch_score_it<true, true>(h, G, a, smem, blocks) : launch_score_it<true, false>(h, G, a, smem, blocks);
+    else
+        rc = tile ? launch_score_it<false, true>(h, G, a, smem, blocks) : launch_score_it<false, false>(h, G, a, smem, blocks);
+    if (rc) return rc;
+    h->stats.lanes_per_particle = G;
+    h->stats.map_tile_used = tile ? 2 : 1;
+    h->stats.evals = local * (long long)h->num_beams;
+    h->have_scores = true;
+    return MCL_OK;
+}
+
+int run_normalize(mcl_engine* h)
+{
+    if (!h->have_scores) return fail(h, MCL_ERR_STATE, "mcl_score has not run");
+    double* w = h->weight[h->wcur];
+    floor_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->params.weight_floor);
+    CKL(h);
+    int rc = seq_total(h, w, false);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->ess_acc, 0, sizeof(double), h->stream));
+    divide_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(w, h->n, h->total, h->ess_acc);
+    CKL(h);
+    return MCL_OK;
+}
+
+int run_estimate(mcl_engine* h)
+{
+    const PoseSoA& p = h->pose[h->cur];
+    estimate_partial_kernel<<<h->est_count, kEstBlock, 0, h->stream>>>(p.x, p.y, p.th, h->weight[h->wcur], h->n,
+                                                                      h->est_partials);
+    CKL(h);
+    estimate_final_kernel<<<1, kEstBlock, 0, h->stream>>>(h->est_partials, h->est_count, h->est_out);
+    CKL(h);
+    return MCL_OK;
+}
+
+int run_action(mcl_engine* h, const mcl_action_t* act, int64_t utime, const float* noise_dev, bool from_index)
+{
+    ActionArgs a{};
+    const PoseSoA& src = h->pose[h->cur];
+    const int dst_i = h->cur ^ 1;
+    a.sx = src.x; a.sy = src.y; a.sth = src.th;
+    a.src_index = from_index ? h->idx : nullptr;
+    a.dx = h->pose[dst_i].x; a.dy = h->pose[dst_i].y; a.dth = h->pose[dst_i].th;
+    a.dpx = h->parent[dst_i].x; a.dpy = h->parent[dst_i].y; a.dpth = h->parent[dst_i].th;
+    a.lo = h->lo; a.hi = h->hi;
+    a.rot1 = act->rot1; a.trans = act->trans; a.rot2 = act->rot2;
+    a.s1 = act->rot1_std; a.st = act->trans_std; a.s2 = act->rot2_std;
+    a.moved = act->moved;
+    a.noise = noise_dev;
+    a.seed = h->seed;
+    a.update_no = h->update_no;
+    action_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(a);
+    CKL(h);
+    h->cur = dst_i;
+    // action_model.cpp:92-93: parent keeps the old pose (and its utime), pose.utime = ActionModel::utime_
+    h->parent_utime = h->pose_utime;
+    h->pose_utime = h->params.legacy_equal_utime ? h->pose_utime : utime;
+    return MCL_OK;
+}
+
+int upload_noise(mcl_engine* h, const float* noise3n, const float** dev_out)
+{
+    *dev_out = nullptr;
+    if (!noise3n) return MCL_OK;
+    if (!h->noise) CK(cudaMalloc((void**)&h->noise, sizeof(float) * 3 * (size_t)h->n));
+    CK(cudaMemcpyAsync(h->noise, noise3n, sizeof(float) * 3 * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    *dev_out = h->noise;
+    return MCL_OK;
+}
+
+int run_resample_indices(mcl_engine* h, double r, const double* w)
+{
+    int rc = seq_total(h, w, true);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
+    resample_search_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->cum, h->n, r, 0, h->n, h->idx,
+                                                                         h->overruns);
+    CKL(h);
+    return MCL_OK;
+}
+
+int read_counters(mcl_engine* h)
+{
+    CK(cudaMemcpyAsync(&h->host_counters[0], h->overruns, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[1], h->gather_counter, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[2], h->fallbacks, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[3], h->total, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[4], h->ess_acc, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.resample_overruns = (int64_t)h->host_counters[0];
+    h->stats.gathers = h->count_gathers ? (int64_t)h->host_counters[1] : -1;
+    h->stats.seq_fallback_chunks = (int64_t)h->host_counters[2];
+    double d;
+    std::memcpy(&d, &h->host_counters[3], 8);
+    h->stats.weight_sum = d;
+    std::memcpy(&d, &h->host_counters[4], 8);
+    h->stats.effective_sample_size = d > 0 ? 1.0 / d : 0.0;
+    return MCL_OK;
+}
+
+int fetch_estimate(mcl_engine* h, int64_t utime)
+{
+    CK(cudaMemcpyAsync(h->est_host, h->est_out, sizeof(float) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_estimate.x = h->est_host[0];
+    h->last_estimate.y = h->est_host[1];
+    h->last_estimate.theta = h->est_host[2];
+    h->last_estimate.utime = utime;
+    return MCL_OK;
+}
+
+// The five stages of ParticleFilter::updateFilter on the engine's stream, no host synchronisation unless the tile
+// heuristic needs the cloud's bounding box.
+int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r, const float* noise_dev)
+{
+    h->launches = 0;
+    cudaEventRecord(h->ev[0], h->stream);
+    int rc = run_resample_indices(h, r, h->weight[h->wcur]);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[1], h->stream);
+    rc = run_action(h, a, utime, noise_dev, true);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[2], h->stream);
+    rc = run_score(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[3], h->stream);
+    rc = run_normalize(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[4], h->stream);
+    rc = run_estimate(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[5], h->stream);
+    h->stats.kernel_launches = h->launches;
+    ++h->update_no;
+    ++h->stats.updates;
+    return MCL_OK;
+}
+
+void free_all(mcl_engine* h)
+{
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    for (int b = 0; b < 2; ++b) {
+        F(h->pose[b].x); F(h->pose[b].y); F(h->pose[b].th);
+        F(h->parent[b].x); F(h->parent[b].y); F(h->parent[b].th);
+        F(h->weight[b]);
+    }
+    F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
+    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter);
+    F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
+    if (h->est_host) cudaFreeHost(h->est_host);
+    if (h->beams_host) cudaFreeHost(h->beams_host);
+    if (h->host_bbox) cudaFreeHost(h->host_bbox);
+    if (h->host_counters) cudaFreeHost(h->host_counters);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+void mcl_default_params(mcl_params* p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->min_range = 0.15f;
+    p->weight_floor = 0.001;
+    p->init_std = 0.01;
+    p->legacy_equal_utime = 0;
+    p->lanes_per_particle = 0;
+    p->map_tile = 0;
+}
+
+const char* mcl_last_error(const mcl_engine* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_engine** out)
+{
+    mcl_engine* h = nullptr;
+    if (!out) return fail(h, MCL_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (num_particles < 2 || num_particles > 0x7fffffffLL)     // particle_filter.cpp:11 asserts > 1; indices are int32
+        return fail(h, MCL_ERR_INVALID, "num_particles must be in [2, 2^31)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(h, MCL_ERR_NO_DEVICE, "no CUDA device %d (found %d): this engine has no CPU fallback", device, count);
+    }
+    h = new (std::nothrow) mcl_engine();
+    if (!h) return fail(nullptr, MCL_ERR_INVALID, "out of host memory");
+    if (params) h->params = *params; else mcl_default_params(&h->params);
+    h->device = device;
+    h->n = num_particles;
+    h->lo = 0; h->hi = num_particles;
+    auto bail = [&](int rc) { g_last_error = h->err; free_all(h); delete h; return rc; };
+#define CKB(call)                                                                                                    \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess) {                                                                                    \
+            fail(h, MCL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));                                  \
+            return bail(MCL_ERR_CUDA);                                                                               \
+        }                                                                                                            \
+    } while (0)
+    CKB(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKB(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        fail(h, MCL_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+             prop.minor);
+        return bail(MCL_ERR_NO_DEVICE);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CKB(cudaEventCreate(&e));
+    const size_t n = (size_t)h->n;
+    h->n1 = (h->n + kL1 - 1) / kL1;
+    h->n2 = (h->n1 + kL2 - 1) / kL2;
+    for (int b = 0; b < 2; ++b) {
+        CKB(cudaMalloc((void**)&h->pose[b].x, 4 * n)); CKB(cudaMalloc((void**)&h->pose[b].y, 4 * n));
+        CKB(cudaMalloc((void**)&h->pose[b].th, 4 * n));
+        CKB(cudaMalloc((void**)&h->parent[b].x, 4 * n)); CKB(cudaMalloc((void**)&h->parent[b].y, 4 * n));
+        CKB(cudaMalloc((void**)&h->parent[b].th, 4 * n));
+        CKB(cudaMalloc((void**)&h->weight[b], 8 * n));
+    }
+    CKB(cudaMalloc((void**)&h->score2, 4 * n));
+    CKB(cudaMalloc((void**)&h->idx, 4 * n));
+    CKB(cudaMalloc((void**)&h->cum, 8 * n));
+    const size_t n1 = (size_t)h->n1, n2 = (size_t)h->n2;
+    CKB(cudaMalloc((void**)&h->sums, 8 * n1)); CKB(cudaMalloc((void**)&h->cin1, 8 * n1));
+    CKB(cudaMalloc((void**)&h->ebias, 4 * n1)); CKB(cudaMalloc((void**)&h->q0, 8 * n1));
+    CKB(cudaMalloc((void**)&h->q1, 8 * n1));
+    CKB(cudaMalloc((void**)&h->cin2, 8 * n2)); CKB(cudaMalloc((void**)&h->gebias, 4 * n2));
+    CKB(cudaMalloc((void**)&h->opened, 4 * n2)); CKB(cudaMalloc((void**)&h->g0, 8 * n2));
+    CKB(cudaMalloc((void**)&h->g1, 8 * n2));
+    CKB(cudaMalloc((void**)&h->total, 8)); CKB(cudaMalloc((void**)&h->fallbacks, 8));
+    CKB(cudaMalloc((void**)&h->overruns, 8)); CKB(cudaMalloc((void**)&h->gather_counter, 8));
+    CKB(cudaMalloc((void**)&h->ess_acc, 8)); CKB(cudaMalloc((void**)&h->bbox, 16));
+    CKB(cudaMemset(h->total, 0, 8)); CKB(cudaMemset(h->fallbacks, 0, 8)); CKB(cudaMemset(h->overruns, 0, 8));
+    CKB(cudaMemset(h->gather_counter, 0, 8)); CKB(cudaMemset(h->ess_acc, 0, 8));
+    h->est_count = (int)((h->n + kEstChunk - 1) / kEstChunk);
+    CKB(cudaMalloc((void**)&h->est_partials, sizeof(double4) * (size_t)h->est_count));
+    CKB(cudaMalloc((void**)&h->est_out, 16));
+    CKB(cudaMallocHost((void**)&h->est_host, 16));
+    CKB(cudaMallocHost((void**)&h->host_bbox, 16));
+    CKB(cudaMallocHost((void**)&h->host_counters, 64));
+#undef CKB
+    h->stats.num_particles = h->n;
+    h->stats.local_particles = h->n;
+    h->stats.gathers = -1;
+    *out = h;
+    return MCL_OK;
+}
+
+void mcl_destroy(mcl_engine* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+#ifdef MCL_WITH_NCCL
+    if (h->comm) ncclCommDestroy(h->comm);
+#endif
+    free_all(h);
+    delete h;
+}
+
+void* mcl_stream(mcl_engine* h) { return h ? (void*)h->stream : nullptr; }
+
+int mcl_sync(mcl_engine* h)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+int mcl_comm_unique_id(void* id128_out)
+{
+    mcl_engine* h = nullptr;
+#ifdef MCL_WITH_NCCL
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return fail(h, MCL_ERR_COMM, "ncclGetUniqueId failed");
+    std::memcpy(id128_out, &id, 128);
+    return MCL_OK;
+#else
+    (void)id128_out;
+    return fail(h, MCL_ERR_COMM, "library built without NCCL");
+#endif
+}
+
+int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
+{
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(h, MCL_ERR_INVALID, "bad comm arguments");
+#ifdef MCL_WITH_NCCL
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    if (ncclCommInitRank(&h->comm, world, id, rank) != ncclSuccess) return fail(h, MCL_ERR_COMM, "ncclCommInitRank failed");
+    h->rank = rank; h->world = world;
+    h->lo = h->n * rank / world;
+    h->hi = h->n * (rank + 1) / world;
+    h->stats.local_particles = h->hi - h->lo;
+    return MCL_OK;
+#else
+    return fail(h, MCL_ERR_COMM, "library built without NCCL");
+#endif
+}
+
+// ---- map -----------------------------------------------------------------------------------------------------------
+int mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float ox, float oy, float mpc, float cpm)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!cells || width <= 0 || height <= 0) return fail(h, MCL_ERR_INVALID, "bad map");
+    CK(cudaSetDevice(h->device));
+    const int pitch = (width + 15) & ~15;     // 16-byte rows: aligned word loads for the tile stager (and TMA-ready)
+    if (!h->map || h->grid.pitch != pitch || h->grid.height != height) {
+        if (h->map) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->map); h->map = nullptr; }
+        CK(cudaMalloc((void**)&h->map, (size_t)pitch * height + 16));
+    }
+    CK(cudaMemsetAsync(h->map, 0, (size_t)pitch * height + 16, h->stream));
+    CK(cudaMemcpy2DAsync(h->map, pitch, cells, width, width, height, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));     // cells is pageable caller memory: finish before returning
+    h->grid.cells = h->map; h->grid.width = width; h->grid.height = height; h->grid.pitch = pitch;
+    h->grid.origin_x = ox; h->grid.origin_y = oy; h->grid.cells_per_meter = cpm;
+    h->meters_per_cell = mpc;
+    h->have_map = true;
+    return MCL_OK;
+}
+
+int mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const int8_t* src, int src_stride)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    if (!src || w <= 0 || hgt <= 0 || x0 < 0 || y0 < 0 || x0 + w > h->grid.width || y0 + hgt > h->grid.height ||
+        src_stride < w)
+        return fail(h, MCL_ERR_INVALID, "bad map rectangle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2DAsync(h->map + (size_t)y0 * h->grid.pitch + x0, h->grid.pitch, src, src_stride, w, hgt,
+                         cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+// ---- particles -----------------------------------------------------------------------------------------------------
+int mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime, uint64_t seed)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(h->device));
+    h->seed = seed;
+    h->update_no = 0;
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    init_at_pose_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(p.x, p.y, p.th, q.x, q.y, q.th, h->n, x, y,
+                                                                      theta, h->params.init_std, seed);
+    CKL(h);
+    fill_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->weight[h->wcur], h->n, 1.0 / (double)h->n);
+    CKL(h);
+    h->pose_utime = h->parent_utime = utime;     // particle_filter.cpp:29-30
+    h->have_particles = true;
+    h->have_scores = false;
+    h->last_estimate.x = x; h->last_estimate.y = y; h->last_estimate.theta = theta; h->last_estimate.utime = utime;
+    return MCL_OK;
+}
+
+int mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map must precede mcl_init_uniform");
+    CK(cudaSetDevice(h->device));
+    h->seed = seed;
+    h->update_no = 0;
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    init_uniform_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(
+        p.x, p.y, p.th, q.x, q.y, q.th, h->n, h->grid.origin_x, h->grid.origin_y,
+        h->grid.width * h->meters_per_cell, h->grid.height * h->meters_per_cell, seed);
+    CKL(h);
+    fill_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->weight[h->wcur], h->n, 1.0 / (double)h->n);
+    CKL(h);
+    h->pose_utime = h->parent_utime = utime;
+    h->have_particles = true;
+    h->have_scores = false;
+    return MCL_OK;
+}
+
+int mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!aos || n != h->n) return fail(h, MCL_ERR_INVALID, "import needs exactly num_particles particles");
+    for (int64_t i = 1; i < n; ++i)
+        if (aos[i].pose.utime != aos[0].pose.utime || aos[i].parent_pose.utime != aos[0].parent_pose.utime)
+            return fail(h, MCL_ERR_INVALID, "particles must share one pose.utime and one parent_pose.utime (particle %lld differs)",
+                        (long long)i);
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_staging(h, sizeof(mcl_particle_t) * (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->staging, aos, sizeof(mcl_particle_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    aos_to_soa_kernel<<<grid_for(h, n, 256), 256, 0, h->stream>>>((const AosParticle*)h->staging, n, p.x, p.y, p.th,
+                                                                 q.x, q.y, q.th, h->weight[h->wcur]);
+    CKL(h);
+    CK(cudaStreamSynchronize(h->stream));
+    h->pose_utime = aos[0].pose.utime;
+    h->parent_utime = aos[0].parent_pose.utime;
+    h->have_particles = true;
+    h->have_scores = false;
+    return MCL_OK;
+}
+
+int mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int64_t stride, int64_t* n_out)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!aos || max_n < 0 || stride < 1) return fail(h, MCL_ERR_INVALID, "bad export arguments");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    CK(cudaSetDevice(h->device));
+    const long long count = std::min<long long>(max_n, (h->n + stride - 1) / stride);
+    if (count > 0) {
+        int rc = ensure_staging(h, sizeof(mcl_particle_t) * (size_t)count);
+        if (rc) return rc;
+        const PoseSoA& p = h->pose[h->cur];
+        const PoseSoA& q = h->parent[h->cur];
+        soa_to_aos_kernel<<<grid_for(h, count, 256), 256, 0, h->stream>>>((AosParticle*)h->staging, count, stride,
+                                                                         h->pose_utime, h->parent_utime, p.x, p.y,
+                                                                         p.th, q.x, q.y, q.th, h->weight[h->wcur]);
+        CKL(h);
+        CK(cudaMemcpyAsync(aos, h->staging, sizeof(mcl_particle_t) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (n_out) *n_out = count;
+    return MCL_OK;
+}
+
+// ---- host scalar action model (action_model.cpp:22-75) ---------------------------------------------------------------
+void mcl_action_reset(mcl_action_t* a) { std::memset(a, 0, sizeof(*a)); }
+
+static double angle_diff_host(double l, double r)
+{
+    double d = l - r;
+    if (std::fabs(d) > M_PI) d -= (d > 0) ? M_PI * 2 : M_PI * -2;
+    return d;
+}
+
+int mcl_action_update(mcl_action_t* a, const mcl_pose_t* odom)
+{
+    if (!a->initialized) { a->previous_odometry = *odom; a->initialized = 1; }
+    const mcl_pose_t& prev = a->previous_odometry;
+    const float dx = odom->x - prev.x;                                   // float deltas (:29-30)
+    const float dy = odom->y - prev.y;
+    const float dth = (float)angle_diff_host((double)odom->theta, (double)prev.theta);
+    float dir = 1.0f;
+    a->rot1 = angle_diff_host((double)atan2f(dy, dx), (double)prev.theta);   // float atan2 (:34)
+    a->trans = (double)sqrtf(dx * dx + dy * dy);                         // float sqrt (:35)
+    if (std::fabs(a->trans) < 0.0001) {
+        a->rot1 = 0.0;
+    } else if (std::fabs(a->rot1) > M_PI / 2.0) {                        // backward motion (:40-43)
+        a->rot1 = -angle_diff_host(M_PI, a->rot1);
+        dir = -1.0f;
+    }
+    a->trans *= (double)dir;
+    a->rot2 = angle_diff_host((double)dth, a->rot1);
+    a->moved = ((std::fabs(a->trans) + std::fabs(a->rot2)) < (double)0.00001f) ? 0 : 1;   // (:52)
+    a->rot1_std = 0.05; a->trans_std = 0.005; a->rot2_std = 0.05;        // (:64-66)
+    a->previous_odometry = *odom;
+    return a->moved;
+}
+
+// ---- stages ----------------------------------------------------------------------------------------------------------
+int mcl_resample(mcl_engine* h, double r, const double* weights, int32_t* indices_out)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    if (h->world > 1) return fail(h, MCL_ERR_STATE, "stand-alone stages run on single-GPU engines; use mcl_update");
+    CK(cudaSetDevice(h->device));
+    h->launches = 0;
+    double* w = h->weight[h->wcur];
+    if (weights) CK(cudaMemcpyAsync(w, weights, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_resample_indices(h, r, w);
+    if (rc) return rc;
+    GatherArgs g{};
+    const int s = h->cur, d = h->cur ^ 1;
+    g.sx = h->pose[s].x; g.sy = h->pose[s].y; g.sth = h->pose[s].th;
+    g.spx = h->parent[s].x; g.spy = h->parent[s].y; g.spth = h->parent[s].th;
+    g.sw = w;
+    g.dx = h->pose[d].x; g.dy = h->pose[d].y; g.dth = h->pose[d].th;
+    g.dpx = h->parent[d].x; g.dpy = h->parent[d].y; g.dpth = h->parent[d].th;
+    g.dw = h->weight[h->wcur ^ 1];
+    g.idx = h->idx; g.n = h->n;
+    gather_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(g);
+    CKL(h);
+    h->cur = d;
+    h->wcur ^= 1;
+    if (indices_out)
+        CK(cudaMemcpyAsync(indices_out, h->idx, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    return read_counters(h);
+}
+
+int mcl_apply_action(mcl_engine* h, const mcl_action_t* a, int64_t utime, const float* noise3n)
+{
+    if (!h || !a) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    CK(cudaSetDevice(h->device));
+    const float* nd;
+    int rc = upload_noise(h, noise3n, &nd);
+    if (rc) return rc;
+    rc = run_action(h, a, utime, nd, false);
+    if (rc) return rc;
+    ++h->update_no;
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+int mcl_upload_scan(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int nb,
+                    int64_t odometry_utime)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));   // the pinned staging buffer may still be in flight
+    // utimes the next action step will assign: parent <- current pose.utime, pose <- odometry utime
+    const long long t_end = h->params.legacy_equal_utime ? h->pose_utime : odometry_utime;
+    return prepare_scan(h, ranges, thetas, times, nb, h->pose_utime, t_end);
+}
+
+int mcl_score(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int nb, double* scores_out)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (h->world > 1) return fail(h, MCL_ERR_STATE, "stand-alone stages run on single-GPU engines; use mcl_update");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = prepare_scan(h, ranges, thetas, times, nb, h->parent_utime, h->pose_utime);
+    if (rc) return rc;
+    h->launches = 0;
+    rc = run_score(h);
+    if (rc) return rc;
+    if (scores_out) {
+        rc = ensure_staging(h, sizeof(double) * (size_t)h->n);
+        if (rc) return rc;
+        score_to_double_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, (double*)h->staging, h->n);
+        CKL(h);
+        CK(cudaMemcpyAsync(scores_out, h->staging, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return read_counters(h);
+}
+
+int mcl_normalize(mcl_engine* h, double* weights_out)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(h->device));
+    h->launches = 0;
+    int rc = run_normalize(h);
+    if (rc) return rc;
+    if (weights_out)
+        CK(cudaMemcpyAsync(weights_out, h->weight[h->wcur], sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost,
+                           h->stream));
+    return read_counters(h);
+}
+
+int mcl_estimate(mcl_engine* h, mcl_pose_t* pose_out)
+{
+    if (!h || !pose_out) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    CK(cudaSetDevice(h->device));
+    int rc = run_estimate(h);
+    if (rc) return rc;
+    rc = fetch_estimate(h, h->pose_utime);
+    if (rc) return rc;
+    *pose_out = h->last_estimate;
+    return MCL_OK;
+}
+
+// ---- fused -----------------------------------------------------------------------------------------------------------
+int mcl_update(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, const float* ranges, const float* thetas,
+               const int64_t* times, int nb, double r, const float* noise3n, mcl_pose_t* pose_out)
+{
+    if (!h || !a || !pose_out) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    CK(cudaSetDevice(h->device));
+    if (a->moved) {                                             // particle_filter.cpp:43
+        const float* nd;
+        int rc = upload_noise(h, noise3n, &nd);
+        if (rc) return rc;
+        // the scan's interpolation ratios depend on the utimes the action step is about to assign
+        const long long t_end = h->params.legacy_equal_utime ? h->pose_utime : odometry_utime;
+        CK(cudaStreamSynchronize(h->stream));
+        rc = prepare_scan(h, ranges, thetas, times, nb, h->pose_utime, t_end);
+        if (rc) return rc;
+        rc = enqueue_update(h, a, odometry_utime, r, nd);
+        if (rc) return rc;
+        rc = fetch_estimate(h, odometry_utime);
+        if (rc) return rc;
+        rc = read_counters(h);
+        if (rc) return rc;
+        float ms = 0;
+        float* slots[5] = {&h->stats.ms_resample, &h->stats.ms_action, &h->stats.ms_score, &h->stats.ms_normalize,
+                           &h->stats.ms_estimate};
+        for (int i = 0; i < 5; ++i) { cudaEventElapsedTime(slots[i], h->ev[i], h->ev[i + 1]); }
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]);
+        h->stats.ms_total = ms;
+    }
+    h->last_estimate.utime = odometry_utime;                    // particle_filter.cpp:50
+    *pose_out = h->last_estimate;
+    return MCL_OK;
+}
+
+int mcl_update_action_only(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, const float* noise3n)
+{
+    if (!h || !a) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    if (!a->moved) return MCL_OK;                               // particle_filter.cpp:57
+    return mcl_apply_action(h, a, odometry_utime, noise3n);
+}
+
+int mcl_update_enqueue(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, double r)
+{
+    if (!h || !a) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_particles || !h->have_map || !h->have_scan) return fail(h, MCL_ERR_STATE, "engine not ready");
+    if (!a->moved) return MCL_OK;
+    CK(cudaSetDevice(h->device));
+    if (r < 0.0) {
+        // host-side Philox-free draw is fine here: r only needs to be uniform in [0, 1/N)
+        uint64_t s = h->seed ^ (0x9E3779B97F4A7C15ull * (h->update_no + 1));
+        s ^= s >> 33; s *= 0xff51afd7ed558ccdULL; s ^= s >> 33;
+        r = ((double)(s >> 11) * (1.0 / 9007199254740992.0)) / (double)h->n;
+    }
+    return enqueue_update(h, a, odometry_utime, r, nullptr);
+}
+
+int mcl_read_estimate(mcl_engine* h, mcl_pose_t* pose_out)
+{
+    if (!h || !pose_out) return fail(h, MCL_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_estimate(h, h->pose_utime);
+    if (rc) return rc;
+    *pose_out = h->last_estimate;
+    return MCL_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------------------
+int mcl_get_stats(mcl_engine* h, mcl_stats* out)
+{
+    if (!h || !out) return fail(h, MCL_ERR_INVALID, "null argument");
+    *out = h->stats;
+    return MCL_OK;
+}
+
+int mcl_set_gather_counting(mcl_engine* h, int on)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    h->count_gathers = on != 0;
+    return MCL_OK;
+}
+
+int mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t reads, double* sectors_per_s_out)
+{
+    if (!h || !sectors_per_s_out || footprint_bytes < 1024 || reads < 1) return fail(h, MCL_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    unsigned long long pow2 = 1024;
+    while ((long long)(pow2 << 1) <= footprint_bytes) pow2 <<= 1;
+    int8_t* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, pow2));
+    CK(cudaMemsetAsync(buf, 1, pow2, h->stream));
+    const int blocks = h->sm_count * 8, threads = 256;
+    const long long per_thread = std::max<long long>(1, reads / ((long long)blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    gather_peak_kernel<<<blocks, threads, 0, h->stream>>>(buf, pow2 - 1, per_thread / 4 + 1, h->overruns);   // warm-up
+    CK(cudaEventRecord(e0, h->stream));
+    gather_peak_kernel<<<blocks, threads, 0, h->stream>>>(buf, pow2 - 1, per_thread, h->overruns);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    *sectors_per_s_out = (double)per_thread * blocks * threads / ((double)ms * 1e-3);
+    return MCL_OK;
+}
+
+int mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* s, float* c)
+{
+    if (!h || !x || !s || !c || n < 1) return fail(h, MCL_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_staging(h, sizeof(float) * 3 * (size_t)n);
+    if (rc) return rc;
+    float* dx = (float*)h->staging;
+    CK(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    debug_sincosf_kernel<<<grid_for(h, n, 256), 256, 0, h->stream>>>(dx, n, dx + n, dx + 2 * n);
+    CKL(h);
+    CK(cudaMemcpyAsync(s, dx + n, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c, dx + 2 * n, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,652 @@
+// Kernels of the MCL update for sm_100a.  See DESIGN.md for the data layout and the per-kernel rooflines.
+#pragma once
+#include "mcl_device.cuh"
+
+namespace mcl {
+
+// =================================================================================================================
+// K3  sensor model.  G lanes share one particle (G = 32 is "a warp per particle, a lane per beam"; smaller G keeps
+// more particles in flight per warp).  Beams are staged in shared memory once per CTA; the particle's ray base lives in
+// registers; each lane scores beams g, g+G, ... and the per-particle half-unit score is reduced with warp shuffles.
+// TILE: the map window [tile_x0, tile_x0+tile_w) x [tile_y0, tile_y0+tile_h) is staged in shared memory (zero-filled
+// outside the grid, which is exactly OccupancyGrid::logOdds' out-of-grid value); reads outside the window fall back to
+// the global mirror, so the result never depends on the window choice.
+// =================================================================================================================
+struct ScoreArgs {
+    const float *x, *y, *th;        // pose (SoA)
+    const float *px, *py, *pth;     // parent pose
+    int32_t* score2;                // out: per-particle score in half units
+    long long lo, hi;               // particle slice scored by this launch
+    const Beam* beams;
+    int num_beams;
+    DevGrid grid;
+    int tile_x0, tile_y0, tile_w, tile_h, tile_pitch;   // TILE only
+    unsigned long long* gather_counter;                  // COUNT only
+};
+
+struct GlobalReader {
+    const DevGrid& g;
+    __device__ __forceinline__ int operator()(int x, int y) const { return grid_read(g, x, y); }
+};
+
+struct TileReader {
+    const DevGrid& g;
+    const int8_t* tile;
+    int x0, y0, w, h, pitch;
+    __device__ __forceinline__ int operator()(int x, int y) const
+    {
+        const unsigned tx = (unsigned)(x - x0), ty = (unsigned)(y - y0);
+        if (tx < (unsigned)w && ty < (unsigned)h) return (int)tile[ty * pitch + tx];
+        return grid_read(g, x, y);
+    }
+};
+
+template <int G, bool INTERP, bool TILE, bool COUNT>
+__global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    Beam* sbeams = reinterpret_cast<Beam*>(smem);
+    int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(Beam));
+
+    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
+    if (TILE) {
+        // 4-byte granules; tile_pitch and tile_x0 are multiples of 4, the mirror's pitch is a multiple of 16.
+        const int words_per_row = a.tile_pitch >> 2;
+        const int total = words_per_row * a.tile_h;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int ty = i / words_per_row, tw = i - ty * words_per_row;
+            const int gx = a.tile_x0 + (tw << 2), gy = a.tile_y0 + ty;
+            uint32_t v = 0;
+            if ((unsigned)gy < (unsigned)a.grid.height && gx >= 0 && gx < a.grid.pitch)
+                v = __ldg(reinterpret_cast<const uint32_t*>(a.grid.cells + (size_t)gy * a.grid.pitch + gx));
+            reinterpret_cast<uint32_t*>(stile)[i] = v;   // mirror rows are zero-padded to the pitch
+        }
+    }
+    __syncthreads();
+
+    const GlobalReader gread{a.grid};
+    const TileReader tread{a.grid, stile, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch};
+    const float gx = a.grid.origin_x, gy = a.grid.origin_y, cpm = a.grid.cells_per_meter;
+
+    constexpr int PPB = 256 / G;                 // particles per CTA per iteration
+    const int sub = threadIdx.x % G;
+    const int slot = threadIdx.x / G;
+    int gathers = 0;
+    for (long long base = a.lo + (long long)blockIdx.x * PPB; base < a.hi; base += (long long)gridDim.x * PPB) {
+        const long long p = base + slot;
+        int acc = 0;
+        if (p < a.hi) {
+            const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
+#pragma unroll 2
+            for (int j = sub; j < a.num_beams; j += G) {
+                const Beam b = sbeams[j];
+                acc += TILE ? score_beam<INTERP>(rb, b, gx, gy, cpm, tread, gathers)
+                            : score_beam<INTERP>(rb, b, gx, gy, cpm, gread, gathers);
+            }
+        }
+#pragma unroll
+        for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (sub == 0 && p < a.hi) a.score2[p] = acc;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gathers += __shfl_xor_sync(0xffffffffu, gathers, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.gather_counter, (unsigned long long)gathers);
+    }
+}
+
+// =================================================================================================================
+// K2  action model (action_model.cpp:78-103), optionally fused with the resampling gather (particle_filter.cpp:100):
+// child m reads its parent's pose through src_index (or m itself), writes parent_pose = that pose and the moved pose.
+// =================================================================================================================
+struct ActionArgs {
+    const float *sx, *sy, *sth;        // source pose arrays (global)
+    const int32_t* src_index;          // null = identity
+    float *dx, *dy, *dth;              // destination pose
+    float *dpx, *dpy, *dpth;           // destination parent pose
+    long long lo, hi;
+    double rot1, trans, rot2, s1, st, s2;
+    int moved;
+    const float* noise;                // 3 floats per particle (global index) or null
+    uint64_t seed;
+    uint32_t update_no;
+};
+
+__global__ void __launch_bounds__(256) action_kernel(const ActionArgs a)
+{
+    for (long long m = a.lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.hi;
+         m += (long long)gridDim.x * blockDim.x) {
+        const long long src = a.src_index ? (long long)a.src_index[m] : m;
+        const float x = a.sx[src], y = a.sy[src], th = a.sth[src];
+        float nx = x, ny = y, nth = th;
+        if (a.moved) {
+            float r1, tr, r2;
+            if (a.noise) {
+                r1 = a.noise[3 * m + 0]; tr = a.noise[3 * m + 1]; r2 = a.noise[3 * m + 2];
+            } else {
+                const uint4 w = philox4x32_10(make_uint4((uint32_t)m, (uint32_t)((unsigned long long)m >> 32),
+                                                         a.update_no, 0x4d434cu),
+                                              make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                float z0, z1, z2, z3;
+                philox_normals(w, z0, z1, z2, z3);
+                r1 = (float)__dadd_rn(__dmul_rn((double)z0, a.s1), a.rot1);   // (float)(z*sigma + mu), double affine
+                tr = (float)__dadd_rn(__dmul_rn((double)z1, a.st), a.trans);
+                r2 = (float)__dadd_rn(__dmul_rn((double)z2, a.s2), a.rot2);
+            }
+            const float h = __fadd_rn(th, r1);                                  // float sum (:88)
+            double sn, cs;
+            sincos((double)h, &sn, &cs);                                        // unqualified cos/sin -> double
+            nx = (float)__dadd_rn((double)x, __dmul_rn((double)tr, cs));
+            ny = (float)__dadd_rn((double)y, __dmul_rn((double)tr, sn));
+            nth = wrap_to_pi(__fadd_rn(h, r2));                                 // (th + r1) + r2, float (:90)
+        }
+        a.dpx[m] = x; a.dpy[m] = y; a.dpth[m] = th;                             // parent_pose = sample.pose (:93)
+        a.dx[m] = nx; a.dy[m] = ny; a.dth[m] = nth;
+    }
+}
+
+// Whole-particle gather for the stand-alone resample stage (prior[m] = posterior_[i], particle_filter.cpp:100).
+struct GatherArgs {
+    const float *sx, *sy, *sth, *spx, *spy, *spth;
+    const double* sw;
+    float *dx, *dy, *dth, *dpx, *dpy, *dpth;
+    double* dw;
+    const int32_t* idx;
+    long long n;
+};
+__global__ void gather_kernel(const GatherArgs a)
+{
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < a.n; m += (long long)gridDim.x * blockDim.x) {
+        const int i = a.idx[m];
+        a.dx[m] = a.sx[i]; a.dy[m] = a.sy[i]; a.dth[m] = a.sth[i];
+        a.dpx[m] = a.spx[i]; a.dpy[m] = a.spy[i]; a.dpth[m] = a.spth[i];
+        a.dw[m] = a.sw[i];
+    }
+}
+
+// =================================================================================================================
+// K4  weights and estimate.
+// =================================================================================================================
+// particle_filter.cpp:126-133: v = score < floor ? floor : score, from half-unit integer scores.
+__global__ void floor_kernel(const int32_t* score2, double* v, long long n, double floor_w)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double s = 0.5 * (double)score2[i];
+        v[i] = s < floor_w ? floor_w : s;
+    }
+}
+
+// particle_filter.cpp:136-138: w /= wSum (IEEE double division, correctly rounded on both sides).
+__global__ void divide_kernel(double* w, long long n, const double* wsum, double* ess_acc)
+{
+    const double s = *wsum;
+    double sq = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double q = __ddiv_rn(w[i], s);
+        w[i] = q;
+        sq += q * q;
+    }
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0 && ess_acc) atomicAdd(ess_acc, sq);
+}
+
+__global__ void fill_kernel(double* w, long long n, double v)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        w[i] = v;
+}
+
+// particle_filter.cpp:144-160.  Deterministic two-stage reduction of (sum w*x, sum w*y, sum w*sinf, sum w*cosf) in
+// double: fixed chunk -> block mapping, fixed tree, so the estimate does not depend on the GPU count or the run.
+constexpr int kEstBlock = 256;
+constexpr int kEstChunk = 4096;   // particles per partial
+__global__ void __launch_bounds__(kEstBlock) estimate_partial_kernel(const float* x, const float* y, const float* th,
+                                                                     const double* w, long long n, double4* partials)
+{
+    __shared__ double4 red[kEstBlock];
+    const long long base = (long long)blockIdx.x * kEstChunk;
+    double4 acc = make_double4(0, 0, 0, 0);
+    for (int k = threadIdx.x; k < kEstChunk; k += kEstBlock) {
+        const long long i = base + k;
+        if (i < n) {
+            const double wi = w[i];
+            float s, c;
+            glibc_sincosf(th[i], &s, &c);       // std::sin/std::cos(float) -> sincosf in the reference build
+            acc.x = __dadd_rn(acc.x, __dmul_rn(wi, (double)x[i]));
+            acc.y = __dadd_rn(acc.y, __dmul_rn(wi, (double)y[i]));
+            acc.z = __dadd_rn(acc.z, __dmul_rn(wi, (double)s));
+            acc.w = __dadd_rn(acc.w, __dmul_rn(wi, (double)c));
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = kEstBlock / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            double4 o = red[threadIdx.x + off], m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[threadIdx.x] = m;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+// out4 = (x, y, theta, unused) as floats; single block.
+__global__ void __launch_bounds__(kEstBlock) estimate_final_kernel(const double4* partials, int count, float* out4)
+{
+    __shared__ double4 red[kEstBlock];
+    double4 acc = make_double4(0, 0, 0, 0);
+    for (int k = threadIdx.x; k < count; k += kEstBlock) {      // fixed order per thread
+        const double4 p = partials[k];
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = kEstBlock / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            double4 o = red[threadIdx.x + off], m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[threadIdx.x] = m;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out4[0] = (float)red[0].x;
+        out4[1] = (float)red[0].y;
+        out4[2] = (float)atan2(red[0].z, red[0].w);
+        out4[3] = 0.0f;
+    }
+}
+
+// =================================================================================================================
+// K1  resampling.  The reference compares U_m = r + m/N against c, a LEFT-TO-RIGHT double running sum
+// (particle_filter.cpp:93-99).  A parallel double scan rounds differently, so indices would differ.  The kernels below
+// reproduce the sequential rounding EXACTLY, in parallel:
+//   while c stays inside one binade [2^e, 2^(e+1)) every step is c += (w rounded to a multiple of ulp_e, ties by the
+//   parity of c/ulp_e), so over a chunk of elements the map c_in -> c_out is "add D[parity(c_in/ulp)]": two integers.
+//   Such maps compose associatively.  Chunks whose running sum may cross a binade edge are walked serially with real
+//   double adds.  D[0], D[1] themselves are obtained with real double adds from the two representatives 2^e and
+//   2^e + ulp, so hardware rounding does the tie handling.
+// Level 1: kL1 elements per chunk;  level 2: kL2 level-1 chunks per group.  Every assumption (binade of the true
+// running sum at chunk entry, no overflow out of the binade) is verified against exact values during the serial walk;
+// failures take the serial path, so the result never depends on the heuristics.
+// =================================================================================================================
+constexpr int kL1 = 128;
+constexpr int kL2 = 64;
+constexpr int kSeqTileChunks = 32;            // level-1 chunks staged per CTA
+constexpr int kSeqRowPitch = kL1 + 1;         // doubles; odd pitch => conflict-free column walks
+
+__device__ __forceinline__ int dbl_exp(double v) { return (int)((__double_as_longlong(v) >> 52) & 0x7ff); }
+
+// Stage kSeqTileChunks chunks (coalesced) into shared memory, zero padded past n.
+__device__ __forceinline__ void seq_stage(const double* w, long long n, long long first_elem, double* tile)
+{
+    for (int i = threadIdx.x; i < kSeqTileChunks * kL1; i += blockDim.x) {
+        const long long g = first_elem + i;
+        tile[(i / kL1) * kSeqRowPitch + (i % kL1)] = g < n ? w[g] : 0.0;
+    }
+}
+
+// S1: plain per-chunk sums (approximate prefix only steers the binade guess).
+__global__ void __launch_bounds__(128) seq_chunk_sums_kernel(const double* w, long long n, long long n1, double* sums)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    const long long chunk0 = (long long)blockIdx.x * kSeqTileChunks;
+    seq_stage(w, n, chunk0 * kL1, tile);
+    __syncthreads();
+    if (threadIdx.x < kSeqTileChunks && chunk0 + threadIdx.x < n1) {
+        const double* row = tile + threadIdx.x * kSeqRowPitch;
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < kL1; ++i) s += row[i];
+        sums[chunk0 + threadIdx.x] = s;
+    }
+}
+
+// S2: exclusive scan of the chunk sums (single CTA) and the binade guess per chunk:
+// ebias[k] = biased exponent shared by the whole chunk's running sum, or 0 = "walk it serially".
+__global__ void __launch_bounds__(1024) seq_scan_classify_kernel(const double* sums, long long n1, int* ebias)
+{
+    __shared__ double warp_tot[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (long long base = 0; base < n1; base += 1024) {
+        const long long k = base + threadIdx.x;
+        const double v = k < n1 ? sums[k] : 0.0;
+        double inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            double t = warp_tot[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, t, off);
+                if (lane >= off) t += u;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const double carry = carry_s;
+        const double incl = carry + (wid ? warp_tot[wid - 1] : 0.0) + inc;
+        const double excl = incl - v;
+        if (k < n1) {
+            const double lo = excl * (1.0 - 1e-6), hi = incl * (1.0 + 1e-6);
+            const int elo = dbl_exp(lo), ehi = dbl_exp(hi);
+            ebias[k] = (lo > 0.0 && elo == ehi && elo > 60 && elo < 2000) ? elo : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+}
+
+// S3: per level-1 chunk, Q[p] = (c_out - c_in)/ulp for entry parity p, from two real double-add chains started at the
+// binade's two representatives.  A chain that leaves the binade invalidates the chunk (ebias := 0).
+__global__ void __launch_bounds__(128) seq_chunk_maps_kernel(const double* w, long long n, long long n1, int* ebias,
+                                                             long long* q0, long long* q1)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    const long long chunk0 = (long long)blockIdx.x * kSeqTileChunks;
+    seq_stage(w, n, chunk0 * kL1, tile);
+    __syncthreads();
+    const long long k = chunk0 + threadIdx.x;
+    if (threadIdx.x < kSeqTileChunks && k < n1) {
+        const int e = ebias[k];
+        if (e != 0) {
+            const double base0 = __longlong_as_double((long long)e << 52);
+            const double ulp = __longlong_as_double((long long)(e - 52) << 52);
+            const double base1 = base0 + ulp;
+            const double top = base0 + base0;
+            const double* row = tile + threadIdx.x * kSeqRowPitch;
+            double c0 = base0, c1 = base1;
+#pragma unroll 8
+            for (int i = 0; i < kL1; ++i) {
+                const double v = row[i];
+                c0 = __dadd_rn(c0, v);
+                c1 = __dadd_rn(c1, v);
+            }
+            if (c0 < top && c1 < top && c0 >= base0 && c1 >= base1) {
+                // exact: both differences are multiples of ulp below 2^52 ulp
+                q0[k] = __double_as_longlong(c0) - __double_as_longlong(base0);   // same binade: bit patterns count ulps
+                q1[k] = __double_as_longlong(c1) - __double_as_longlong(base1);
+            } else {
+                ebias[k] = 0;
+            }
+        }
+    }
+}
+
+// S4: compose the level-1 maps of each level-2 group (serial over kL2 entries per thread: tiny).
+// gebias = common exponent or 0; (g0, g1) = composed map.
+__global__ void seq_group_maps_kernel(const int* ebias, const long long* q0, const long long* q1, long long n1,
+                                      long long n2, int* gebias, long long* g0, long long* g1)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const long long first = j * kL2;
+    const long long last = first + kL2 < n1 ? first + kL2 : n1;
+    const int e = ebias[first];
+    bool ok = e != 0;
+    long long a0 = 0, a1 = 0;     // running composed map for entry parity 0 / 1
+    for (long long k = first; k < last && ok; ++k) {
+        if (ebias[k] != e) { ok = false; break; }
+        const long long f0 = q0[k], f1 = q1[k];
+        a0 += ((a0 & 1) ? f1 : f0);
+        a1 += (((a1 + 1) & 1) ? f1 : f0);   // entry parity 1: current parity = (1 + a1) & 1
+    }
+    gebias[j] = ok ? e : 0;
+    g0[j] = a0;
+    g1[j] = a1;
+}
+
+// Apply a verified map to an exact running sum: returns false if the entry binade differs or the sum would leave it.
+__device__ __forceinline__ bool seq_apply(double& c, int e, long long m0, long long m1)
+{
+    if (e == 0 || dbl_exp(c) != e) return false;
+    const long long bits = __double_as_longlong(c);
+    const long long add = (bits & 1) ? m1 : m0;
+    const long long nb = bits + add;                // same binade <=> exponent field unchanged
+    if (((nb >> 52) & 0x7ff) != e) return false;
+    c = __longlong_as_double(nb);
+    return true;
+}
+
+// S5: the serial walk (one warp; all lanes compute the same chain so shuffles broadcast staged values).
+// Produces the exact running sum at the entry of every level-2 group (cin2), of every level-1 chunk of groups that
+// had to be opened (cin1, flagged in opened[j]), the exact total, and the number of chunks that took raw adds.
+__global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long n, long long n1, long long n2,
+                                                      const int* ebias, const long long* q0, const long long* q1,
+                                                      const int* gebias, const long long* g0, const long long* g1,
+                                                      double* cin2, double* cin1, int* opened, double* total,
+                                                      long long* fallback_chunks)
+{
+    const int lane = threadIdx.x;
+    double c = 0.0;
+    long long fallbacks = 0;
+    for (long long jb = 0; jb < n2; jb += 32) {
+        const long long jl = jb + lane;
+        const int ge_l = jl < n2 ? gebias[jl] : 0;
+        const long long g0_l = jl < n2 ? g0[jl] : 0, g1_l = jl < n2 ? g1[jl] : 0;
+        const int cnt = (int)(n2 - jb < 32 ? n2 - jb : 32);
+        for (int t = 0; t < cnt; ++t) {
+            const long long j = jb + t;
+            const int ge = __shfl_sync(0xffffffffu, ge_l, t);
+            const long long m0 = __shfl_sync(0xffffffffu, g0_l, t), m1 = __shfl_sync(0xffffffffu, g1_l, t);
+            if (lane == 0) cin2[j] = c;
+            if (seq_apply(c, ge, m0, m1)) {
+                if (lane == 0) opened[j] = 0;
+                continue;
+            }
+            if (lane == 0) opened[j] = 1;
+            const long long kfirst = j * kL2;
+            const long long klast = kfirst + kL2 < n1 ? kfirst + kL2 : n1;
+            for (long long kb = kfirst; kb < klast; kb += 32) {
+                const long long kl = kb + lane;
+                const int e_l = kl < klast ? ebias[kl] : 0;
+                const long long f0_l = kl < klast ? q0[kl] : 0, f1_l = kl < klast ? q1[kl] : 0;
+                const int kc = (int)(klast - kb < 32 ? klast - kb : 32);
+                for (int s = 0; s < kc; ++s) {
+                    const long long k = kb + s;
+                    const int e = __shfl_sync(0xffffffffu, e_l, s);
+                    const long long f0 = __shfl_sync(0xffffffffu, f0_l, s), f1 = __shfl_sync(0xffffffffu, f1_l, s);
+                    if (lane == 0) cin1[k] = c;
+                    if (seq_apply(c, e, f0, f1)) continue;
+                    ++fallbacks;
+                    const long long efirst = k * kL1;
+                    for (int eb = 0; eb < kL1; eb += 32) {
+                        const long long gi = efirst + eb + lane;
+                        const double v_l = gi < n ? w[gi] : 0.0;
+                        for (int u = 0; u < 32; ++u) c = __dadd_rn(c, __shfl_sync(0xffffffffu, v_l, u));
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        *total = c;
+        *fallback_chunks = fallbacks;
+    }
+}
+
+// S6: entry sums of the level-1 chunks inside groups the walk did not open (all in one binade, verified by S5).
+__global__ void seq_group_expand_kernel(const long long* q0, const long long* q1, long long n1, long long n2,
+                                        const double* cin2, const int* opened, double* cin1)
+{
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n2 || opened[j]) return;
+    const long long first = j * kL2;
+    const long long last = first + kL2 < n1 ? first + kL2 : n1;
+    long long bits = __double_as_longlong(cin2[j]);
+    for (long long k = first; k < last; ++k) {
+        cin1[k] = __longlong_as_double(bits);
+        bits += (bits & 1) ? q1[k] : q0[k];
+    }
+}
+
+// S7: materialise the exact running sum c_i for every element: real sequential double adds inside each chunk.
+__global__ void __launch_bounds__(128) seq_materialize_kernel(const double* w, long long n, long long n1,
+                                                              const double* cin1, double* cum)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    const long long chunk0 = (long long)blockIdx.x * kSeqTileChunks;
+    seq_stage(w, n, chunk0 * kL1, tile);
+    __syncthreads();
+    const long long k = chunk0 + threadIdx.x;
+    if (threadIdx.x < kSeqTileChunks && k < n1) {
+        double* row = tile + threadIdx.x * kSeqRowPitch;
+        double c = cin1[k];
+#pragma unroll 8
+        for (int i = 0; i < kL1; ++i) {
+            c = __dadd_rn(c, row[i]);
+            row[i] = c;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSeqTileChunks * kL1; i += blockDim.x) {
+        const long long g = chunk0 * kL1 + i;
+        if (g < n) cum[g] = tile[(i / kL1) * kSeqRowPitch + (i % kL1)];
+    }
+}
+
+// Systematic search: child m takes the first i with !(U_m > c_i), U_m = r + m*(1/N) evaluated exactly like the
+// reference (double product, double sum; particle_filter.cpp:89,95-99).  c is non-decreasing, so the reference's
+// forward-only loop equals a lower-bound search.  Past-the-end (the reference's unbounded loop) clamps to N-1.
+__global__ void resample_search_kernel(const double* cum, long long n, double r, long long lo, long long hi,
+                                       int32_t* idx, unsigned long long* overruns)
+{
+    const double m_inv = __ddiv_rn(1.0, (double)n);
+    for (long long m = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < hi;
+         m += (long long)gridDim.x * blockDim.x) {
+        const double u = __dadd_rn(r, __dmul_rn((double)m, m_inv));
+        long long a = 0, b = n;
+        while (a < b) {
+            const long long mid = (a + b) >> 1;
+            if (u > cum[mid]) a = mid + 1; else b = mid;
+        }
+        if (a >= n) { a = n - 1; atomicAdd(overruns, 1ull); }
+        idx[m] = (int32_t)a;
+    }
+}
+
+// =================================================================================================================
+// Initialisers and utilities.
+// =================================================================================================================
+// particle_filter.cpp:16-34 with Philox normals: x,y,theta ~ pose + N(0, std); last particle = exact pose (:33).
+__global__ void init_at_pose_kernel(float* x, float* y, float* th, float* px, float* py, float* pth, long long n,
+                                    float x0, float y0, float th0, double std, uint64_t seed)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0u, 0x494e4954u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float z0, z1, z2, z3;
+        philox_normals(w, z0, z1, z2, z3);
+        const float xs = (float)__dadd_rn((double)x0, __dmul_rn((double)z0, std));
+        const float ys = (float)__dadd_rn((double)y0, __dmul_rn((double)z1, std));
+        const float ts = wrap_to_pi((float)__dadd_rn((double)th0, __dmul_rn((double)z2, std)));
+        px[i] = xs; py[i] = ys; pth[i] = ts;
+        const bool last = i == n - 1;
+        x[i] = last ? x0 : xs; y[i] = last ? y0 : ys; th[i] = last ? th0 : ts;
+    }
+}
+
+__global__ void init_uniform_kernel(float* x, float* y, float* th, float* px, float* py, float* pth, long long n,
+                                    float gx, float gy, float wm, float hm, uint64_t seed)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0u, 0x554e4946u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float k = 2.3283064365386963e-10f;
+        const float xs = gx + wm * ((float)w.x * k);
+        const float ys = gy + hm * ((float)w.y * k);
+        const float ts = wrap_to_pi((float)(((double)w.z * 2.3283064365386963e-10 - 0.5) * kTwoPi));
+        x[i] = px[i] = xs; y[i] = py[i] = ys; th[i] = pth[i] = ts;
+    }
+}
+
+// AoS particle_t <-> SoA
+struct AosParticle { long long utime; float x, y, th; long long putime; float px, py, pth; double w; };
+static_assert(sizeof(AosParticle) == 56, "particle_t layout");
+
+__global__ void aos_to_soa_kernel(const AosParticle* aos, long long n, float* x, float* y, float* th, float* px,
+                                  float* py, float* pth, double* w)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const AosParticle p = aos[i];
+        x[i] = p.x; y[i] = p.y; th[i] = p.th; px[i] = p.px; py[i] = p.py; pth[i] = p.pth; w[i] = p.w;
+    }
+}
+
+__global__ void soa_to_aos_kernel(AosParticle* aos, long long count, long long stride, long long utime,
+                                  long long putime, const float* x, const float* y, const float* th, const float* px,
+                                  const float* py, const float* pth, const double* w)
+{
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count; k += (long long)gridDim.x * blockDim.x) {
+        const long long i = k * stride;
+        AosParticle p;
+        p.utime = utime; p.x = x[i]; p.y = y[i]; p.th = th[i];
+        p.putime = putime; p.px = px[i]; p.py = py[i]; p.pth = pth[i];
+        p.w = w[i];
+        aos[k] = p;
+    }
+}
+
+__global__ void score_to_double_kernel(const int32_t* score2, double* out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = 0.5 * (double)score2[i];
+}
+
+// Bounding box of the poses in [lo, hi) as ordered-int atomics: box = (minx, miny, maxx, maxy) of float bit patterns
+// mapped to a monotone integer order.
+__device__ __forceinline__ int float_order(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__global__ void bbox_kernel(const float* x, const float* y, const float* px, const float* py, long long lo,
+                            long long hi, int* box)
+{
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int a = float_order(x[i]), b = float_order(y[i]), c = float_order(px[i]), d = float_order(py[i]);
+        mnx = min(mnx, min(a, c)); mxx = max(mxx, max(a, c));
+        mny = min(mny, min(b, d)); mxy = max(mxy, max(b, d));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(box + 0, mnx); atomicMin(box + 1, mny);
+        atomicMax(box + 2, mxx); atomicMax(box + 3, mxy);
+    }
+}
+
+// Roofline denominator: uniformly random 1-byte reads, L1 bypassed (ld.global.cg), one per lane per step.
+__global__ void gather_peak_kernel(const int8_t* buf, unsigned long long mask, long long reads_per_thread,
+                                   unsigned long long* sink)
+{
+    unsigned long long s = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 1;
+    int acc = 0;
+    for (long long i = 0; i < reads_per_thread; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;          // xorshift64
+        acc += (int)__ldcg(buf + (s & mask));
+    }
+    if (acc == 0x7fffffff) *sink = (unsigned long long)acc;
+}
+
+__global__ void debug_sincosf_kernel(const float* x, long long n, float* s, float* c)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        glibc_sincosf(x[i], s + i, c + i);
+}
+
+}  // namespace mcl

@@ -1,0 +1,165 @@
+/* mcl_cuda.h -- C ABI of the B200-native Monte Carlo localization engine (libmcl_cuda.so).
+ *
+ * This is the thin extern-"C" layer of the new src/slam/cuda/ module: the entry points botLab's C++ host classes
+ * (ParticleFilter / ActionModel / SensorModel / MovingLaserScan / OccupancyGrid device mirror) bind instead of running
+ * their serial CPU loops.  The reference has no FFI of its own; each function below names the reference code it replaces
+ * (paths relative to the reference root).  Plain pointers and sizes only; every pointer argument is caller-owned HOST
+ * memory valid for the duration of the call; device memory is owned by the engine.
+ *
+ * Conventions: every function returns 0 on success or a negative MCL_ERR_* code; mcl_last_error() gives the message.
+ * Nothing throws or aborts.  One caller thread per handle; one CUDA stream per handle.  There is no CPU fallback:
+ * without a CUDA device mcl_create fails.
+ */
+#ifndef MCL_CUDA_H
+#define MCL_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCL_OK 0
+#define MCL_ERR_INVALID (-1)    /* bad argument */
+#define MCL_ERR_CUDA (-2)       /* CUDA runtime / driver failure */
+#define MCL_ERR_STATE (-3)      /* call order (no map, no particles, no scan ...) */
+#define MCL_ERR_NO_DEVICE (-4)  /* no usable sm_100 GPU */
+#define MCL_ERR_COMM (-5)       /* multi-GPU exchange failure */
+
+typedef struct mcl_engine mcl_engine;
+
+/* lcmtypes/pose_xyt_t.lcm:1-8 -- 24 bytes */
+typedef struct { int64_t utime; float x, y, theta; } mcl_pose_t;
+/* lcmtypes/particle_t.lcm:4-9 -- 56 bytes, identical to the reference's particle_t */
+typedef struct { mcl_pose_t pose, parent_pose; double weight; } mcl_particle_t;
+
+/* Compile-time constants of the reference exposed as parameters; defaults are the reference's values. */
+typedef struct {
+    float  min_range;           /* moving_laser_scan.cpp:24   0.15f  */
+    double weight_floor;        /* particle_filter.cpp:121    0.001  */
+    double init_std;            /* particle_filter.cpp:23     0.01   */
+    int    legacy_equal_utime;  /* 1: every particle keeps pose.utime == parent_pose.utime, the reference's de-facto
+                                   behaviour (ActionModel::utime_ is never assigned, action_model.hpp:72), so the
+                                   per-ray interpolation degenerates to "all rays from the current pose".  0 (default):
+                                   pose.utime = odometry utime, real per-ray interpolation (the evident intent). */
+    int    lanes_per_particle;  /* sensor kernel mapping: 0 = auto, else 1, 2, 4, 8, 16 or 32 lanes share one particle */
+    int    map_tile;            /* 0 = auto, 1 = force L2/global gathers, 2 = force shared-memory map tile */
+    int    reserved[8];
+} mcl_params;
+
+/* ActionModel state + per-update parameters (action_model.hpp:66-76). */
+typedef struct {
+    mcl_pose_t previous_odometry;
+    int    initialized;
+    int    moved;
+    double rot1, trans, rot2;
+    double rot1_std, trans_std, rot2_std;
+} mcl_action_t;
+
+typedef struct {
+    int64_t num_particles;        /* global particle count */
+    int64_t local_particles;      /* particles scored by this rank */
+    int64_t updates;              /* fused updates run so far */
+    int64_t valid_beams;          /* beams of the current scan with range > min_range */
+    int64_t evals;                /* particle-beam evaluations of the last mcl_score / mcl_update (this rank) */
+    int64_t gathers;              /* map reads of the last scoring pass if gather counting is on, else -1 */
+    int64_t resample_overruns;    /* draws the reference's unbounded loop would have run past the end for (clamped) */
+    int64_t seq_fallback_chunks;  /* chunks of the exact sequential-sum emulation that took the serial path */
+    double  weight_sum;           /* wSum of the last normalise (sequential-double semantics) */
+    double  effective_sample_size;
+    float   ms_resample, ms_action, ms_score, ms_normalize, ms_estimate, ms_total;  /* last mcl_update, CUDA events */
+    int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
+    int     map_tile_used;        /* 1 = L2/global gathers, 2 = shared-memory tile */
+    int     kernel_launches;      /* kernels launched by the last mcl_update */
+    int     reserved[5];
+} mcl_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+void mcl_default_params(mcl_params* p);
+/* ParticleFilter::ParticleFilter(int) (particle_filter.cpp:8-13).  device: CUDA ordinal. */
+int  mcl_create(const mcl_params* params_or_null, int64_t num_particles, int device, mcl_engine** out);
+void mcl_destroy(mcl_engine* h);
+const char* mcl_last_error(const mcl_engine* h_or_null);
+/* The engine's CUDA stream (cudaStream_t) so a caller can order its own work / events against it. */
+void* mcl_stream(mcl_engine* h);
+int  mcl_sync(mcl_engine* h);
+
+/* ---- multi-GPU: one engine per process per GPU; rank r scores the global particle slice [r*N/R, (r+1)*N/R) ------ */
+/* nccl_unique_id: the 128-byte ncclUniqueId made by mcl_comm_unique_id on rank 0 and shipped by the host
+ * (torch.distributed / MPI / a socket).  The map is replicated: call mcl_set_map on every rank. */
+int  mcl_comm_unique_id(void* id128_out);
+int  mcl_comm_init(mcl_engine* h, const void* nccl_unique_id128, int rank, int world_size);
+
+/* ---- OccupancyGrid device mirror (occupancy_grid.cpp:63-71 read side; slam.cpp:274-281 mutates it every update) -- */
+/* cells: row-major int8, index y*width+x (occupancy_grid.hpp:208).  cells_per_meter is explicit because the
+ * reference's can be stale after loadFromFile (occupancy_grid.cpp:151-159). */
+int  mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float origin_x, float origin_y,
+                 float meters_per_cell, float cells_per_meter);
+int  mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const int8_t* src, int src_stride);
+
+/* ---- particle state -------------------------------------------------------------------------------------------- */
+/* ParticleFilter::initializeFilterAtPose (particle_filter.cpp:16-34) with the intended weight 1.0/N and a seeded
+ * counter-based generator instead of std::random_device. */
+int  mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime, uint64_t seed);
+/* Extension for global localisation (no reference equivalent): x,y uniform over the map, theta uniform in [-pi,pi). */
+int  mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed);
+/* AoS particle_t in/out (ParticleFilter::particles, particle_filter.cpp:75-81).  All particles must share one
+ * pose.utime and one parent_pose.utime (true for every cloud the reference produces).  Export writes
+ * min(max_n, ceil(N/stride)) particles: every stride-th one. */
+int  mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n);
+int  mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int64_t stride, int64_t* n_out);
+
+/* ---- host-side scalar part of the action model: ActionModel::updateAction (action_model.cpp:22-75) ------------- */
+void mcl_action_reset(mcl_action_t* a);
+int  mcl_action_update(mcl_action_t* a, const mcl_pose_t* odometry);   /* returns moved (1/0) */
+
+/* ---- stages, each usable alone for stage-wise parity ------------------------------------------------------------ */
+/* ParticleFilter::resamplePosteriorDistribution (particle_filter.cpp:84-103).  r = rand()/RAND_MAX/N is injected.
+ * weights_or_null: N doubles replacing the particles' weights first.  The running sum c reproduces the reference's
+ * sequential double rounding exactly, so indices are bit-identical to the reference loop.  indices_out_or_null gets
+ * the N source indices.  Particles (pose, parent_pose, weight) are gathered in place like prior[m] = posterior_[i]. */
+int  mcl_resample(mcl_engine* h, double r, const double* weights_or_null, int32_t* indices_out_or_null);
+/* ActionModel::applyAction over all particles (action_model.cpp:78-103, particle_filter.cpp:106-113).
+ * noise3n_or_null: N x (rot1, trans, rot2) float draws to inject (the reference's recorded draws); NULL = draw from the
+ * engine's Philox4x32-10 stream keyed by (seed, update counter, global particle index). */
+int  mcl_apply_action(mcl_engine* h, const mcl_action_t* a, int64_t utime, const float* noise3n_or_null);
+/* SensorModel::likelihood for every particle (sensor_model.cpp:14-86, moving_laser_scan.cpp:8-39,
+ * interpolation.hpp:24-50).  Scan = lidar_t's arrays (lcmtypes/lidar_t.lcm).  scores_out_or_null: N doubles. */
+int  mcl_score(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int num_ranges,
+               double* scores_out_or_null);
+/* ParticleFilter::computeNormalizedPosterior's floor / sum / divide (particle_filter.cpp:120-138), on the scores of
+ * the last mcl_score.  The sum has the reference's sequential-double semantics.  weights_out_or_null: N doubles. */
+int  mcl_normalize(mcl_engine* h, double* weights_out_or_null);
+/* ParticleFilter::estimatePosteriorPose (particle_filter.cpp:144-160): weighted mean x,y and circular mean theta. */
+int  mcl_estimate(mcl_engine* h, mcl_pose_t* pose_out);
+
+/* ---- fused update: ParticleFilter::updateFilter (particle_filter.cpp:37-52) -------------------------------------- */
+/* a: filled by mcl_action_update for this odometry.  If !a->moved nothing runs and pose_out is the previous estimate
+ * with utime = odometry_utime.  r: the resample draw.  noise3n_or_null as in mcl_apply_action. */
+int  mcl_update(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, const float* ranges, const float* thetas,
+                const int64_t* times, int num_ranges, double r, const float* noise3n_or_null, mcl_pose_t* pose_out);
+/* ParticleFilter::updateFilterActionOnly (particle_filter.cpp:54-65): action model only, no resample, no scoring. */
+int  mcl_update_action_only(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime,
+                            const float* noise3n_or_null);
+
+/* Device-resident pipelining for throughput runs: upload a scan once, then enqueue updates without host round trips.
+ * mcl_update_enqueue neither copies inputs nor synchronises; the estimate is read back later with mcl_read_estimate
+ * (which synchronises).  r_or_negative < 0 draws r from the Philox stream. */
+int  mcl_upload_scan(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int num_ranges,
+                     int64_t odometry_utime);
+int  mcl_update_enqueue(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, double r_or_negative);
+int  mcl_read_estimate(mcl_engine* h, mcl_pose_t* pose_out);
+
+/* ---- introspection ------------------------------------------------------------------------------------------------ */
+int  mcl_get_stats(mcl_engine* h, mcl_stats* out);
+int  mcl_set_gather_counting(mcl_engine* h, int on);   /* debug counter of map reads (slower scoring kernel) */
+/* Roofline denominator measured on this device: uniformly random 1-byte reads over a footprint of map_bytes, L1
+ * bypassed, one per lane.  Returns sectors (32 B) per second. */
+int  mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t reads, double* sectors_per_s_out);
+/* glibc-sincosf restatement evaluated on the device for n floats (test hook for the trig parity contract). */
+int  mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* sin_out, float* cos_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_CUDA_H */

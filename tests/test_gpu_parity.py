@@ -1,0 +1,403 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (botlab_b200/libmcl_cuda.so), against
+ (a) golden vectors produced by the compiled, unmodified reference (tests/golden/), and
+ (b) the oracle (oracle/mcl_oracle.c; and oracle/_ref where it travelled) on seeded inputs,
+ plus size-independent properties at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north_star): resample indices bit-exact; action poses within 1e-5 m / 1e-5 rad with injected draws;
+per-particle scores within 1e-5 relative (asserted EXACTLY here: they are multiples of 0.5); weights within 1e-6 abs."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, synth_grid_from_golden
+from botlab_b200 import engine, synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-5
+WEIGHT_TOL = 1e-6
+
+
+def port_grid(spec):
+    return port.Grid(spec.cells, spec.origin_x, spec.origin_y, spec.cells_per_meter)
+
+
+def make_engine(n, grid, **params):
+    e = engine.Engine(n, **params)
+    e.set_map(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
+    return e
+
+
+def angle_err(a, b):
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    return np.minimum(d, 2 * np.pi - d)
+
+
+# ------------------------------------------------------------------------------------------------ sensor model
+def test_sensor_known_answers(real_map):
+    k = load_golden("kat")
+    for i, expect in enumerate([3138.0, 1322.5, 1787.5, 2969.0]):
+        p = np.concatenate([k["particles"][i:i + 1]] * 2)
+        e = make_engine(2, real_map)
+        e.import_particles(p)
+        s = e.score(k["ranges"], k["thetas"], k["times"])
+        assert list(s) == [expect, expect]
+        e.close()
+
+
+@pytest.mark.parametrize("name", ["real", "synth"])
+@pytest.mark.parametrize("variant", ["interp", "degen"])
+@pytest.mark.parametrize("lanes,tile", [(0, 0), (32, 1), (1, 2), (8, 2), (4, 1)])
+def test_sensor_golden(name, variant, lanes, tile, real_map, sensor_golden):
+    sg = sensor_golden
+    grid = real_map if name == "real" else synth_grid_from_golden(sg)
+    p = sg[f"{name}_{variant}_particles"].copy()
+    if tile == 2:
+        # a forced tile needs a bounded cloud: keep the hostile headings, drop the far-away / NaN positions
+        p = p[np.r_[2:4, 5:len(p)]]
+    e = make_engine(len(p), grid, lanes_per_particle=lanes, map_tile=tile)
+    e.import_particles(p)
+    e.set_gather_counting(True)
+    s = e.score(sg[f"{name}_ranges"], sg[f"{name}_thetas"], sg[f"{name}_times"])
+    want, gathers, evals = port.likelihood(port_grid(grid), p, sg[f"{name}_ranges"], sg[f"{name}_thetas"],
+                                           sg[f"{name}_times"])
+    if tile != 2:
+        assert np.array_equal(want, sg[f"{name}_{variant}_scores"])        # oracle == reference golden
+    assert np.array_equal(s, want)                                        # engine == oracle, bit for bit
+    st = e.stats()
+    assert st["evals"] == evals and st["gathers"] == gathers              # algorithmic work agrees with the oracle
+    assert st["map_tile_used"] == (2 if tile == 2 else st["map_tile_used"])
+    e.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_sensor_random_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    grid = synth.make_map(400, seed=seed)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, num_beams=360 + 13 * seed, seed=seed)
+    clouds = [synth.make_particles(30_000, truth, seed=seed, parent_utime=int(t[0]), pose_utime=int(t[-1])),
+              synth.make_uniform_particles(30_000, grid, seed=seed, utime=int(t[-1]))]
+    for cloud in clouds:
+        e = make_engine(len(cloud), grid)
+        e.import_particles(cloud)
+        s = e.score(r, th, t)
+        want, _, _ = port.likelihood(port_grid(grid), cloud, r, th, t)
+        assert np.array_equal(s, want)
+        e.close()
+
+
+def test_sensor_ragged_inputs(real_map):
+    """Empty scan, all-invalid scan, one beam, 720 beams."""
+    p = synth.make_particles(64, (0.0, 0.0, 0.3), seed=1)
+    e = make_engine(64, real_map)
+    e.import_particles(p)
+    z = np.zeros(0, np.float32)
+    assert np.array_equal(e.score(z, z, np.zeros(0, np.int64)), np.zeros(64))
+    assert np.array_equal(e.score(np.full(10, 0.1, np.float32), np.zeros(10, np.float32), np.zeros(10, np.int64)),
+                          np.zeros(64))
+    for nb in (1, 720):
+        r, th, t = synth.make_scan(real_map, (0.0, 0.0, 0.3), num_beams=nb, seed=nb)
+        want, _, _ = port.likelihood(port_grid(real_map), p, r, th, t)
+        assert np.array_equal(e.score(r, th, t), want)
+    e.close()
+
+
+def test_map_rect_update_equals_full_upload(real_map):
+    rng = np.random.default_rng(5)
+    p = synth.make_particles(2000, (0.0, 0.0, 0.0), seed=2)
+    r, th, t = synth.make_scan(real_map, (0.0, 0.0, 0.0), seed=3)
+    e = make_engine(2000, real_map)
+    e.import_particles(p)
+    cells = real_map.cells.copy()
+    patch = rng.integers(-128, 128, (37, 53)).astype(np.int8)
+    cells[60:97, 71:124] = patch
+    e.update_map_rect(71, 60, patch)
+    changed = synth.GridSpec(cells, real_map.origin_x, real_map.origin_y, real_map.meters_per_cell,
+                             real_map.cells_per_meter)
+    want, _, _ = port.likelihood(port_grid(changed), p, r, th, t)
+    assert np.array_equal(e.score(r, th, t), want)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ action model
+def test_action_golden_injected_draws(real_map):
+    a = load_golden("action")
+    am = engine.ActionModel()
+    am.update(0.3, -0.2, 0.1)
+    assert am.update(0.32, -0.19, 0.11)
+    e = engine.Engine(512)
+    e.import_particles(a["particles_in"])
+    e.apply_action(am, utime=int(a["utime"]), noise=a["draws"])
+    out = e.export_particles()
+    want = a["particles_out"]
+    assert np.abs(out["pose"]["x"].astype(np.float64) - want["pose"]["x"]).max() <= POSE_TOL
+    assert np.abs(out["pose"]["y"].astype(np.float64) - want["pose"]["y"]).max() <= POSE_TOL
+    assert angle_err(out["pose"]["theta"], want["pose"]["theta"]).max() <= POSE_TOL
+    # parent_pose = the old pose, utime = the planted ActionModel::utime_
+    for f in ("x", "y", "theta"):
+        assert np.array_equal(out["parent_pose"][f], want["parent_pose"][f])
+    assert (out["pose"]["utime"] == want["pose"]["utime"]).all()
+    assert (out["parent_pose"]["utime"] == want["parent_pose"]["utime"]).all()
+    # in practice the poses are bit-identical except where libm's double sin/cos differs in the last place
+    same = sum(np.array_equal(out["pose"][f], want["pose"][f]) for f in ("x", "y", "theta"))
+    assert same >= 1
+    e.close()
+
+
+def test_action_philox_statistics():
+    n = 400_000
+    am = engine.ActionModel()
+    am.update(0.0, 0.0, 0.0)
+    am.update(0.10, 0.0, 0.0)
+    e = engine.Engine(n)
+    p = np.zeros(n, engine.PARTICLE_DTYPE)
+    p["weight"] = 1.0 / n
+    e.import_particles(p)
+    e.apply_action(am, utime=5)
+    out = e.export_particles()
+    # trans ~ N(0.1, 0.005), rot1, rot2 ~ N(0, 0.05): E[x] ~ 0.1*E[cos r1], theta std ~ sqrt(2)*0.05
+    assert abs(out["pose"]["x"].mean() - 0.1 * np.exp(-0.05 ** 2 / 2)) < 2e-4
+    assert abs(out["pose"]["theta"].std() - np.sqrt(2) * 0.05) < 1e-3
+    assert abs(out["pose"]["y"].mean()) < 2e-4
+    assert (out["parent_pose"]["x"] == 0).all() and (out["pose"]["utime"] == 5).all()
+    e2 = engine.Engine(n)
+    e2.import_particles(p)
+    e2.apply_action(am, utime=5)
+    assert np.array_equal(e2.export_particles()["pose"]["x"], out["pose"]["x"])     # counter-based => reproducible
+    e.close(); e2.close()
+
+
+def test_init_at_pose():
+    n = 200_000
+    e = engine.Engine(n)
+    e.init_at_pose(1.5, -2.0, 3.14, utime=77, seed=9)
+    p = e.export_particles()
+    assert abs(p["pose"]["x"][:-1].mean() - 1.5) < 1e-4 and abs(p["pose"]["x"][:-1].std() - 0.01) < 1e-4
+    assert abs(p["pose"]["y"][:-1].std() - 0.01) < 1e-4
+    assert np.abs(p["pose"]["theta"]).max() <= np.float32(np.pi)
+    assert (p["pose"]["x"][-1], p["pose"]["y"][-1], p["pose"]["theta"][-1]) == (np.float32(1.5), np.float32(-2.0),
+                                                                               np.float32(3.14))   # :33
+    assert (p["weight"] == 1.0 / n).all() and (p["pose"]["utime"] == 77).all()
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ resampling
+@pytest.mark.parametrize("n", [200, 4096, 100_000])
+def test_resample_golden_bit_exact(n):
+    g = load_golden("resample")
+    e = engine.Engine(n)
+    e.init_at_pose(0, 0, 0)
+    idx = e.resample(float(g[f"r_{n}"]), weights=g[f"w_{n}"])
+    assert np.array_equal(idx, g[f"idx_{n}"])
+    assert e.stats()["resample_overruns"] == 0
+    e.close()
+
+
+def test_resample_known_answer():
+    k = load_golden("kat")
+    e = engine.Engine(8)
+    e.import_particles(k["resample_particles"])
+    idx = e.resample(float(k["resample_r"]))
+    assert list(idx) == [1, 1, 3, 3, 4, 5, 6, 7]
+    out = e.export_particles()
+    assert np.array_equal(out["pose"]["x"], k["resample_particles"]["pose"]["x"][idx])
+    assert np.array_equal(out["weight"], k["resample_particles"]["weight"][idx])   # prior[m] = posterior_[i] (:100)
+    e.close()
+
+
+@pytest.mark.parametrize("n,seed", [(1_000_000, 1), (1_000_003, 2), (16_000_000, 3)])
+def test_resample_large_vs_oracle_bit_exact(n, seed):
+    """At these sizes a plain parallel double scan (and an exact one) disagrees with the sequential reference
+    (SURVEY 7.2 hard part 1); the engine must not."""
+    w = synth.filter_shaped_weights(n, seed=seed)
+    r = 0.8401877171547095 / n                                                  # first unseeded rand()/RAND_MAX
+    want, over = port.resample(w, r)
+    e = engine.Engine(n)
+    e.init_at_pose(0, 0, 0)
+    idx = e.resample(r, weights=w)
+    st = e.stats()
+    assert st["resample_overruns"] == over
+    assert np.array_equal(idx, want)
+    e.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "one_hot", "tiny_tail", "zeros_inside", "unnormalised", "denormal"])
+def test_resample_edge_weights(kind):
+    n = 50_000
+    rng = np.random.default_rng(3)
+    if kind == "uniform":
+        w = np.full(n, 1.0 / n)
+    elif kind == "one_hot":
+        w = np.zeros(n); w[n // 3] = 1.0
+    elif kind == "tiny_tail":
+        w = rng.random(n); w[n // 2:] *= 1e-18; w /= w.sum()
+    elif kind == "zeros_inside":
+        w = rng.random(n); w[rng.random(n) < 0.5] = 0.0; w /= w.sum()
+    elif kind == "unnormalised":
+        w = rng.random(n) * 37.0
+    else:
+        w = rng.random(n); w[:100] = 5e-324; w /= w.sum()
+    r = 0.3 / n
+    want, over = port.resample(w, r)
+    e = engine.Engine(n)
+    e.init_at_pose(0, 0, 0)
+    idx = e.resample(r, weights=w)
+    assert np.array_equal(idx, want)
+    assert e.stats()["resample_overruns"] == over
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ normalise / estimate
+def test_normalize_and_estimate_golden(sensor_golden):
+    g = load_golden("normalize")
+    sg = sensor_golden
+    grid = synth_grid_from_golden(sg)
+    e = make_engine(len(g["proposal"]), grid)
+    e.import_particles(g["proposal"])
+    e.score(sg["synth_ranges"], sg["synth_thetas"], sg["synth_times"], want_scores=False)
+    w = e.normalize()
+    assert np.abs(w - g["posterior"]["weight"]).max() <= WEIGHT_TOL
+    assert np.array_equal(w, g["posterior"]["weight"])          # the sequential-sum emulation makes them identical
+    est = e.estimate()
+    assert abs(est.x - float(g["estimate"]["x"])) <= POSE_TOL
+    assert abs(est.y - float(g["estimate"]["y"])) <= POSE_TOL
+    assert angle_err(est.theta, float(g["estimate"]["theta"])) <= POSE_TOL
+    st = e.stats()
+    scores, _, _ = port.likelihood(port_grid(grid), g["proposal"], sg["synth_ranges"], sg["synth_thetas"],
+                                   sg["synth_times"])
+    assert st["weight_sum"] == port.normalize(scores)[1]       # wSum with the reference's sequential rounding
+    assert 1.0 <= st["effective_sample_size"] <= len(w)
+    e.close()
+
+
+def test_estimate_known_answer():
+    k = load_golden("kat")
+    e = engine.Engine(8)
+    e.import_particles(k["resample_particles"])
+    est = e.estimate()
+    assert abs(est.x - 3.3499999) <= POSE_TOL and abs(est.y - 0.335000008) <= POSE_TOL
+    assert angle_err(est.theta, 3.09885478) <= POSE_TOL
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ fused update
+@pytest.mark.parametrize("variant", ["interp", "legacy"])
+def test_update_trajectory_golden(variant, real_map):
+    """Four ParticleFilter::updateFilter calls on the real map with the reference's rand() draw and mt19937 action draws
+    injected: particles, weights and estimates follow the reference."""
+    t = load_golden("trajectory")
+    n = len(t[f"{variant}_init"])
+    e = make_engine(n, real_map, legacy_equal_utime=1 if variant == "legacy" else 0)
+    e.import_particles(t[f"{variant}_init"])
+    am = engine.ActionModel()
+    assert am.update(0.0, 0.0, 0.0, 1_000_000) is False
+    for step in range(4):
+        odom = t[f"{variant}_{step}_odom"]
+        moved = am.update(float(odom["x"]), float(odom["y"]), float(odom["theta"]), int(odom["utime"]))
+        assert moved == bool(t[f"{variant}_{step}_moved"])
+        est = e.update(am, int(odom["utime"]), t[f"{variant}_{step}_ranges"], t[f"{variant}_{step}_thetas"],
+                       t[f"{variant}_{step}_times"], float(t[f"{variant}_{step}_r"]), noise=t[f"{variant}_{step}_draws"])
+        want = t[f"{variant}_{step}_particles"]
+        got = e.export_particles()
+        # identical resample indices <=> identical parent poses (they are copies of the chosen particles)
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(got["parent_pose"][f], want["parent_pose"][f]), (step, f)
+        assert np.abs(got["pose"]["x"].astype(np.float64) - want["pose"]["x"]).max() <= POSE_TOL
+        assert np.abs(got["pose"]["y"].astype(np.float64) - want["pose"]["y"]).max() <= POSE_TOL
+        assert angle_err(got["pose"]["theta"], want["pose"]["theta"]).max() <= POSE_TOL
+        assert np.abs(got["weight"] - want["weight"]).max() <= WEIGHT_TOL
+        g = t[f"{variant}_{step}_estimate"]
+        assert abs(est.x - float(g["x"])) <= POSE_TOL and abs(est.y - float(g["y"])) <= POSE_TOL
+        assert angle_err(est.theta, float(g["theta"])) <= POSE_TOL and est.utime == int(g["utime"])
+        if variant == "interp":
+            assert (got["pose"]["utime"] == int(odom["utime"])).all()
+    st = e.stats()
+    assert st["updates"] == 4 and st["kernel_launches"] > 0 and st["ms_total"] > 0
+    e.close()
+
+
+def test_update_without_motion_returns_previous_estimate(real_map):
+    e = make_engine(1000, real_map)
+    e.init_at_pose(0.5, 0.25, 0.1, utime=10, seed=4)
+    am = engine.ActionModel()
+    am.update(0.5, 0.25, 0.1, 10)
+    assert am.update(0.5, 0.25, 0.1, 20) is False
+    r, th, t = synth.make_scan(real_map, (0.5, 0.25, 0.1))
+    before = e.export_particles()
+    est = e.update(am, 20, r, th, t, 0.5 / 1000)
+    assert (est.x, est.y, est.theta, est.utime) == (np.float32(0.5), np.float32(0.25), np.float32(0.1), 20)  # :50
+    assert e.export_particles().tobytes() == before.tobytes()
+    e.close()
+
+
+def test_update_action_only(real_map):
+    a = load_golden("action")
+    am = engine.ActionModel()
+    am.update(0.3, -0.2, 0.1)
+    am.update(0.32, -0.19, 0.11)
+    e = engine.Engine(512)
+    e.import_particles(a["particles_in"])
+    e.update_action_only(am, int(a["utime"]), noise=a["draws"])
+    out = e.export_particles()
+    assert np.abs(out["pose"]["x"].astype(np.float64) - a["particles_out"]["pose"]["x"]).max() <= POSE_TOL
+    assert np.array_equal(out["weight"], a["particles_in"]["weight"])          # no resample, no reweighting (:54-65)
+    e.close()
+
+
+def test_export_stride_and_cap():
+    n = 10_000
+    p = synth.make_particles(n, (0, 0, 0), seed=8)
+    e = engine.Engine(n)
+    e.import_particles(p)
+    sub = e.export_particles(stride=7)
+    assert len(sub) == -(-n // 7) and np.array_equal(sub["pose"]["x"], p["pose"]["x"][::7])
+    assert len(e.export_particles(max_n=100, stride=3)) == 100
+    e.close()
+
+
+def test_import_rejects_mixed_utimes():
+    p = synth.make_particles(100, (0, 0, 0), seed=8)
+    p["pose"]["utime"][50] += 1
+    e = engine.Engine(100)
+    with pytest.raises(engine.MclError, match="utime"):
+        e.import_particles(p)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("config", ["config3"])
+def test_full_size_properties(config):
+    """BASELINE configs at full size: size-independent properties + a sub-sample against the oracle."""
+    n, side = synth.CONFIGS[config]
+    rng = np.random.default_rng(17)
+    grid = synth.make_map(side, seed=synth.MAP_SEED + 3)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=17)
+    nb_valid = int((r > np.float32(0.15)).sum())
+    e = make_engine(n, grid)
+    e.init_at_pose(*truth, utime=int(t[0]) - 100_000, seed=17)
+    am = engine.ActionModel()
+    am.update(*truth, int(t[0]) - 100_000)
+    moved = am.update(truth[0] + 0.02, truth[1] + 0.01, truth[2] + 0.01, int(t[-1]))
+    assert moved
+    rdraw = 0.8401877171547095 / n
+    est = e.update(am, int(t[-1]), r, th, t, rdraw)
+    st = e.stats()
+    assert st["evals"] == n * nb_valid and st["resample_overruns"] == 0
+    sub = e.export_particles(stride=997)
+    scores, _, _ = port.likelihood(port_grid(grid), sub, r, th, t)
+    w = np.maximum(scores, 0.001) / st["weight_sum"]
+    assert np.abs(w - sub["weight"]).max() <= WEIGHT_TOL and np.array_equal(w, sub["weight"])
+    assert abs(est.x - truth[0]) < 0.2 and abs(est.y - truth[1]) < 0.2
+    # second update: resampling from the weights just computed; indices sorted, counts follow the weights
+    am.update(truth[0] + 0.04, truth[1] + 0.02, truth[2] + 0.02, int(t[-1]) + 100_000)
+    wfull = e.normalize()                      # idempotent: same scores -> same weights
+    assert abs(wfull.sum() - 1.0) < 1e-9
+    idx = e.resample(rdraw)
+    assert (np.diff(idx) >= 0).all()
+    counts = np.bincount(idx, minlength=n)
+    assert np.abs(counts - wfull * n).max() <= 1.0 + 1e-6      # systematic resampling: |count - N w| < 1
+    want, _ = port.resample(wfull, rdraw)
+    assert np.array_equal(idx, want)
+    e.close()

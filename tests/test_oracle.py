@@ -1,0 +1,176 @@
+"""CPU tests: the plain-C restatement (oracle/mcl_oracle.c) against golden vectors produced by the compiled,
+unmodified reference (tests/golden/make_golden.py), and against the live reference library where it is present."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, synth_grid_from_golden
+from oracle import port, ref
+from botlab_b200 import synth
+
+
+def port_grid(spec):
+    return port.Grid(spec.cells, spec.origin_x, spec.origin_y, spec.cells_per_meter)
+
+
+def same_particles(a, b):
+    """Field-wise bit equality (the 4 padding bytes after each pose are indeterminate in the reference's structs)."""
+    for k in ("pose", "parent_pose"):
+        for f, t in (("utime", np.int64), ("x", np.uint32), ("y", np.uint32), ("theta", np.uint32)):
+            if not np.array_equal(np.ascontiguousarray(a[k][f]).view(t), np.ascontiguousarray(b[k][f]).view(t)):
+                return False
+    return np.array_equal(a["weight"].view(np.uint64), b["weight"].view(np.uint64))
+
+
+def test_layouts():
+    assert port.POSE_DTYPE.itemsize == 24 and port.PARTICLE_DTYPE.itemsize == 56
+
+
+def test_kat_sensor_scores(real_map):
+    k = load_golden("kat")
+    s, gathers, evals = port.likelihood(port_grid(real_map), k["particles"], k["ranges"], k["thetas"], k["times"])
+    assert np.array_equal(s, k["scores"])
+    assert np.array_equal(k["scores"], [3138.0, 1322.5, 1787.5, 2969.0])
+    assert evals == 4 * 360 and 4 * 360 <= gathers <= 3 * 4 * 360
+
+
+def test_kat_moving_scan():
+    k = load_golden("kat")
+    p = k["particles"]
+    rb = port.moving_scan(k["ranges"], k["thetas"], k["times"], p["parent_pose"][1], p["pose"][1])
+    rd = port.moving_scan(k["ranges"], k["thetas"], k["times"], p["parent_pose"][3], p["pose"][3])
+    assert np.array_equal(rb.view(np.uint32), k["rays_b"].view(np.uint32))
+    assert np.array_equal(rd.view(np.uint32), k["rays_d"].view(np.uint32))
+    assert len(rd) == 360 and np.isclose(rd[359][3], 3.11791658)                    # B7
+
+
+def test_kat_action():
+    k = load_golden("kat")
+    am = port.ActionModel()
+    am.update(synth.make_pose(0, 0, 0))
+    moved, params = am.update(synth.make_pose(0.02, 0.01, 0.01))
+    assert moved and np.array_equal(params, k["action_forward"])                    # B8
+    out = am.apply(k["action_in"], k["action_draws"])
+    for f in ("x", "y", "theta"):
+        assert np.array_equal(out["pose"][f], k["action_out"]["pose"][f])           # B9
+    am2 = port.ActionModel()
+    am2.update(synth.make_pose(0, 0, 0))
+    _, back = am2.update(synth.make_pose(-0.02, 0, 0))
+    assert np.array_equal(back, k["action_backward"])                               # B10
+
+
+def test_kat_mt19937_and_normal():
+    rng = port.Rng(5489)
+    assert rng.next_u32() == 3499211612
+    rng = port.Rng(5489)
+    assert rng.normal(0.0, 1.0) == 0.13452965847232812
+    # the draws the reference's applyAction made in B9 (default-seeded generator, after updateAction of B8)
+    k = load_golden("kat")
+    am = port.ActionModel()
+    am.update(synth.make_pose(0, 0, 0))
+    am.update(synth.make_pose(0.02, 0.01, 0.01))
+    assert np.array_equal(am.draws(port.Rng(5489), 2), k["action_draws"])
+
+
+def test_kat_resample_and_estimate():
+    k = load_golden("kat")
+    ps = k["resample_particles"]
+    assert k["resample_r"] == 0.10502346464433869                                   # B11
+    idx, over = port.resample(ps["weight"], float(k["resample_r"]))
+    assert over == 0 and np.array_equal(idx, k["resample_idx"]) and list(idx) == [1, 1, 3, 3, 4, 5, 6, 7]
+    est = port.estimate(ps)
+    g = k["estimate"]
+    assert est["x"] == g["x"] and est["y"] == g["y"] and est["theta"] == g["theta"]  # B12
+
+
+@pytest.mark.parametrize("name", ["real", "synth"])
+@pytest.mark.parametrize("variant", ["interp", "degen"])
+def test_sensor_golden(name, variant, real_map, sensor_golden):
+    sg = sensor_golden
+    grid = real_map if name == "real" else synth_grid_from_golden(sg)
+    s, gathers, evals = port.likelihood(port_grid(grid), sg[f"{name}_{variant}_particles"], sg[f"{name}_ranges"],
+                                        sg[f"{name}_thetas"], sg[f"{name}_times"])
+    assert np.array_equal(s, sg[f"{name}_{variant}_scores"])
+    assert (s * 2 == np.round(s * 2)).all()           # scores are exact multiples of 0.5
+    assert s[5:].max() > 0
+
+
+def test_action_golden():
+    a = load_golden("action")
+    am = port.ActionModel()
+    am.update(synth.make_pose(0.3, -0.2, 0.1))
+    moved, params = am.update(synth.make_pose(0.32, -0.19, 0.11))
+    assert moved == bool(a["moved"]) and np.array_equal(params, a["params"])
+    out = am.apply(a["particles_in"], a["draws"], utime=int(a["utime"]))
+    assert same_particles(out, a["particles_out"])
+    # and the draws themselves from the libstdc++ restatement (generator seeded 12345)
+    assert np.array_equal(am.draws(port.Rng(12345), 512), a["draws"])
+
+
+@pytest.mark.parametrize("n", [200, 4096, 100_000])
+def test_resample_golden(n):
+    g = load_golden("resample")
+    idx, over = port.resample(g[f"w_{n}"], float(g[f"r_{n}"]))
+    assert over == 0 and np.array_equal(idx, g[f"idx_{n}"])
+
+
+def test_normalize_estimate_golden(sensor_golden):
+    g = load_golden("normalize")
+    grid = synth_grid_from_golden(sensor_golden)
+    sg = sensor_golden
+    s, _, _ = port.likelihood(port_grid(grid), g["proposal"], sg["synth_ranges"], sg["synth_thetas"], sg["synth_times"])
+    w, wsum = port.normalize(s)
+    assert np.array_equal(w, g["posterior"]["weight"])
+    est = port.estimate(g["posterior"])
+    for f in ("x", "y", "theta"):
+        assert est[f] == g["estimate"][f]
+
+
+@pytest.mark.parametrize("variant", ["interp", "legacy"])
+def test_trajectory_golden(variant, real_map):
+    t = load_golden("trajectory")
+    pf = port.ParticleFilter(t[f"{variant}_init"])
+    grid = port_grid(real_map)
+    # first reference call only latched the odometry at pose (0,0,0)
+    pf.action.update(synth.make_pose(0.0, 0.0, 0.0, utime=1_000_000))
+    for step in range(4):
+        odom = t[f"{variant}_{step}_odom"]
+        autime = int(odom["utime"]) if variant == "interp" else 900_000
+        est, moved = pf.update(grid, odom, t[f"{variant}_{step}_ranges"], t[f"{variant}_{step}_thetas"],
+                               t[f"{variant}_{step}_times"], float(t[f"{variant}_{step}_r"]),
+                               t[f"{variant}_{step}_draws"], action_utime=autime)
+        assert moved == bool(t[f"{variant}_{step}_moved"])
+        assert same_particles(pf.particles, t[f"{variant}_{step}_particles"])
+        g = t[f"{variant}_{step}_estimate"]
+        assert est["x"] == g["x"] and est["y"] == g["y"] and est["theta"] == g["theta"] and est["utime"] == g["utime"]
+
+
+# ---------------------------------------------------------------- live cross-checks where oracle/_ref was built
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_port_vs_reference_sensor_random(seed):
+    rng = np.random.default_rng(seed)
+    grid = synth.make_map(240, seed=seed)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, num_beams=360 + 17 * seed, seed=seed)
+    p = synth.make_particles(2000, truth, seed=seed, parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    u = synth.make_uniform_particles(2000, grid, seed=seed, utime=int(t[-1]))
+    rg = ref.RefGrid.from_cells(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell)
+    for cloud in (p, u):
+        a = ref.likelihood(rg, cloud, ref.Scan(r, th, t))
+        b, _, _ = port.likelihood(port_grid(grid), cloud, r, th, t)
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+def test_port_vs_reference_resample_large():
+    n = 1_000_000
+    w = synth.filter_shaped_weights(n, seed=42)
+    pf = ref.RefParticleFilter(n)
+    ps = np.zeros(n, ref.PARTICLE_DTYPE)
+    ps["weight"] = w
+    pf.set_particles(ps)
+    idx, over = port.resample(w, ref.resample_draw(1, n))
+    assert over == 0 and np.array_equal(idx, pf.resample(1))
