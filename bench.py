@@ -205,9 +205,9 @@ def run_engine(args):
         e.comm_init(bytes(uid.cpu().tolist()), rank, world)
     e.set_map(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
     pose0, r0, th0, t0 = scans[0]
-    e.init_at_pose(*pose0, utime=int(t0[0]) - 100_000, seed=42)
+    e.init_at_pose(*pose0, utime=int(t0[0]), seed=42)
     am = engine.ActionModel()
-    am.update(*pose0, int(t0[0]) - 100_000)
+    am.update(*pose0, int(t0[0]))
 
     def barrier():
         if world > 1:
@@ -227,8 +227,11 @@ def run_engine(args):
     def next_inputs():
         k = step_no[0]
         step_no[0] += 1
-        pose, r, th, t = scans[(k + 1) % len(scans)]
+        pose, r, th, _ = scans[(k + 1) % len(scans)]
+        # one 10 Hz sweep ending at this update's odometry time, as OccupancyGridSLAM pairs them
+        # (slam.cpp:227: odometry is sampled at scan.times.back())
         ut = int(t0[0]) + 100_000 * (k + 1)
+        t = ut - 100_000 + (np.arange(len(r), dtype=np.int64) * 100_000) // len(r) + 100_000 // len(r)
         # odometry alternates so the action model always reports motion
         am.update(pose[0] + 1e-3 * (k % 7), pose[1], pose[2], ut)
         assert am.moved
@@ -279,10 +282,9 @@ def run_engine(args):
 
     # ---- algorithmic traffic of the sensor kernel: one untimed counted pass --------------------------------------
     e.set_gather_counting(True)
-    e.update(am, ut + 100_000, r, th, t, 0.5 / n) if False else None
     local_n = e.stats()["local_particles"]
-    am.update(pose0[0] + 0.5e-3, pose0[1], pose0[2], ut + 100_000)
-    e.update(am, ut + 100_000, r, th, t, 0.5 / n)
+    r, th, t, ut = next_inputs()
+    e.update(am, ut, r, th, t, 0.5 / n)
     st = e.stats()
     e.set_gather_counting(False)
     gathers = st["gathers"]

@@ -96,4 +96,75 @@ GS_HD void glibc_sincosf(float xf, float* sinp, float* cosp)
     else      { *sinp = sv; *cosp = cv; }
 }
 
+// Branch-free variant for the hot loop, bit-identical to glibc_sincosf for |x| < 120 (checked exhaustively on [-4, 4]
+// by tests/csrc/sincosf_sweep.c):
+//  - the quadrant formula n = ((int)(x*hpi_inv) + 2^23) >> 24 gives n = 0 for |x| < pi/4, where x - 0*hpi = x exactly,
+//    so glibc's separate small-argument path computes the same polynomial;
+//  - for |x| < 2^-12 the polynomial itself rounds to (x, 1.0f), glibc's shortcut values;
+//  - __sincosf_table[1] is table[0] with the cosine coefficients negated, and sign[n&3] multiplies the reduced
+//    argument of an odd polynomial: round-to-nearest is sign-symmetric, so both signs can be applied to the final
+//    floats instead (no multiplies by +-1).
+#if defined(__CUDACC__)
+// Device copies of the constants in constant memory: FP64 instructions take them as c[bank][offset] operands, instead of
+// the two 32-bit immediate moves per use that literal doubles cost.
+__device__ __constant__ double gs_k[10] = {GS_HPI_INV, GS_HPI, GS_S1, GS_S2, GS_S3, GS_C0, GS_C1, GS_C2, GS_C3, GS_C4};
+#endif
+#if defined(__CUDA_ARCH__)
+#define GS_K(i, lit) gs_k[i]
+#else
+#define GS_K(i, lit) (lit)
+#endif
+
+// _core differs from glibc in exactly one input: x = -0.0f yields sin = +0.0f instead of -0.0f (the polynomial's
+// x3*S1 term is +0).  The sensor model only ever truncates range*sin*cpm + start to an int, where the sign of a zero
+// cannot matter, so the hot loop uses _core; glibc_sincosf_fast adds the one select that makes it exact everywhere.
+GS_HD void glibc_sincosf_core(float xf, float* sinp, float* cosp)
+{
+    const double x = (double)xf;
+    const double r = GS_MUL(x, GS_K(0, GS_HPI_INV));
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    const double xr = GS_FMA(-(double)n, GS_K(1, GS_HPI), x);
+    const double x2 = GS_MUL(xr, xr);
+    const double x3 = GS_MUL(x2, xr);
+    const double x4 = GS_MUL(x2, x2);
+    const double s1 = GS_FMA(x2, GS_K(4, GS_S3), GS_K(3, GS_S2));
+    const double c2 = GS_FMA(x2, GS_K(9, GS_C4), GS_K(8, GS_C3));
+    const double c1 = GS_FMA(x2, GS_K(6, GS_C1), GS_K(5, GS_C0));
+    const double x5 = GS_MUL(x2, x3);
+    const double x6 = GS_MUL(x2, x4);
+    const double s = GS_FMA(x3, GS_K(2, GS_S1), xr);
+    const double c = GS_FMA(x4, GS_K(7, GS_C2), c1);
+    const float sv = (float)GS_FMA(x5, s1, s);
+    const float cv = (float)GS_FMA(x6, c2, c);
+    const uint32_t sbit = ((uint32_t)(n + 1) & 2u) << 30;    // sign[n & 3] = {+,-,-,+}
+    const uint32_t cbit = ((uint32_t)n & 2u) << 30;          // table[1] when n & 2
+#if defined(__CUDA_ARCH__)
+    const float ss = __uint_as_float(__float_as_uint(sv) ^ sbit);
+    const float cc = __uint_as_float(__float_as_uint(cv) ^ cbit);
+#else
+    uint32_t us = gs_float_bits(sv) ^ sbit, uc = gs_float_bits(cv) ^ cbit;
+    float ss, cc;
+    memcpy(&ss, &us, 4);
+    memcpy(&cc, &uc, 4);
+#endif
+    *sinp = (n & 1) ? cc : ss;
+    *cosp = (n & 1) ? ss : cc;
+}
+
+GS_HD void glibc_sincosf_fast(float xf, float* sinp, float* cosp)
+{
+    float s, c;
+    glibc_sincosf_core(xf, &s, &c);
+    *sinp = (xf == 0.0f) ? xf : s;
+    *cosp = c;
+}
+
+// wrap_to_pi (common/angle_functions.hpp:12-24) fast path for a in (-3*pi, -pi]: the reference computes
+// (float)((double)a + 2*M_PI).  With 2*M_PI = H + L (H = (float)(2*M_PI)), a + H is exact in float (Sterbenz range) and
+// the double sum is exact too, so the result is RN_float(t + L) with t = a + H.  Adding the float-rounded L instead gives
+// the same rounding unless |t| is tiny (checked exhaustively by tests/csrc/sincosf_sweep.c over every float in range);
+// callers take the double path when |t| < 2^-20.
+#define GS_TWO_PI_HI 6.2831854820251465f       /* (float)(2*M_PI) */
+#define GS_TWO_PI_LO (-1.7484555e-7f)          /* (float)(2*M_PI - H) */
+
 #endif  // BOTLAB_B200_GLIBC_SINCOSF_H

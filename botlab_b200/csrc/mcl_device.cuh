@@ -41,7 +41,7 @@ __device__ __forceinline__ float wrap_to_pi(float a)
 // common/angle_functions.hpp:78-87 / :128-138 share this fold.
 __device__ __forceinline__ double fold_pi(double v)
 {
-    if (fabs(v) > kPi) v = __dadd_rn(v, (v > 0) ? -kTwoPi : kTwoPi);
+    if (__builtin_expect(fabs(v) > kPi, 0)) v = __dadd_rn(v, (v > 0) ? -kTwoPi : kTwoPi);
     return v;
 }
 
@@ -91,11 +91,75 @@ __device__ __forceinline__ RayBase make_ray_base(float xa, float ya, float tha, 
     return r;
 }
 
+// wrap_to_pi with a float-only fast path for the common case a in (-3*pi, -pi] (see glibc_sincosf.h: exact by the
+// exhaustive sweep); everything else takes the reference's double loop.
+__device__ __forceinline__ float wrap_to_pi_fast(float a)
+{
+    if (a <= -kPiF || a >= kPiF) {
+        const float t = __fadd_rn(a, GS_TWO_PI_HI);
+        if (a > -9.42477f && a < 0.0f && fabsf(t) >= 9.5367431640625e-07f) a = __fadd_rn(t, GS_TWO_PI_LO);
+        else a = wrap_to_pi(a);
+    }
+    return a;
+}
+
+// Map window a CTA reads from: either the shared-memory tile or the whole global mirror.  Cells with
+// 1 <= x-x0 < w-1 and 1 <= y-y0 < h-1 ("interior") have all eight neighbours inside the window, so the endpoint and
+// its two Bresenham neighbours are read without further checks.
+struct Window {
+    const int8_t* base;
+    int x0, y0, w, h, pitch;
+};
+
+// Hoisted per-CTA grid constants.
+struct GridConst {
+    double gx, gy, cpm_d;
+    float cpm;
+};
+
 // One particle-beam evaluation: moving_laser_scan.cpp:26-33 + sensor_model.cpp:28-59.  Returns the ray score in
-// HALF units (2*odds, or o1, or o2): exact integers.  READ(x, y) reads the map.
-template <bool INTERP, class Reader>
-__device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, float gx, float gy, float cpm,
-                                          const Reader& READ, int& gathers)
+// HALF units (2*odds, or o1, or o2): exact integers.  SMEM selects the window's address space.
+// Fast path: all coordinates are small (so float->int conversion and 32-bit differences cannot overflow) and the
+// endpoint is interior to the window.  Anything else -- NaN/huge poses, endpoints at the window edge or off the map --
+// takes slow_ray(), the literal restatement with x86 conversion semantics and bounds-checked global reads.
+template <bool SMEM>
+__device__ __forceinline__ int window_read(const Window& w, int idx)
+{
+    return SMEM ? (int)w.base[idx] : (int)__ldg(w.base + idx);
+}
+
+__device__ __forceinline__ int slow_ray(const DevGrid& g, float px, float py, float sx, float sy, int* gathers)
+{
+    const int ex = f2i_x86(__fadd_rn(px, sx));
+    const int ey = f2i_x86(__fadd_rn(py, sy));
+    const int xx = f2i_x86(__fadd_rn(__fmul_rn(2.0f, px), sx));
+    const int xy = f2i_x86(__fadd_rn(__fmul_rn(2.0f, py), sy));
+    const int odds = grid_read(g, ex, ey);
+    *gathers += 1;
+    if (odds > 0) return 2 * odds;
+    int ax, ay, bx, by;
+    bresenham_step(ex, ey, f2i_x86(sx), f2i_x86(sy), ax, ay);
+    bresenham_step(ex, ey, xx, xy, bx, by);
+    const int o1 = grid_read(g, ax, ay);
+    const int o2 = grid_read(g, bx, by);
+    *gathers += 2;
+    return o1 > 0 ? o1 : (o2 > 0 ? o2 : 0);
+}
+
+// Offset (in window bytes) of the cell one Bresenham step from (x1,y1) toward (x2,y2); 32-bit arithmetic, valid while
+// all coordinates are below 2^28 in magnitude (sensor_model.cpp:61-86: step x iff 2dx >= dy, step y iff dx <= 2dy).
+__device__ __forceinline__ int step_offset(int x1, int y1, int x2, int y2, int pitch)
+{
+    const int ddx = x2 - x1, ddy = y2 - y1;
+    const int dx = abs(ddx), dy = abs(ddy);
+    const int sx = ddx > 0 ? 1 : -1;
+    const int sy = ddy > 0 ? pitch : -pitch;
+    return ((2 * dx >= dy) ? sx : 0) + ((dx <= 2 * dy) ? sy : 0);
+}
+
+template <bool INTERP, bool SMEM, bool COUNT>
+__device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const GridConst& gc, const Window& win,
+                                          const DevGrid& grid, int& gathers)
 {
     float ox, oy, thr;
     if (INTERP) {
@@ -105,29 +169,43 @@ __device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, float
     } else {
         ox = p.xa; oy = p.ya; thr = p.tha;                                      // :29-34 equal-utime early-out
     }
-    const float th = wrap_to_pi(__fsub_rn(thr, b.theta));                      // moving_laser_scan.cpp:33
+    const float th = wrap_to_pi_fast(__fsub_rn(thr, b.theta));                 // moving_laser_scan.cpp:33
     // grid_utils.hpp:50-55: double math, stored into Point<float>
-    const float sx = (float)__dmul_rn(__dsub_rn((double)ox, (double)gx), (double)cpm);
-    const float sy = (float)__dmul_rn(__dsub_rn((double)oy, (double)gy), (double)cpm);
+    const float sx = (float)__dmul_rn(__dsub_rn((double)ox, gc.gx), gc.cpm_d);
+    const float sy = (float)__dmul_rn(__dsub_rn((double)oy, gc.gy), gc.cpm_d);
     float s, c;
-    glibc_sincosf(th, &s, &c);
-    const float px = __fmul_rn(__fmul_rn(b.range, c), cpm);                    // (range*cos)*cpm, float
-    const float py = __fmul_rn(__fmul_rn(b.range, s), cpm);
-    const int ex = f2i_x86(__fadd_rn(px, sx));                                 // sensor_model.cpp:34
-    const int ey = f2i_x86(__fadd_rn(py, sy));                                 // :35
+    glibc_sincosf_core(th, &s, &c);
+    const float px = __fmul_rn(__fmul_rn(b.range, c), gc.cpm);                 // (range*cos)*cpm, float
+    const float py = __fmul_rn(__fmul_rn(b.range, s), gc.cpm);
+    // one guard for every conversion below: NaN or anything >= 2^27 fails it
+    const float mag = __fadd_rn(__fadd_rn(fabsf(sx), fabsf(sy)), __fadd_rn(fabsf(px), fabsf(py)));
+    const int ex = __float2int_rz(__fadd_rn(px, sx));                          // sensor_model.cpp:34
+    const int ey = __float2int_rz(__fadd_rn(py, sy));                          // :35
+    const int tx = ex - win.x0, ty = ey - win.y0;
+    const bool small = mag < 134217728.0f;
+    const bool fast = small && ((unsigned)(tx - 1) < (unsigned)(win.w - 2)) && ((unsigned)(ty - 1) < (unsigned)(win.h - 2));
+    if (__builtin_expect(!fast, 0)) {
+        // endpoint two or more cells outside the grid: it and both neighbours read 0 (occupancy_grid.cpp:65-70)
+        if (small && ((unsigned)(ex + 1) > (unsigned)(grid.width + 1) || (unsigned)(ey + 1) > (unsigned)(grid.height + 1))) {
+            if (COUNT) gathers += 3;
+            return 0;
+        }
+        return slow_ray(grid, px, py, sx, sy, &gathers);
+    }
     // :37-38  ((2*range)*cos)*cpm == 2*px exactly (power-of-two scaling commutes with rounding)
-    const int xx = f2i_x86(__fadd_rn(__fmul_rn(2.0f, px), sx));
-    const int xy = f2i_x86(__fadd_rn(__fmul_rn(2.0f, py), sy));
-    const int odds = READ(ex, ey);                                             // :41
-    gathers += 1;
-    if (odds > 0) return 2 * odds;
-    int ax, ay, bx, by;
-    bresenham_step(ex, ey, f2i_x86(sx), f2i_x86(sy), ax, ay);                  // :48 toward the robot
-    bresenham_step(ex, ey, xx, xy, bx, by);                                    // :49 away from the robot
-    const int o1 = READ(ax, ay);
-    const int o2 = READ(bx, by);
-    gathers += 2;
-    return o1 > 0 ? o1 : (o2 > 0 ? o2 : 0);
+    const int xx = __float2int_rz(__fadd_rn(__fmul_rn(2.0f, px), sx));
+    const int xy = __float2int_rz(__fadd_rn(__fmul_rn(2.0f, py), sy));
+    const int idx = ty * win.pitch + tx;
+    const int odds = window_read<SMEM>(win, idx);                              // :41
+    const int off1 = step_offset(ex, ey, __float2int_rz(sx), __float2int_rz(sy), win.pitch);   // :48 toward the robot
+    const int off2 = step_offset(ex, ey, xx, xy, win.pitch);                   // :49 away from the robot
+    int o1 = 0, o2 = 0;
+    if (odds <= 0) {
+        o1 = window_read<SMEM>(win, idx + off1);
+        o2 = window_read<SMEM>(win, idx + off2);
+    }
+    if (COUNT) gathers += odds > 0 ? 1 : 3;
+    return odds > 0 ? 2 * odds : (o1 > 0 ? o1 : max(o2, 0));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

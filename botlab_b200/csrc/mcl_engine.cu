@@ -298,12 +298,13 @@ int run_score(mcl_engine* h)
             const double cy0 = std::floor(((double)mny - h->grid.origin_y) * cpm - reach);
             const double cx1 = std::ceil(((double)mxx - h->grid.origin_x) * cpm + reach);
             const double cy1 = std::ceil(((double)mxy - h->grid.origin_y) * cpm + reach);
-            // clip to the grid (outside reads are 0 through the global fallback anyway)
-            long long x0 = (long long)std::max(cx0, 0.0), y0 = (long long)std::max(cy0, 0.0);
-            long long x1 = (long long)std::min(cx1, (double)h->grid.width - 1);
-            long long y1 = (long long)std::min(cy1, (double)h->grid.height - 1);
+            // clip to the grid plus a 2-cell zero margin: endpoints on the map's outer wall stay interior to the
+            // window (cells outside the grid are staged as 0, OccupancyGrid::logOdds' out-of-grid value)
+            long long x0 = (long long)std::max(cx0, -2.0), y0 = (long long)std::max(cy0, -2.0);
+            long long x1 = (long long)std::min(cx1, (double)h->grid.width + 1);
+            long long y1 = (long long)std::min(cy1, (double)h->grid.height + 1);
             if (x1 >= x0 && y1 >= y0) {
-                x0 &= ~3ll;
+                x0 = (x0 >= 0) ? (x0 & ~3ll) : -(((-x0) + 3) & ~3ll);   // 4-byte aligned, rounding down
                 const long long tw = x1 - x0 + 1, th = y1 - y0 + 1;
                 long long pitch = (tw + 3) & ~3ll;
                 if (((pitch >> 2) & 1) == 0) pitch += 4;     // odd number of 4-byte words per row: spreads rows over banks

@@ -24,25 +24,8 @@ struct ScoreArgs {
     unsigned long long* gather_counter;                  // COUNT only
 };
 
-struct GlobalReader {
-    const DevGrid& g;
-    __device__ __forceinline__ int operator()(int x, int y) const { return grid_read(g, x, y); }
-};
-
-struct TileReader {
-    const DevGrid& g;
-    const int8_t* tile;
-    int x0, y0, w, h, pitch;
-    __device__ __forceinline__ int operator()(int x, int y) const
-    {
-        const unsigned tx = (unsigned)(x - x0), ty = (unsigned)(y - y0);
-        if (tx < (unsigned)w && ty < (unsigned)h) return (int)tile[ty * pitch + tx];
-        return grid_read(g, x, y);
-    }
-};
-
 template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a)
+__global__ void __launch_bounds__(256, 2) score_kernel(const ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     Beam* sbeams = reinterpret_cast<Beam*>(smem);
@@ -64,9 +47,17 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a)
     }
     __syncthreads();
 
-    const GlobalReader gread{a.grid};
-    const TileReader tread{a.grid, stile, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch};
-    const float gx = a.grid.origin_x, gy = a.grid.origin_y, cpm = a.grid.cells_per_meter;
+    Window win;
+    if (TILE) {
+        win.base = stile; win.x0 = a.tile_x0; win.y0 = a.tile_y0; win.w = a.tile_w; win.h = a.tile_h;
+        win.pitch = a.tile_pitch;
+    } else {
+        win.base = a.grid.cells; win.x0 = 0; win.y0 = 0; win.w = a.grid.width; win.h = a.grid.height;
+        win.pitch = a.grid.pitch;
+    }
+    GridConst gc;
+    gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
+    gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
 
     constexpr int PPB = 256 / G;                 // particles per CTA per iteration
     const int sub = threadIdx.x % G;
@@ -78,11 +69,8 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a)
         if (p < a.hi) {
             const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
 #pragma unroll 2
-            for (int j = sub; j < a.num_beams; j += G) {
-                const Beam b = sbeams[j];
-                acc += TILE ? score_beam<INTERP>(rb, b, gx, gy, cpm, tread, gathers)
-                            : score_beam<INTERP>(rb, b, gx, gy, cpm, gread, gathers);
-            }
+            for (int j = sub; j < a.num_beams; j += G)
+                acc += score_beam<INTERP, TILE, COUNT>(rb, sbeams[j], gc, win, a.grid, gathers);
         }
 #pragma unroll
         for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
