@@ -100,6 +100,7 @@ struct mcl_engine {
     uint32_t update_no = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
+    int collectives = 0;
 };
 
 namespace {
@@ -182,6 +183,38 @@ int seq_total(mcl_engine* h, const double* w, bool materialize)
         CKL(h);
     }
     return MCL_OK;
+}
+
+// ---- multi-GPU slice exchange: every rank contributes buf[lo_r, hi_r) and ends with the complete array ------------------
+// In place on the engine's stream (no host synchronisation).  Equal slices use ncclAllGather; ragged ones a group of
+// broadcasts.  These are the only collectives of an update: 3 x 4 B/particle of poses and 4 B/particle of scores.
+int exchange_slices(mcl_engine* h, void* buf, size_t elem)
+{
+    if (h->world == 1) return MCL_OK;
+#ifdef MCL_WITH_NCCL
+    char* base = (char*)buf;
+    ncclResult_t rc;
+    if (h->n % h->world == 0) {
+        const size_t count = (size_t)(h->n / h->world) * elem;
+        rc = ncclAllGather(base + (size_t)h->lo * elem, base, count, ncclChar, h->comm, h->stream);
+    } else {
+        ncclGroupStart();
+        rc = ncclSuccess;
+        for (int r = 0; r < h->world && rc == ncclSuccess; ++r) {
+            const long long lo = h->n * r / h->world, hi = h->n * (r + 1) / h->world;
+            rc = ncclBroadcast(base + (size_t)lo * elem, base + (size_t)lo * elem, (size_t)(hi - lo) * elem, ncclChar, r,
+                               h->comm, h->stream);
+        }
+        ncclResult_t rc2 = ncclGroupEnd();
+        if (rc == ncclSuccess) rc = rc2;
+    }
+    if (rc != ncclSuccess) return fail(h, MCL_ERR_COMM, "NCCL slice exchange failed: %s", ncclGetErrorString(rc));
+    ++h->collectives;
+    return MCL_OK;
+#else
+    (void)buf; (void)elem;
+    return fail(h, MCL_ERR_COMM, "library built without NCCL");
+#endif
 }
 
 // ---- scan preparation (host): valid-beam compaction + interpolation ratios ------------------
@@ -334,6 +367,8 @@ int run_score(mcl_engine* h)
     else
         rc = tile ? launch_score_it<false, true>(h, G, a, smem, blocks) : launch_score_it<false, false>(h, G, a, smem, blocks);
     if (rc) return rc;
+    rc = exchange_slices(h, h->score2, sizeof(int32_t));
+    if (rc) return rc;
     h->stats.lanes_per_particle = G;
     h->stats.map_tile_used = tile ? 2 : 1;
     h->stats.evals = local * (long long)h->num_beams;
@@ -384,6 +419,11 @@ int run_action(mcl_engine* h, const mcl_action_t* act, int64_t utime, const floa
     a.update_no = h->update_no;
     action_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(a);
     CKL(h);
+    // every rank needs the complete new cloud: the next resampling gathers parents from anywhere in it
+    for (float* arr : {h->pose[dst_i].x, h->pose[dst_i].y, h->pose[dst_i].th}) {
+        int rc = exchange_slices(h, arr, sizeof(float));
+        if (rc) return rc;
+    }
     h->cur = dst_i;
     // action_model.cpp:92-93: parent keeps the old pose (and its utime), pose.utime = ActionModel::utime_
     h->parent_utime = h->pose_utime;
@@ -406,8 +446,8 @@ int run_resample_indices(mcl_engine* h, double r, const double* w)
     int rc = seq_total(h, w, true);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
-    resample_search_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->cum, h->n, r, 0, h->n, h->idx,
-                                                                         h->overruns);
+    resample_search_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(h->cum, h->n, r, h->lo, h->hi,
+                                                                                 h->idx, h->overruns);
     CKL(h);
     return MCL_OK;
 }
@@ -447,6 +487,7 @@ int fetch_estimate(mcl_engine* h, int64_t utime)
 int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r, const float* noise_dev)
 {
     h->launches = 0;
+    h->collectives = 0;
     cudaEventRecord(h->ev[0], h->stream);
     int rc = run_resample_indices(h, r, h->weight[h->wcur]);
     if (rc) return rc;
@@ -464,6 +505,7 @@ int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r
     if (rc) return rc;
     cudaEventRecord(h->ev[5], h->stream);
     h->stats.kernel_launches = h->launches;
+    h->stats.collectives = h->collectives;
     ++h->update_no;
     ++h->stats.updates;
     return MCL_OK;
@@ -747,6 +789,13 @@ int mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int6
     if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
     CK(cudaSetDevice(h->device));
     const long long count = std::min<long long>(max_n, (h->n + stride - 1) / stride);
+    if (h->world > 1) {   // parent poses live only on the owning rank: collective call in multi-GPU mode
+        const PoseSoA& q = h->parent[h->cur];
+        for (float* arr : {q.x, q.y, q.th}) {
+            int rc = exchange_slices(h, arr, sizeof(float));
+            if (rc) return rc;
+        }
+    }
     if (count > 0) {
         int rc = ensure_staging(h, sizeof(mcl_particle_t) * (size_t)count);
         if (rc) return rc;

@@ -557,7 +557,7 @@ __global__ void init_uniform_kernel(float* x, float* y, float* th, float* px, fl
 }
 
 // AoS particle_t <-> SoA
-struct AosParticle { long long utime; float x, y, th; long long putime; float px, py, pth; double w; };
+struct AosParticle { long long utime; float x, y, th; int pad0; long long putime; float px, py, pth; int pad1; double w; };
 static_assert(sizeof(AosParticle) == 56, "particle_t layout");
 
 __global__ void aos_to_soa_kernel(const AosParticle* aos, long long n, float* x, float* y, float* th, float* px,
@@ -576,8 +576,8 @@ __global__ void soa_to_aos_kernel(AosParticle* aos, long long count, long long s
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count; k += (long long)gridDim.x * blockDim.x) {
         const long long i = k * stride;
         AosParticle p;
-        p.utime = utime; p.x = x[i]; p.y = y[i]; p.th = th[i];
-        p.putime = putime; p.px = px[i]; p.py = py[i]; p.pth = pth[i];
+        p.utime = utime; p.x = x[i]; p.y = y[i]; p.th = th[i]; p.pad0 = 0;     // padding bytes exported as zeros
+        p.putime = putime; p.px = px[i]; p.py = py[i]; p.pth = pth[i]; p.pad1 = 0;
         p.w = w[i];
         aos[k] = p;
     }

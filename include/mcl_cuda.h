@@ -71,7 +71,8 @@ typedef struct {
     int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
     int     map_tile_used;        /* 1 = L2/global gathers, 2 = shared-memory tile */
     int     kernel_launches;      /* kernels launched by the last mcl_update */
-    int     reserved[5];
+    int     collectives;          /* NCCL slice exchanges enqueued by the last mcl_update (0 on one GPU) */
+    int     reserved[4];
 } mcl_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
@@ -107,6 +108,7 @@ int  mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed);
  * pose.utime and one parent_pose.utime (true for every cloud the reference produces).  Export writes
  * min(max_n, ceil(N/stride)) particles: every stride-th one. */
 int  mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n);
+/* With mcl_comm_init'd engines export is COLLECTIVE (every rank calls it): parent poses are exchanged first. */
 int  mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int64_t stride, int64_t* n_out);
 
 /* ---- host-side scalar part of the action model: ActionModel::updateAction (action_model.cpp:22-75) ------------- */
