@@ -195,6 +195,8 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n, grid, truth, scans = build_workload(args.config)
+    if args.particles:
+        n = args.particles
     e = engine.Engine(n, device=local_rank, lanes_per_particle=args.lanes, map_tile=args.tile)
     if world > 1:
         if rank == 0:
@@ -205,7 +207,11 @@ def run_engine(args):
         e.comm_init(bytes(uid.cpu().tolist()), rank, world)
     e.set_map(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
     pose0, r0, th0, t0 = scans[0]
-    e.init_at_pose(*pose0, utime=int(t0[0]), seed=42)
+    uniform = args.config == "config5" or args.uniform     # global localisation: uniformly initialised cloud
+    if uniform:
+        e.init_uniform(utime=int(t0[0]), seed=42)
+    else:
+        e.init_at_pose(*pose0, utime=int(t0[0]), seed=42)
     am = engine.ActionModel()
     am.update(*pose0, int(t0[0]))
 
@@ -253,6 +259,8 @@ def run_engine(args):
     score_ms, stage_ms, evals_e2e, launches = [], [], 0, 0
     for _ in range(args.steps):
         r, th, t, ut = next_inputs()
+        if uniform:
+            e.init_uniform(utime=ut - 100_000, seed=1000 + step_no[0])   # every step scores a fresh uniform cloud
         e.update(am, ut, r, th, t, 0.5 / n)
         st = e.stats()
         score_ms.append(st["ms_score"])
@@ -271,7 +279,9 @@ def run_engine(args):
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record(stream)
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        if uniform:
+            e.init_uniform(utime=ut - 100_000, seed=2000 + k)
         e.update_enqueue(am, ut)
     ev3.record(stream)
     barrier()
@@ -284,6 +294,8 @@ def run_engine(args):
     e.set_gather_counting(True)
     local_n = e.stats()["local_particles"]
     r, th, t, ut = next_inputs()
+    if uniform:
+        e.init_uniform(utime=ut - 100_000, seed=3000)
     e.update(am, ut, r, th, t, 0.5 / n)
     st = e.stats()
     e.set_gather_counting(False)
@@ -303,7 +315,9 @@ def run_engine(args):
             "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic), int32 scores, int8 map",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {n} particles x 360 beams ({valid} valid), "
-                                   f"{grid.width}x{grid.height} int8 grid, tracking cloud",
+                                   f"{grid.width}x{grid.height} int8 grid, "
+                                   + ("uniform cloud re-initialised every step (global localisation)" if uniform
+                                      else "tracking cloud"),
                        "updates_per_sec": args.steps / (res_ms * 1e-3),
                        "l2_policy": "inputs larger than L2: 28 B/particle of pose+parent+score state streams from HBM "
                                     f"every step ({28 * n / 1e6:.0f} MB); the int8 map is L2/shared-memory resident by design",
@@ -349,6 +363,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--uniform", action="store_true", help="uniform cloud (global localisation) on any config")
+    ap.add_argument("--particles", type=int, default=0, help="override the config's particle count")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":

@@ -115,6 +115,46 @@ __device__ __constant__ double gs_k[10] = {GS_HPI_INV, GS_HPI, GS_S1, GS_S2, GS_
 #define GS_K(i, lit) (lit)
 #endif
 
+#if defined(__CUDACC__)
+// The hot loop keeps the ten constants in registers: gs_load_consts() reads them once per thread through volatile
+// loads, which the compiler cannot rematerialise (as immediates or constant-bank loads) inside the loop.
+struct GsConsts { double hpi_inv, hpi, s1, s2, s3, c0, c1, c2, c3, c4; };
+__device__ double gs_kg[10] = {GS_HPI_INV, GS_HPI, GS_S1, GS_S2, GS_S3, GS_C0, GS_C1, GS_C2, GS_C3, GS_C4};
+__device__ __forceinline__ GsConsts gs_load_consts()
+{
+    // volatile global loads: neither NVVM nor ptxas may re-issue them, so the values stay in registers
+    const volatile double* p = gs_kg;
+    GsConsts k = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9]};
+    return k;
+}
+// Same arithmetic as glibc_sincosf_core with the constants passed in.
+__device__ __forceinline__ void glibc_sincosf_regs(const GsConsts& k, float xf, float* sinp, float* cosp)
+{
+    const double x = (double)xf;
+    const double r = __dmul_rn(x, k.hpi_inv);
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    const double xr = __fma_rn(-(double)n, k.hpi, x);
+    const double x2 = __dmul_rn(xr, xr);
+    const double x3 = __dmul_rn(x2, xr);
+    const double x4 = __dmul_rn(x2, x2);
+    const double s1 = __fma_rn(x2, k.s3, k.s2);
+    const double c2 = __fma_rn(x2, k.c4, k.c3);
+    const double c1 = __fma_rn(x2, k.c1, k.c0);
+    const double x5 = __dmul_rn(x2, x3);
+    const double x6 = __dmul_rn(x2, x4);
+    const double s = __fma_rn(x3, k.s1, xr);
+    const double c = __fma_rn(x4, k.c2, c1);
+    const float sv = (float)__fma_rn(x5, s1, s);
+    const float cv = (float)__fma_rn(x6, c2, c);
+    const uint32_t sbit = ((uint32_t)(n + 1) & 2u) << 30;
+    const uint32_t cbit = ((uint32_t)n & 2u) << 30;
+    const float ss = __uint_as_float(__float_as_uint(sv) ^ sbit);
+    const float cc = __uint_as_float(__float_as_uint(cv) ^ cbit);
+    *sinp = (n & 1) ? cc : ss;
+    *cosp = (n & 1) ? ss : cc;
+}
+#endif
+
 // _core differs from glibc in exactly one input: x = -0.0f yields sin = +0.0f instead of -0.0f (the polynomial's
 // x3*S1 term is +0).  The sensor model only ever truncates range*sin*cpm + start to an int, where the sign of a zero
 // cannot matter, so the hot loop uses _core; glibc_sincosf_fast adds the one select that makes it exact everywhere.

@@ -115,6 +115,7 @@ struct Window {
 struct GridConst {
     double gx, gy, cpm_d;
     float cpm;
+    GsConsts trig;     // sincosf constants held in registers
 };
 
 // One particle-beam evaluation: moving_laser_scan.cpp:26-33 + sensor_model.cpp:28-59.  Returns the ray score in
@@ -174,31 +175,40 @@ __device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const
     const float sx = (float)__dmul_rn(__dsub_rn((double)ox, gc.gx), gc.cpm_d);
     const float sy = (float)__dmul_rn(__dsub_rn((double)oy, gc.gy), gc.cpm_d);
     float s, c;
-    glibc_sincosf_core(th, &s, &c);
+    glibc_sincosf_regs(gc.trig, th, &s, &c);
     const float px = __fmul_rn(__fmul_rn(b.range, c), gc.cpm);                 // (range*cos)*cpm, float
     const float py = __fmul_rn(__fmul_rn(b.range, s), gc.cpm);
-    // one guard for every conversion below: NaN or anything >= 2^27 fails it
-    const float mag = __fadd_rn(__fadd_rn(fabsf(sx), fabsf(sy)), __fadd_rn(fabsf(px), fabsf(py)));
-    const int ex = __float2int_rz(__fadd_rn(px, sx));                          // sensor_model.cpp:34
-    const int ey = __float2int_rz(__fadd_rn(py, sy));                          // :35
-    const int tx = ex - win.x0, ty = ey - win.y0;
-    const bool small = mag < 134217728.0f;
+    const float e1x = __fadd_rn(px, sx);                                       // sensor_model.cpp:34 (before truncation)
+    const float e1y = __fadd_rn(py, sy);                                       // :35
+    // One guard for every conversion below: the robot cell and the endpoint must be non-negative and below 2^22.
+    // As unsigned bit patterns that is a single compare (negative values, -0, NaN and infinities all exceed it).
+    const unsigned gmax = max(max(__float_as_uint(sx), __float_as_uint(sy)), max(__float_as_uint(e1x), __float_as_uint(e1y)));
+    const bool small = gmax < 0x4A800000u;
+    // Truncation of a non-negative float below 2^23 without the conversion unit: a round-toward-zero add of 2^23 leaves
+    // floor(v) in the mantissa, so the bit pattern is 0x4B000000 + (int)v.
+    const int bex = __float_as_int(__fadd_rz(e1x, 8388608.0f));
+    const int bey = __float_as_int(__fadd_rz(e1y, 8388608.0f));
+    const int bsx = __float_as_int(__fadd_rz(sx, 8388608.0f));
+    const int bsy = __float_as_int(__fadd_rz(sy, 8388608.0f));
+    const int tx = bex - (0x4B000000 + win.x0), ty = bey - (0x4B000000 + win.y0);
     const bool fast = small && ((unsigned)(tx - 1) < (unsigned)(win.w - 2)) && ((unsigned)(ty - 1) < (unsigned)(win.h - 2));
     if (__builtin_expect(!fast, 0)) {
+        const int ex = f2i_x86(e1x), ey = f2i_x86(e1y);
         // endpoint two or more cells outside the grid: it and both neighbours read 0 (occupancy_grid.cpp:65-70)
-        if (small && ((unsigned)(ex + 1) > (unsigned)(grid.width + 1) || (unsigned)(ey + 1) > (unsigned)(grid.height + 1))) {
+        // (holds for any robot cell / extended point, even INT_MIN ones: a Bresenham step moves at most one cell)
+        if ((unsigned)(ex + 1) > (unsigned)(grid.width + 1) || (unsigned)(ey + 1) > (unsigned)(grid.height + 1)) {
             if (COUNT) gathers += 3;
             return 0;
         }
         return slow_ray(grid, px, py, sx, sy, &gathers);
     }
-    // :37-38  ((2*range)*cos)*cpm == 2*px exactly (power-of-two scaling commutes with rounding)
+    // :37-38  ((2*range)*cos)*cpm == 2*px exactly (power-of-two scaling commutes with rounding); may be negative
     const int xx = __float2int_rz(__fadd_rn(__fmul_rn(2.0f, px), sx));
     const int xy = __float2int_rz(__fadd_rn(__fmul_rn(2.0f, py), sy));
     const int idx = ty * win.pitch + tx;
     const int odds = window_read<SMEM>(win, idx);                              // :41
-    const int off1 = step_offset(ex, ey, __float2int_rz(sx), __float2int_rz(sy), win.pitch);   // :48 toward the robot
-    const int off2 = step_offset(ex, ey, xx, xy, win.pitch);                   // :49 away from the robot
+    const int off1 = step_offset(bex, bey, bsx, bsy, win.pitch);               // :48 toward the robot (same bias on both)
+    const int off2 = step_offset(bex - 0x4B000000, bey - 0x4B000000, xx, xy, win.pitch);   // :49 away from the robot
     int o1 = 0, o2 = 0;
     if (odds <= 0) {
         o1 = window_read<SMEM>(win, idx + off1);

@@ -257,23 +257,26 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
 
 // ---- sensor-model launch ---------------------------------------------------------------------------------------------
 template <int G, bool INTERP, bool TILE>
-int launch_score_g(mcl_engine* h, const ScoreArgs& a, size_t smem, int blocks)
+int launch_score_g(mcl_engine* h, const ScoreArgs& a, size_t smem, long long want_blocks)
 {
-    if (h->count_gathers) {
-        auto k = score_kernel<G, INTERP, TILE, true>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, 256, smem, h->stream>>>(a);
-    } else {
-        auto k = score_kernel<G, INTERP, TILE, false>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, 256, smem, h->stream>>>(a);
-    }
+    // persistent CTAs: exactly one resident wave (SMs x CTAs that really fit: registers and shared memory)
+    auto launch = [&](auto kernel) -> int {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem));
+        per_sm = std::max(per_sm, 1);
+        const int blocks = (int)std::max<long long>(1, std::min<long long>(want_blocks, (long long)h->sm_count * per_sm));
+        kernel<<<blocks, 256, smem, h->stream>>>(a);
+        return MCL_OK;
+    };
+    int rc = h->count_gathers ? launch(score_kernel<G, INTERP, TILE, true>) : launch(score_kernel<G, INTERP, TILE, false>);
+    if (rc) return rc;
     CKL(h);
     return MCL_OK;
 }
 
 template <bool INTERP, bool TILE>
-int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, size_t smem, int blocks)
+int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, size_t smem, long long blocks)
 {
     switch (G) {
         case 1: return launch_score_g<1, INTERP, TILE>(h, a, smem, blocks);
@@ -355,11 +358,8 @@ int run_score(mcl_engine* h)
             return fail(h, MCL_ERR_INVALID, "map_tile=2 forced but the cloud's window does not fit in shared memory");
     }
 
-    // persistent CTAs: a multiple of the SM count, as many as the shared-memory footprint allows per SM
-    int per_sm = tile ? std::max(1, std::min(8, (int)((size_t)(h->max_smem_optin + 1024) / (smem + 1024)))) : 8;
     const int ppb = 256 / G;
-    long long want = (local + ppb - 1) / ppb;
-    int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * per_sm));
+    const long long blocks = (local + ppb - 1) / ppb;      // upper bound; the launcher clamps to one resident wave
 
     int rc;
     if (h->scan_interp)

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256, 2) score_kernel(const ScoreArgs a)
     GridConst gc;
     gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
     gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
+    gc.trig = gs_load_consts();
 
     constexpr int PPB = 256 / G;                 // particles per CTA per iteration
     const int sub = threadIdx.x % G;
@@ -633,8 +634,14 @@ __global__ void gather_peak_kernel(const int8_t* buf, unsigned long long mask, l
 
 __global__ void debug_sincosf_kernel(const float* x, long long n, float* s, float* c)
 {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        glibc_sincosf(x[i], s + i, c + i);
+    // the exact variant the sensor kernel runs, plus the signed-zero fix-up of glibc_sincosf_fast
+    const GsConsts k = gs_load_consts();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float sv, cv;
+        glibc_sincosf_regs(k, x[i], &sv, &cv);
+        s[i] = (x[i] == 0.0f) ? x[i] : sv;
+        c[i] = cv;
+    }
 }
 
 }  // namespace mcl
