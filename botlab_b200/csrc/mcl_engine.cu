@@ -58,6 +58,7 @@ struct mcl_engine {
     // sequential-sum workspace
     long long n1 = 0, n2 = 0;
     double *cum = nullptr, *sums = nullptr, *cin1 = nullptr, *cin2 = nullptr, *total = nullptr;
+    double *tile_sums = nullptr, *tile_excl = nullptr;
     int *ebias = nullptr, *gebias = nullptr, *opened = nullptr;
     long long *q0 = nullptr, *q1 = nullptr, *g0 = nullptr, *g1 = nullptr, *fallbacks = nullptr;
     unsigned long long* overruns = nullptr;
@@ -163,11 +164,11 @@ int seq_total(mcl_engine* h, const double* w, bool materialize)
 {
     const long long n = h->n, n1 = h->n1, n2 = h->n2;
     const int tiles = (int)((n1 + kSeqTileChunks - 1) / kSeqTileChunks);
-    seq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums);
+    seq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums, h->tile_sums);
     CKL(h);
-    seq_scan_classify_kernel<<<1, 1024, 0, h->stream>>>(h->sums, n1, h->ebias);
+    seq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tiles, h->tile_excl);
     CKL(h);
-    seq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->ebias, h->q0, h->q1);
+    seq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums, h->tile_excl, h->ebias, h->q0, h->q1);
     CKL(h);
     seq_group_maps_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->ebias, h->q0, h->q1, n1, n2, h->gebias,
                                                                           h->g0, h->g1);
@@ -519,6 +520,7 @@ void free_all(mcl_engine* h)
         F(h->parent[b].x); F(h->parent[b].y); F(h->parent[b].th);
         F(h->weight[b]);
     }
+    F(h->tile_sums); F(h->tile_excl);
     F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
     F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter);
     F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
@@ -602,6 +604,8 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMalloc((void**)&h->cum, 8 * n));
     const size_t n1 = (size_t)h->n1, n2 = (size_t)h->n2;
     CKB(cudaMalloc((void**)&h->sums, 8 * n1)); CKB(cudaMalloc((void**)&h->cin1, 8 * n1));
+    CKB(cudaMalloc((void**)&h->tile_sums, 8 * (n1 / kSeqTileChunks + 1)));
+    CKB(cudaMalloc((void**)&h->tile_excl, 8 * (n1 / kSeqTileChunks + 1)));
     CKB(cudaMalloc((void**)&h->ebias, 4 * n1)); CKB(cudaMalloc((void**)&h->q0, 8 * n1));
     CKB(cudaMalloc((void**)&h->q1, 8 * n1));
     CKB(cudaMalloc((void**)&h->cin2, 8 * n2)); CKB(cudaMalloc((void**)&h->gebias, 4 * n2));

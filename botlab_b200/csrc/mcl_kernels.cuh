@@ -276,34 +276,38 @@ __device__ __forceinline__ void seq_stage(const double* w, long long n, long lon
     }
 }
 
-// S1: plain per-chunk sums (approximate prefix only steers the binade guess).
-__global__ void __launch_bounds__(128) seq_chunk_sums_kernel(const double* w, long long n, long long n1, double* sums)
+// S1: plain per-chunk sums and per-tile totals (approximate: they only steer the binade guess).
+__global__ void __launch_bounds__(128) seq_chunk_sums_kernel(const double* w, long long n, long long n1, double* sums,
+                                                             double* tile_sums)
 {
     __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
     const long long chunk0 = (long long)blockIdx.x * kSeqTileChunks;
     seq_stage(w, n, chunk0 * kL1, tile);
     __syncthreads();
-    if (threadIdx.x < kSeqTileChunks && chunk0 + threadIdx.x < n1) {
-        const double* row = tile + threadIdx.x * kSeqRowPitch;
+    if (threadIdx.x < kSeqTileChunks) {                 // warp 0: one lane per chunk
         double s = 0.0;
+        if (chunk0 + threadIdx.x < n1) {
+            const double* row = tile + threadIdx.x * kSeqRowPitch;
 #pragma unroll 8
-        for (int i = 0; i < kL1; ++i) s += row[i];
-        sums[chunk0 + threadIdx.x] = s;
+            for (int i = 0; i < kL1; ++i) s += row[i];
+            sums[chunk0 + threadIdx.x] = s;
+        }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
     }
 }
 
-// S2: exclusive scan of the chunk sums (single CTA) and the binade guess per chunk:
-// ebias[k] = biased exponent shared by the whole chunk's running sum, or 0 = "walk it serially".
-__global__ void __launch_bounds__(1024) seq_scan_classify_kernel(const double* sums, long long n1, int* ebias)
+// S2: exclusive scan of the per-tile totals (single CTA; a tile is 32 chunks, so this is N/4096 values).
+__global__ void __launch_bounds__(1024) seq_tile_scan_kernel(const double* tile_sums, long long ntiles, double* tile_excl)
 {
     __shared__ double warp_tot[32];
     __shared__ double carry_s;
     if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (long long base = 0; base < n1; base += 1024) {
+    for (long long base = 0; base < ntiles; base += 1024) {
         const long long k = base + threadIdx.x;
-        const double v = k < n1 ? sums[k] : 0.0;
+        const double v = k < ntiles ? tile_sums[k] : 0.0;
         double inc = v;
         for (int off = 1; off < 32; off <<= 1) {
             const double t = __shfl_up_sync(0xffffffffu, inc, off);
@@ -320,14 +324,8 @@ __global__ void __launch_bounds__(1024) seq_scan_classify_kernel(const double* s
             warp_tot[lane] = t;
         }
         __syncthreads();
-        const double carry = carry_s;
-        const double incl = carry + (wid ? warp_tot[wid - 1] : 0.0) + inc;
-        const double excl = incl - v;
-        if (k < n1) {
-            const double lo = excl * (1.0 - 1e-6), hi = incl * (1.0 + 1e-6);
-            const int elo = dbl_exp(lo), ehi = dbl_exp(hi);
-            ebias[k] = (lo > 0.0 && elo == ehi && elo > 60 && elo < 2000) ? elo : 0;
-        }
+        const double incl = carry_s + (wid ? warp_tot[wid - 1] : 0.0) + inc;
+        if (k < ntiles) tile_excl[k] = incl - v;
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = incl;
         __syncthreads();
@@ -336,7 +334,11 @@ __global__ void __launch_bounds__(1024) seq_scan_classify_kernel(const double* s
 
 // S3: per level-1 chunk, Q[p] = (c_out - c_in)/ulp for entry parity p, from two real double-add chains started at the
 // binade's two representatives.  A chain that leaves the binade invalidates the chunk (ebias := 0).
-__global__ void __launch_bounds__(128) seq_chunk_maps_kernel(const double* w, long long n, long long n1, int* ebias,
+// The binade guess comes first: ebias[k] = biased exponent shared by the chunk's whole running sum according to the
+// approximate prefix (tile prefix + warp scan of the tile's chunk sums, with a 1e-6 relative safety margin), or 0 =
+// "walk it serially".
+__global__ void __launch_bounds__(128) seq_chunk_maps_kernel(const double* w, long long n, long long n1,
+                                                             const double* sums, const double* tile_excl, int* ebias,
                                                              long long* q0, long long* q1)
 {
     __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
@@ -344,9 +346,19 @@ __global__ void __launch_bounds__(128) seq_chunk_maps_kernel(const double* w, lo
     seq_stage(w, n, chunk0 * kL1, tile);
     __syncthreads();
     const long long k = chunk0 + threadIdx.x;
-    if (threadIdx.x < kSeqTileChunks && k < n1) {
-        const int e = ebias[k];
-        if (e != 0) {
+    if (threadIdx.x < kSeqTileChunks) {                 // warp 0, all 32 lanes (shuffles below)
+        const double v = k < n1 ? sums[k] : 0.0;
+        double inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)threadIdx.x >= off) inc += t;
+        }
+        const double incl = tile_excl[blockIdx.x] + inc, excl = incl - v;
+        const double lo = excl * (1.0 - 1e-6), hi = incl * (1.0 + 1e-6);
+        const int elo = dbl_exp(lo), ehi = dbl_exp(hi);
+        const int e = (lo > 0.0 && elo == ehi && elo > 60 && elo < 1900) ? elo : 0;
+        if (k < n1) ebias[k] = e;
+        if (k < n1 && e != 0) {
             const double base0 = __longlong_as_double((long long)e << 52);
             const double ulp = __longlong_as_double((long long)(e - 52) << 52);
             const double base1 = base0 + ulp;
@@ -405,7 +417,48 @@ __device__ __forceinline__ bool seq_apply(double& c, int e, long long m0, long l
     return true;
 }
 
-// S5: the serial walk (one warp; all lanes compute the same chain so shuffles broadcast staged values).
+// Composition of two "add D[parity]" maps: first a, then b.
+__device__ __forceinline__ void seq_compose(long long a0, long long a1, long long b0, long long b1, long long& r0,
+                                            long long& r1)
+{
+    r0 = a0 + ((a0 & 1) ? b1 : b0);
+    r1 = a1 + (((a1 + 1) & 1) ? b1 : b0);
+}
+
+// Tries to advance the exact running sum c over 32 consecutive maps at once (lane l holds map l: exponent e_l and
+// (m0_l, m1_l); lanes >= cnt hold identity maps).  Succeeds iff every map assumes c's binade and the sum stays inside it
+// through the last one; then cin_l = exact running sum at the entry of map l and c = sum after the last map.
+__device__ __forceinline__ bool seq_apply_warp(double& c, int cnt, int e_l, long long m0_l, long long m1_l, double& cin_l)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = dbl_exp(c);
+    const bool mine_ok = lane >= cnt || (e_l == e && e_l != 0);
+    if (!__all_sync(0xffffffffu, mine_ok)) return false;
+    long long p0 = lane < cnt ? m0_l : 0, p1 = lane < cnt ? m1_l : 0;      // inclusive prefix composition
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const long long q0 = __shfl_up_sync(0xffffffffu, p0, off), q1 = __shfl_up_sync(0xffffffffu, p1, off);
+        if (lane >= off) {
+            long long r0, r1;
+            seq_compose(q0, q1, p0, p1, r0, r1);
+            p0 = r0; p1 = r1;
+        }
+    }
+    const long long bits = __double_as_longlong(c);
+    const long long incl = bits + ((bits & 1) ? p1 : p0);
+    long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = bits;
+    // monotone: if the last sum is still in the binade, all are
+    const long long last = __shfl_sync(0xffffffffu, incl, 31);
+    if (((last >> 52) & 0x7ff) != e || last < bits) return false;
+    cin_l = __longlong_as_double(excl);
+    c = __longlong_as_double(last);
+    return true;
+}
+
+// S5: the walk over the level-2 groups (one warp).  Runs of groups that stay inside one binade advance 32 at a time
+// (seq_apply_warp); the rest one by one, opening a group into its level-1 chunks where its map does not apply and
+// adding raw elements where a chunk's does not.  All lanes carry the same c, so shuffles broadcast staged values.
 // Produces the exact running sum at the entry of every level-2 group (cin2), of every level-1 chunk of groups that
 // had to be opened (cin1, flagged in opened[j]), the exact total, and the number of chunks that took raw adds.
 __global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long n, long long n1, long long n2,
@@ -422,6 +475,11 @@ __global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long
         const int ge_l = jl < n2 ? gebias[jl] : 0;
         const long long g0_l = jl < n2 ? g0[jl] : 0, g1_l = jl < n2 ? g1[jl] : 0;
         const int cnt = (int)(n2 - jb < 32 ? n2 - jb : 32);
+        double cin_l;
+        if (seq_apply_warp(c, cnt, ge_l, g0_l, g1_l, cin_l)) {
+            if (lane < cnt) { cin2[jl] = cin_l; opened[jl] = 0; }
+            continue;
+        }
         for (int t = 0; t < cnt; ++t) {
             const long long j = jb + t;
             const int ge = __shfl_sync(0xffffffffu, ge_l, t);
@@ -439,6 +497,10 @@ __global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long
                 const int e_l = kl < klast ? ebias[kl] : 0;
                 const long long f0_l = kl < klast ? q0[kl] : 0, f1_l = kl < klast ? q1[kl] : 0;
                 const int kc = (int)(klast - kb < 32 ? klast - kb : 32);
+                if (seq_apply_warp(c, kc, e_l, f0_l, f1_l, cin_l)) {
+                    if (lane < kc) cin1[kl] = cin_l;
+                    continue;
+                }
                 for (int s = 0; s < kc; ++s) {
                     const long long k = kb + s;
                     const int e = __shfl_sync(0xffffffffu, e_l, s);
@@ -447,11 +509,15 @@ __global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long
                     if (seq_apply(c, e, f0, f1)) continue;
                     ++fallbacks;
                     const long long efirst = k * kL1;
-                    for (int eb = 0; eb < kL1; eb += 32) {
-                        const long long gi = efirst + eb + lane;
-                        const double v_l = gi < n ? w[gi] : 0.0;
-                        for (int u = 0; u < 32; ++u) c = __dadd_rn(c, __shfl_sync(0xffffffffu, v_l, u));
+                    double v_l[kL1 / 32];
+#pragma unroll
+                    for (int q = 0; q < kL1 / 32; ++q) {                      // all loads in flight before the adds
+                        const long long gi = efirst + q * 32 + lane;
+                        v_l[q] = gi < n ? w[gi] : 0.0;
                     }
+#pragma unroll
+                    for (int q = 0; q < kL1 / 32; ++q)
+                        for (int u = 0; u < 32; ++u) c = __dadd_rn(c, __shfl_sync(0xffffffffu, v_l[q], u));
                 }
             }
         }
