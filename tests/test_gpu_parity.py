@@ -401,3 +401,58 @@ def test_full_size_properties(config):
     want, _ = port.resample(wfull, rdraw)
     assert np.array_equal(idx, want)
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------ config 1 replay
+@pytest.mark.parametrize("legacy", [0, 1])
+def test_config1_replay_follows_the_reference_filter(legacy, real_map):
+    """BASELINE configs[0] in miniature: `slam --localization-only` shape -- the real 10 m x 10 m map, the reference's
+    default 200 particles (slam_main.cpp:21), 40 scans along a synthesised trajectory (the .log is not in the checkout).
+    The oracle filter draws its action noise from the libstdc++ mt19937 restatement exactly like the reference
+    (default seed 5489) and its resampling offset from the reference's unseeded rand() sequence; the engine gets the
+    same draws injected and must follow it particle for particle."""
+    n = 200
+    rng = np.random.default_rng(2026)
+    pose = (0.0, 0.0, 0.0)
+    t = 1_000_000
+    cloud = port.init_at_pose(port.Rng(99), synth.make_pose(*pose, utime=t), n)
+    pf = port.ParticleFilter(cloud)
+    mt = port.Rng(5489)                               # ActionModel's default-constructed std::mt19937
+    e = make_engine(n, real_map, legacy_equal_utime=legacy)
+    e.import_particles(cloud)
+    am = engine.ActionModel()
+    grid = port_grid(real_map)
+    first = synth.make_pose(*pose, utime=t)
+    pf.action.update(first)
+    am.update(*pose, t)
+    # glibc's rand() after srand(1): the first values of the sequence the reference consumes (particle_filter.cpp:92)
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    worst_pose, worst_w = 0.0, 0.0
+    for step in range(40):
+        pose = synth.odometry_step(rng, pose, step=(0.03 * np.cos(pose[2]), 0.03 * np.sin(pose[2]), 0.02))
+        t += 100_000
+        r, th, _ = synth.make_scan(real_map, pose, seed=step, num_beams=290)      # the simulator's beam count
+        tt = t - 100_000 + ((np.arange(290) + 1) * 100_000) // 290
+        odom = synth.make_pose(*pose, utime=t)
+        rdraw = (libc.rand() / 2147483647.0) * (1.0 / n)
+        probe = port.ActionModel()
+        probe.c = type(pf.action.c).from_buffer_copy(pf.action.c)
+        assert probe.update(odom)[0]
+        draws = probe.draws(mt, n)
+        autime = t if not legacy else 1_000_000
+        want_est, moved = pf.update(grid, odom, r, th, tt, rdraw, draws, action_utime=autime)
+        assert moved and am.update(float(odom["x"]), float(odom["y"]), float(odom["theta"]), t)
+        est = e.update(am, t, r, th, tt, rdraw, noise=draws)
+        got = e.export_particles()
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(got["parent_pose"][f], pf.particles["parent_pose"][f]), (step, f)
+            worst_pose = max(worst_pose, np.abs(got["pose"][f].astype(np.float64) - pf.particles["pose"][f]).max())
+        worst_w = max(worst_w, np.abs(got["weight"] - pf.particles["weight"]).max())
+        assert abs(est.x - float(want_est["x"])) <= POSE_TOL and abs(est.y - float(want_est["y"])) <= POSE_TOL
+        assert angle_err(est.theta, float(want_est["theta"])) <= POSE_TOL
+        # the filter tracks the truth on this map
+        assert abs(est.x - pose[0]) < 0.25 and abs(est.y - pose[1]) < 0.25
+    assert worst_pose <= POSE_TOL and worst_w <= WEIGHT_TOL
+    e.close()
