@@ -1,0 +1,34 @@
+// Mapping -- occupancy-grid update from one scan: +hit at ray endpoints, -miss along the rays, saturating int8.
+// Same interface as the reference's src/slam/mapping.hpp:25-34.  It stays on the host, as in the reference: it writes
+// the map the particle filter reads, and OccupancyGrid's dirty rectangle carries those writes to the device mirror.
+#ifndef B200_SLAM_MAPPING_HPP
+#define B200_SLAM_MAPPING_HPP
+
+#include <lcmtypes/pose_xyt_t.hpp>
+#include <cstdint>
+
+class OccupancyGrid;
+class lidar_t;
+struct adjusted_ray_t;
+
+class Mapping
+{
+public:
+    Mapping(float maxLaserDistance, int8_t hitOdds, int8_t missOdds);
+    void updateMap(const lidar_t& scan, const pose_xyt_t& pose, OccupancyGrid& map);
+
+private:
+    const float kMaxLaserDistance_;
+    const int8_t kHitOdds_;
+    const int8_t kMissOdds_;
+    pose_xyt_t previousPose_;
+    bool initialized_;
+
+    void endpointCell(const adjusted_ray_t& ray, const OccupancyGrid& map, float& startX, float& startY, int& cellX,
+                      int& cellY) const;
+    void raiseOdds(int x, int y, OccupancyGrid& map);
+    void lowerOdds(int x, int y, OccupancyGrid& map);
+    void clearAlongRay(int x1, int y1, int x2, int y2, OccupancyGrid& map);
+};
+
+#endif

@@ -6,7 +6,7 @@
 #include <stdexcept>
 
 ParticleFilter::ParticleFilter(int numParticles)
-: kNumParticles_(numParticles), seed_(0x6d636cULL), maxExported_(numParticles)
+: kNumParticles_(numParticles), seed_(0x6d636cULL), maxExported_(numParticles), injectedNoise_(nullptr)
 {
     if (numParticles <= 1) throw std::invalid_argument("ParticleFilter needs more than one particle");
     device_.reset(new b200::DeviceFilter(numParticles, b200::defaultDevice()));
@@ -36,7 +36,8 @@ pose_xyt_t ParticleFilter::updateFilter(const pose_xyt_t& odometry, const lidar_
         const double r = (static_cast<double>(rand()) / static_cast<double>(RAND_MAX)) * (1.0 / kNumParticles_);
         mcl_pose_t est;
         device_->check(mcl_update(device_->engine(), &actionModel_.action(), odometry.utime, laser.ranges.data(),
-                                  laser.thetas.data(), laser.times.data(), laser.num_ranges, r, nullptr, &est));
+                                  laser.thetas.data(), laser.times.data(), laser.num_ranges, r, injectedNoise_, &est));
+        injectedNoise_ = nullptr;
         posteriorPose_.x = est.x;
         posteriorPose_.y = est.y;
         posteriorPose_.theta = est.theta;
@@ -48,7 +49,11 @@ pose_xyt_t ParticleFilter::updateFilter(const pose_xyt_t& odometry, const lidar_
 pose_xyt_t ParticleFilter::updateFilterActionOnly(const pose_xyt_t& odometry)
 {
     if (actionModel_.updateAction(odometry))
-        device_->check(mcl_update_action_only(device_->engine(), &actionModel_.action(), odometry.utime, nullptr));
+    {
+        device_->check(mcl_update_action_only(device_->engine(), &actionModel_.action(), odometry.utime,
+                                              injectedNoise_));
+        injectedNoise_ = nullptr;
+    }
     posteriorPose_ = odometry;
     return posteriorPose_;
 }
@@ -71,6 +76,14 @@ particles_t ParticleFilter::particles(void) const
     out.num_particles = static_cast<int32_t>(n);
     out.utime = posteriorPose_.utime;
     return out;
+}
+
+void ParticleFilter::setParticles(const particles_t& cloud)
+{
+    if (static_cast<int>(cloud.particles.size()) != kNumParticles_)
+        throw std::invalid_argument("setParticles needs exactly numParticles particles");
+    device_->check(mcl_import_particles(device_->engine(), reinterpret_cast<const mcl_particle_t*>(cloud.particles.data()),
+                                        kNumParticles_));
 }
 
 mcl_stats ParticleFilter::stats(void) const

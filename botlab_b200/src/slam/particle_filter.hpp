@@ -45,6 +45,11 @@ public:
     /// Seeds both the device Philox stream (used from the next initializeFilterAtPose) and libc rand().
     void setSeed(uint64_t seed);
     mcl_stats stats(void) const;
+    /// Replaces the cloud (all particles must share pose.utime and parent_pose.utime).
+    void setParticles(const particles_t& cloud);
+    /// Test hook: N x (rot1, trans, rot2) action draws used by the NEXT update instead of the Philox stream
+    /// (the reference's recorded std::mt19937 draws).  The pointer must stay valid until that update returns.
+    void injectActionNoise(const float* draws3n) { injectedNoise_ = draws3n; }
 
 private:
     int kNumParticles_;
@@ -53,6 +58,7 @@ private:
     std::unique_ptr<b200::DeviceFilter> device_;
     uint64_t seed_;
     int64_t maxExported_;
+    const float* injectedNoise_;
 };
 
 #endif

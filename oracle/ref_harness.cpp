@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <deque>
+#include <limits>
 #include <random>
 #include <string>
 #include <vector>
@@ -24,6 +26,8 @@
 #include <slam/sensor_model.hpp>
 #include <slam/moving_laser_scan.hpp>
 #include <slam/occupancy_grid.hpp>
+#include <slam/mapping.hpp>
+#include <common/pose_trace.hpp>
 #undef private
 #include <lcmtypes/lidar_t.hpp>
 #include <lcmtypes/occupancy_grid_t.hpp>
@@ -317,6 +321,102 @@ void ref_pf_action_params(void* p, double* out6)
     ActionModel& a = ((ParticleFilter*)p)->actionModel_;
     out6[0] = a.rot1_; out6[1] = a.trans_; out6[2] = a.rot2_;
     out6[3] = a.rot1Std_; out6[4] = a.transStd_; out6[5] = a.rot2Std_;
+}
+
+// ---------------------------------------------------------------- headless replay of OccupancyGridSLAM's loop
+// The reference's slam.cpp cannot be compiled here (it needs LCM), so its data flow (slam.cpp:88-291) is restated
+// around the reference's OWN ParticleFilter, Mapping, PoseTrace, MovingLaserScan and OccupancyGrid objects.  Same
+// signature as b200_replay_run (botlab_b200/src/slam/replay_c_api.cpp); noise_io receives the draws each update made.
+int ref_replay_run(const int8_t* cells, int w, int h, float ox, float oy, float mpc, int have_map, int num_particles,
+                   int mode, int hit_odds, int miss_odds, float max_laser_distance, int num_scans,
+                   const int32_t* scan_offsets, const float* ranges, const float* thetas, const int64_t* times,
+                   int num_odom, const int64_t* odom_utime, const float* odom_xyt, const float* initial_pose3,
+                   unsigned rand_seed, const void* init_cloud, float* noise_io, float* poses_out,
+                   int8_t* final_map_out, int* iterations_out, char* err, int err_len)
+{
+    (void)err; (void)err_len;
+    ParticleFilter filter(num_particles);
+    OccupancyGrid map(10.0f, 10.0f, 0.05f);                          // slam.cpp:23
+    Mapping mapper(max_laser_distance, (int8_t)hit_odds, (int8_t)miss_odds);
+    PoseTrace odometryPoses;
+    std::deque<lidar_t> incoming;
+    bool haveMap = false, haveInitializedPoses = false;
+    if (have_map) {
+        occupancy_grid_t m;
+        m.utime = 0; m.origin_x = ox; m.origin_y = oy; m.meters_per_cell = mpc; m.width = w; m.height = h;
+        m.num_cells = w * h;
+        m.cells.assign(cells, cells + (size_t)w * h);
+        map.fromLCM(m);
+        haveMap = true;
+    }
+    pose_xyt_t initialPose, previousPose, currentPose, currentOdometry;
+    initialPose.x = initial_pose3[0]; initialPose.y = initial_pose3[1]; initialPose.theta = initial_pose3[2];
+    srand(rand_seed);
+    int io = 0, is = 0, iter = 0;
+    while (io < num_odom || is < num_scans) {
+        const int64_t to = io < num_odom ? odom_utime[io] : INT64_MAX;
+        const int64_t ts = is < num_scans ? times[scan_offsets[is + 1] - 1] : INT64_MAX;
+        if (to <= ts) {                                              // handleOdometry, slam.cpp:131-141
+            pose_xyt_t o;
+            o.utime = odom_utime[io]; o.x = odom_xyt[3 * io]; o.y = odom_xyt[3 * io + 1]; o.theta = odom_xyt[3 * io + 2];
+            odometryPoses.addPose(o);
+            ++io;
+        } else {                                                     // handleLaser, slam.cpp:90-128
+            const int a = scan_offsets[is], b = scan_offsets[is + 1];
+            lidar_t s = make_scan(ranges + a, thetas + a, times + a, b - a);
+            if (!odometryPoses.empty() && odometryPoses.front().utime <= s.times.front()) incoming.push_back(s);
+            ++is;
+        }
+        // isReadyToUpdate, slam.cpp:163-188
+        while (!incoming.empty() && odometryPoses.containsPoseAtTime(incoming.front().times.front())) {
+            lidar_t scan = incoming.front();                         // copyDataForSLAMUpdate, slam.cpp:210-229
+            incoming.pop_front();
+            currentOdometry = odometryPoses.poseAt(scan.times.back());
+            if (!haveInitializedPoses) {                             // slam.cpp:232-250
+                previousPose = initialPose;
+                previousPose.utime = scan.times.front();
+                currentPose = previousPose;
+                currentPose.utime = scan.times.back();
+                haveInitializedPoses = true;
+                filter.initializeFilterAtPose(previousPose);
+                if (init_cloud) std::memcpy(filter.posterior_.data(), init_cloud, sizeof(ref_particle) * num_particles);
+                else for (auto& q : filter.posterior_) q.weight = 1.0 / num_particles;
+            }
+            bool ok = scan.num_ranges > 100;                         // slam.cpp:197
+            if (ok) {
+                if (haveMap) {                                       // updateLocalization, slam.cpp:253-271
+                    previousPose = currentPose;
+                    // the intended ActionModel::utime_ (never assigned in the reference): the odometry's utime
+                    filter.actionModel_.utime_ = currentOdometry.utime;
+                    std::mt19937 gen_before = filter.actionModel_.numberGenerator_;
+                    particle_t sentinel;
+                    sentinel.weight = std::numeric_limits<double>::infinity();
+                    if (mode == 2) {
+                        currentPose = filter.updateFilterActionOnly(currentOdometry);
+                    } else {
+                        filter.posterior_.push_back(sentinel);       // overrun guard, see ref_pf_resample
+                        currentPose = filter.updateFilter(currentOdometry, scan, map);
+                        if (!filter.actionModel_.moved_) filter.posterior_.pop_back();
+                    }
+                    if (noise_io && iter < num_scans && filter.actionModel_.moved_)
+                        replay_draws(gen_before, filter.actionModel_, num_particles,
+                                     noise_io + (size_t)iter * num_particles * 3);
+                }
+                mapper.updateMap(scan, currentPose, map);            // updateMap, slam.cpp:274-281 (always true)
+                haveMap = true;
+            }
+            if (iter < num_scans) {
+                poses_out[5 * iter + 0] = currentPose.x; poses_out[5 * iter + 1] = currentPose.y;
+                poses_out[5 * iter + 2] = currentPose.theta; poses_out[5 * iter + 3] = ok ? 1.0f : 0.0f;
+                poses_out[5 * iter + 4] = (float)(currentPose.utime % 1000000000LL) * 1e-6f;
+            }
+            ++iter;
+        }
+    }
+    *iterations_out = iter;
+    for (int y = 0; y < map.heightInCells() && y < h; ++y)
+        for (int x = 0; x < map.widthInCells() && x < w; ++x) final_map_out[(size_t)y * w + x] = map.logOdds(x, y);
+    return 0;
 }
 
 int ref_sizeof_particle(void) { return (int)sizeof(particle_t); }
