@@ -101,6 +101,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def recorded_traffic(config, world, n):
+    """DRAM bytes of one sensor-kernel launch from the committed ncu capture of this very workload, else None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(f"{config}_{world}gpu")
+        if rec and rec["particles"] == n:
+            return rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -329,7 +342,8 @@ def run_engine(args):
             "gpu_launches": launches,
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": "score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": recorded_traffic(args.config, world, n),
+                         "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "map_reads_per_launch": gathers,
                          "kernel_ms": mean_score_s * 1e3,
                          "l2_gather": {"achieved_sectors_per_s": gathers / mean_score_s,

@@ -44,9 +44,17 @@ struct mcl_engine {
 #ifdef MCL_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // peer push of pose slices over NVLink by the copy engines (no SMs), overlapped with the sensor kernel
+    std::vector<float*> peer_pose_block;         // IPC-mapped pose_block of every rank (own entry = pose_block)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_action_done = nullptr, ev_push_done = nullptr;
+    bool peer_push = false;
+    bool push_pending = false;
+    int* barrier_word = nullptr;
 
     // particle state (global-sized arrays; every rank holds the full cloud, only [lo,hi) is computed locally)
     PoseSoA pose[2], parent[2];
+    float* pose_block = nullptr;                 // one allocation behind pose[0..1].{x,y,th}: [2][3][N] floats
     int cur = 0;
     double* weight[2] = {nullptr, nullptr};
     int wcur = 0;
@@ -218,6 +226,29 @@ int exchange_slices(mcl_engine* h, void* buf, size_t elem)
 #endif
 }
 
+// Cross-rank barrier on the engine's stream (a 4-byte all-reduce), used where no other collective follows a push.
+int rank_barrier(mcl_engine* h)
+{
+    if (h->world == 1) return MCL_OK;
+#ifdef MCL_WITH_NCCL
+    if (ncclAllReduce(h->barrier_word, h->barrier_word, 1, ncclInt, ncclMax, h->comm, h->stream) != ncclSuccess)
+        return fail(h, MCL_ERR_COMM, "NCCL barrier failed");
+    return MCL_OK;
+#else
+    return fail(h, MCL_ERR_COMM, "library built without NCCL");
+#endif
+}
+
+// Orders the engine's stream after this rank's outstanding pose pushes.
+int join_pushes(mcl_engine* h)
+{
+    if (h->push_pending) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_push_done, 0));
+        h->push_pending = false;
+    }
+    return MCL_OK;
+}
+
 // ---- scan preparation (host): valid-beam compaction + interpolation ratios ------------------
 int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const int64_t* times, int nb,
                  long long t_begin, long long t_end)
@@ -368,6 +399,8 @@ int run_score(mcl_engine* h)
     else
         rc = tile ? launch_score_it<false, true>(h, G, a, smem, blocks) : launch_score_it<false, false>(h, G, a, smem, blocks);
     if (rc) return rc;
+    rc = join_pushes(h);
+    if (rc) return rc;
     rc = exchange_slices(h, h->score2, sizeof(int32_t));
     if (rc) return rc;
     h->stats.lanes_per_particle = G;
@@ -421,9 +454,26 @@ int run_action(mcl_engine* h, const mcl_action_t* act, int64_t utime, const floa
     action_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(a);
     CKL(h);
     // every rank needs the complete new cloud: the next resampling gathers parents from anywhere in it
-    for (float* arr : {h->pose[dst_i].x, h->pose[dst_i].y, h->pose[dst_i].th}) {
-        int rc = exchange_slices(h, arr, sizeof(float));
-        if (rc) return rc;
+    if (h->world > 1 && h->peer_push) {
+        // copy engines push this rank's slice of (x, y, theta) into every peer's buffer while the SMs score;
+        // the score exchange that follows waits for this rank's pushes, which makes it the cross-rank barrier
+        CK(cudaEventRecord(h->ev_action_done, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_action_done, 0));
+        const size_t off = (size_t)(3 * dst_i) * h->n + (size_t)h->lo;
+        const size_t width = (size_t)(h->hi - h->lo) * sizeof(float), pitch = (size_t)h->n * sizeof(float);
+        for (int r = 0; r < h->world; ++r) {
+            if (r == h->rank) continue;
+            CK(cudaMemcpy2DAsync(h->peer_pose_block[r] + off, pitch, h->pose_block + off, pitch, width, 3,
+                                 cudaMemcpyDeviceToDevice, h->copy_stream));
+        }
+        CK(cudaEventRecord(h->ev_push_done, h->copy_stream));
+        h->push_pending = true;
+        ++h->collectives;
+    } else {
+        for (float* arr : {h->pose[dst_i].x, h->pose[dst_i].y, h->pose[dst_i].th}) {
+            int rc = exchange_slices(h, arr, sizeof(float));
+            if (rc) return rc;
+        }
     }
     h->cur = dst_i;
     // action_model.cpp:92-93: parent keeps the old pose (and its utime), pose.utime = ActionModel::utime_
@@ -516,10 +566,15 @@ void free_all(mcl_engine* h)
 {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int b = 0; b < 2; ++b) {
-        F(h->pose[b].x); F(h->pose[b].y); F(h->pose[b].th);
         F(h->parent[b].x); F(h->parent[b].y); F(h->parent[b].th);
         F(h->weight[b]);
     }
+    for (size_t r = 0; r < h->peer_pose_block.size(); ++r)
+        if (h->peer_pose_block[r] && h->peer_pose_block[r] != h->pose_block) cudaIpcCloseMemHandle(h->peer_pose_block[r]);
+    F(h->pose_block); F(h->barrier_word);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_action_done) cudaEventDestroy(h->ev_action_done);
+    if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
     F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
     F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter);
@@ -593,8 +648,10 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     h->n1 = (h->n + kL1 - 1) / kL1;
     h->n2 = (h->n1 + kL2 - 1) / kL2;
     for (int b = 0; b < 2; ++b) {
-        CKB(cudaMalloc((void**)&h->pose[b].x, 4 * n)); CKB(cudaMalloc((void**)&h->pose[b].y, 4 * n));
-        CKB(cudaMalloc((void**)&h->pose[b].th, 4 * n));
+        if (b == 0) CKB(cudaMalloc((void**)&h->pose_block, 4 * n * 6));
+        h->pose[b].x = h->pose_block + (size_t)(3 * b + 0) * n;
+        h->pose[b].y = h->pose_block + (size_t)(3 * b + 1) * n;
+        h->pose[b].th = h->pose_block + (size_t)(3 * b + 2) * n;
         CKB(cudaMalloc((void**)&h->parent[b].x, 4 * n)); CKB(cudaMalloc((void**)&h->parent[b].y, 4 * n));
         CKB(cudaMalloc((void**)&h->parent[b].th, 4 * n));
         CKB(cudaMalloc((void**)&h->weight[b], 8 * n));
@@ -634,6 +691,7 @@ void mcl_destroy(mcl_engine* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
 #ifdef MCL_WITH_NCCL
     if (h->comm) ncclCommDestroy(h->comm);
@@ -678,6 +736,43 @@ int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
     h->lo = h->n * rank / world;
     h->hi = h->n * (rank + 1) / world;
     h->stats.local_particles = h->hi - h->lo;
+    CK(cudaMalloc((void**)&h->barrier_word, sizeof(int)));
+    CK(cudaMemset(h->barrier_word, 0, sizeof(int)));
+    // Map every peer's pose block (CUDA IPC over NVLink) so slices can be pushed by the copy engines.  All ranks must
+    // agree: if any mapping fails (or MCL_NO_PEER_PUSH is set) every rank keeps the NCCL all-gather path.
+    h->peer_pose_block.assign(world, nullptr);
+    h->peer_pose_block[rank] = h->pose_block;
+    int ok = (world > 1 && !std::getenv("MCL_NO_PEER_PUSH")) ? 1 : 0;
+    unsigned char* handles_dev = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles(world);
+    CK(cudaMalloc((void**)&handles_dev, sizeof(cudaIpcMemHandle_t) * world));
+    if (ok && cudaIpcGetMemHandle(&handles[rank], h->pose_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    CK(cudaMemcpyAsync(handles_dev + sizeof(cudaIpcMemHandle_t) * rank, &handles[rank], sizeof(cudaIpcMemHandle_t),
+                       cudaMemcpyHostToDevice, h->stream));
+    if (ncclAllGather(handles_dev + sizeof(cudaIpcMemHandle_t) * rank, handles_dev, sizeof(cudaIpcMemHandle_t), ncclChar,
+                      h->comm, h->stream) != ncclSuccess)
+        return fail(h, MCL_ERR_COMM, "NCCL handle exchange failed");
+    CK(cudaMemcpyAsync(handles.data(), handles_dev, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        h->peer_pose_block[r] = (float*)p;
+    }
+    CK(cudaMemcpyAsync(h->barrier_word, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (ncclAllReduce(h->barrier_word, h->barrier_word, 1, ncclInt, ncclMin, h->comm, h->stream) != ncclSuccess)
+        return fail(h, MCL_ERR_COMM, "NCCL agreement failed");
+    CK(cudaMemcpyAsync(&ok, h->barrier_word, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(handles_dev);
+    h->peer_push = ok != 0;
+    if (h->peer_push) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_action_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_push_done, cudaEventDisableTiming));
+    }
+    h->stats.peer_push = h->peer_push ? 1 : 0;
     return MCL_OK;
 #else
     return fail(h, MCL_ERR_COMM, "library built without NCCL");
@@ -794,6 +889,8 @@ int mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int6
     CK(cudaSetDevice(h->device));
     const long long count = std::min<long long>(max_n, (h->n + stride - 1) / stride);
     if (h->world > 1) {   // parent poses live only on the owning rank: collective call in multi-GPU mode
+        int rcj = join_pushes(h);
+        if (rcj) return rcj;
         const PoseSoA& q = h->parent[h->cur];
         for (float* arr : {q.x, q.y, q.th}) {
             int rc = exchange_slices(h, arr, sizeof(float));
@@ -889,6 +986,10 @@ int mcl_apply_action(mcl_engine* h, const mcl_action_t* a, int64_t utime, const 
     int rc = upload_noise(h, noise3n, &nd);
     if (rc) return rc;
     rc = run_action(h, a, utime, nd, false);
+    if (rc) return rc;
+    rc = join_pushes(h);
+    if (rc) return rc;
+    rc = rank_barrier(h);       // no score exchange follows here: make every rank's pushes visible before returning
     if (rc) return rc;
     ++h->update_no;
     CK(cudaStreamSynchronize(h->stream));

@@ -2,6 +2,15 @@
 #pragma once
 #include "mcl_device.cuh"
 
+#ifndef MCL_BEAM_UNROLL
+#define MCL_BEAM_UNROLL 2
+#endif
+#define MCL_PRAGMA_(x) _Pragma(#x)
+#define MCL_UNROLL(n) MCL_PRAGMA_(unroll n)
+#ifndef MCL_SCORE_MIN_CTAS
+#define MCL_SCORE_MIN_CTAS 2
+#endif
+
 namespace mcl {
 
 // =================================================================================================================
@@ -25,7 +34,7 @@ struct ScoreArgs {
 };
 
 template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(256, 2) score_kernel(const ScoreArgs a)
+__global__ void __launch_bounds__(256, MCL_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     Beam* sbeams = reinterpret_cast<Beam*>(smem);
@@ -69,7 +78,7 @@ __global__ void __launch_bounds__(256, 2) score_kernel(const ScoreArgs a)
         int acc = 0;
         if (p < a.hi) {
             const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
-#pragma unroll 2
+MCL_UNROLL(MCL_BEAM_UNROLL)
             for (int j = sub; j < a.num_beams; j += G)
                 acc += score_beam<INTERP, TILE, COUNT>(rb, sbeams[j], gc, win, a.grid, gathers);
         }

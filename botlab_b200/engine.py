@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("effective_sample_size", C.c_double), ("ms_resample", C.c_float), ("ms_action", C.c_float),
                 ("ms_score", C.c_float), ("ms_normalize", C.c_float), ("ms_estimate", C.c_float),
                 ("ms_total", C.c_float), ("lanes_per_particle", C.c_int), ("map_tile_used", C.c_int),
-                ("kernel_launches", C.c_int), ("collectives", C.c_int), ("reserved", C.c_int * 4)]
+                ("kernel_launches", C.c_int), ("collectives", C.c_int), ("peer_push", C.c_int), ("reserved", C.c_int * 3)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -71,8 +71,9 @@ typedef struct {
     int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
     int     map_tile_used;        /* 1 = L2/global gathers, 2 = shared-memory tile */
     int     kernel_launches;      /* kernels launched by the last mcl_update */
-    int     collectives;          /* NCCL slice exchanges enqueued by the last mcl_update (0 on one GPU) */
-    int     reserved[4];
+    int     collectives;          /* slice exchanges enqueued by the last mcl_update (0 on one GPU) */
+    int     peer_push;            /* 1: pose slices travel by copy-engine peer writes (CUDA IPC), else NCCL all-gather */
+    int     reserved[3];
 } mcl_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */

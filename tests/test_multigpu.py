@@ -94,4 +94,5 @@ def test_results_do_not_depend_on_gpu_count(tmp_path, particles):
         assert np.array_equal(o["cloud"]["weight"].view(np.uint64), base["cloud"]["weight"].view(np.uint64))
         assert np.array_equal(o["estimates"], base["estimates"])
         if world > 1:
-            assert int(o["collectives"]) == 4 and int(o["local"]) in (particles // world, particles // world + 1)
+            # one pose exchange (a copy-engine push; three NCCL all-gathers without CUDA IPC) + one score exchange
+            assert int(o["collectives"]) in (2, 4) and int(o["local"]) in (particles // world, particles // world + 1)
