@@ -210,7 +210,8 @@ def run_engine(args):
     n, grid, truth, scans = build_workload(args.config)
     if args.particles:
         n = args.particles
-    e = engine.Engine(n, device=local_rank, lanes_per_particle=args.lanes, map_tile=args.tile)
+    e = engine.Engine(n, device=local_rank, lanes_per_particle=args.lanes, map_tile=args.tile,
+                      sensor_path=args.sensor_path)
     if world > 1:
         if rank == 0:
             uid = torch.tensor(list(engine.comm_unique_id()), dtype=torch.uint8, device="cuda")
@@ -335,6 +336,8 @@ def run_engine(args):
                        "l2_policy": "inputs larger than L2: 28 B/particle of pose+parent+score state streams from HBM "
                                     f"every step ({28 * n / 1e6:.0f} MB); the int8 map is L2/shared-memory resident by design",
                        "lanes_per_particle": st["lanes_per_particle"], "map_tile_used": st["map_tile_used"],
+                       "sensor_path": st["sensor_path"], "deferred_fraction": st["deferred_evals"] / max(st["evals"], 1),
+                       "certification_eps_cells": st["fast_eps"],
                        "particles_per_gpu": local_n},
             "e2e": {"value": evals_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
@@ -376,6 +379,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--sensor-path", type=int, default=0, help="0 = certified float pass + exact re-evaluation, 1 = exact only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--uniform", action="store_true", help="uniform cloud (global localisation) on any config")
     ap.add_argument("--particles", type=int, default=0, help="override the config's particle count")

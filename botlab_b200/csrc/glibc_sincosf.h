@@ -122,9 +122,14 @@ struct GsConsts { double hpi_inv, hpi, s1, s2, s3, c0, c1, c2, c3, c4; };
 __device__ double gs_kg[10] = {GS_HPI_INV, GS_HPI, GS_S1, GS_S2, GS_S3, GS_C0, GS_C1, GS_C2, GS_C3, GS_C4};
 __device__ __forceinline__ GsConsts gs_load_consts()
 {
+#if !defined(MCL_PIN_CONSTS) || MCL_PIN_CONSTS
     // volatile global loads: neither NVVM nor ptxas may re-issue them, so the values stay in registers
     const volatile double* p = gs_kg;
     GsConsts k = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9]};
+#else
+    // constant-bank operands: ten fewer 64-bit registers, for builds that trade them for resident warps
+    GsConsts k = {gs_k[0], gs_k[1], gs_k[2], gs_k[3], gs_k[4], gs_k[5], gs_k[6], gs_k[7], gs_k[8], gs_k[9]};
+#endif
     return k;
 }
 // Same arithmetic as glibc_sincosf_core with the constants passed in.

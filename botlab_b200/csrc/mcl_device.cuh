@@ -39,11 +39,25 @@ __device__ __forceinline__ float wrap_to_pi(float a)
 }
 
 // common/angle_functions.hpp:78-87 / :128-138 share this fold.
+#ifndef MCL_FOLD_NOINLINE
+#define MCL_FOLD_NOINLINE 1
+#endif
+#if MCL_FOLD_NOINLINE
+// the fold is rare (headings within |dth| of +-pi): out of line, so the hot loop pays one compare and one branch
+// instead of five predicated-off issue slots
+__device__ __noinline__ double fold_pi_rare(double v) { return __dadd_rn(v, (v > 0) ? -kTwoPi : kTwoPi); }
+__device__ __forceinline__ double fold_pi(double v)
+{
+    if (__builtin_expect(fabs(v) > kPi, 0)) v = fold_pi_rare(v);
+    return v;
+}
+#else
 __device__ __forceinline__ double fold_pi(double v)
 {
     if (__builtin_expect(fabs(v) > kPi, 0)) v = __dadd_rn(v, (v > 0) ? -kTwoPi : kTwoPi);
     return v;
 }
+#endif
 
 // float -> int the way the x86-64 host does it (cvttss2si): truncate; out of range or NaN -> INT_MIN.
 __device__ __forceinline__ int f2i_x86(float v)
@@ -158,6 +172,9 @@ __device__ __forceinline__ int step_offset(int x1, int y1, int x2, int y2, int p
     return ((2 * dx >= dy) ? sx : 0) + ((dx <= 2 * dy) ? sy : 0);
 }
 
+#ifndef MCL_EAGER_NEIGHBOURS
+#define MCL_EAGER_NEIGHBOURS 1
+#endif
 template <bool INTERP, bool SMEM, bool COUNT>
 __device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const GridConst& gc, const Window& win,
                                           const DevGrid& grid, int& gathers)
@@ -210,12 +227,172 @@ __device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const
     const int off1 = step_offset(bex, bey, bsx, bsy, win.pitch);               // :48 toward the robot (same bias on both)
     const int off2 = step_offset(bex - 0x4B000000, bey - 0x4B000000, xx, xy, win.pitch);   // :49 away from the robot
     int o1 = 0, o2 = 0;
+#if MCL_EAGER_NEIGHBOURS
+    // all three reads in flight at once (the neighbours are interior to the window, so the loads are always safe);
+    // the reference's "only if odds <= 0" is restored by the select below
+    if (SMEM) {
+        o1 = window_read<SMEM>(win, idx + off1);
+        o2 = window_read<SMEM>(win, idx + off2);
+    } else
+#endif
     if (odds <= 0) {
         o1 = window_read<SMEM>(win, idx + off1);
         o2 = window_read<SMEM>(win, idx + off2);
     }
     if (COUNT) gathers += odds > 0 ? 1 : 3;
     return odds > 0 ? 2 * odds : (o1 > 0 ? o1 : max(o2, 0));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Certified fast evaluation (first pass of the sensor model).
+//
+// The literal restatement above costs ~150 issue slots per evaluation, most of them spent reproducing the reference's
+// float/double rounding sequence.  Its OUTPUT, however, is only three cell reads, selected by (a) the endpoint cell
+// (floor of two coordinates) and (b) the octant class of the ray direction (the two Bresenham steps).  Both are
+// insensitive to rounding unless a coordinate lies within the accumulated rounding error of an integer, or the
+// direction lies within that error of an octant boundary.  The fast pass evaluates the same real-valued model
+//     E = S_b + dS*rho + range*cpm*(cos, sin)(th_b + dth*rho - theta_beam)
+// in plain float arithmetic with the SFU sine/cosine, in ~60 issue slots, and CERTIFIES its result:
+//   * |fast - reference| <= eps for every coordinate, eps derived on the host from the map size, the scan's maximum
+//     range and the measured SFU error bound (mcl_engine.cu: fast_plan; DESIGN.md section 5 has the budget);
+//   * an endpoint coordinate whose distance to the nearest integer is <= eps, or that is not interior to the window and
+//     inside the grid, is NOT certain;
+//   * the reference's step is "x iff 2|ddx| >= |ddy|, y iff |ddx| <= 2|ddy|" on differences of floored coordinates,
+//     each within 1 + eps of the real difference p = range*cpm*(cos, sin); so the step is certain iff
+//     |2|px| - |py|| and |2|py| - |px|| exceed 3(1 + eps), and then the step toward the robot is the exact opposite of
+//     the step toward the extended point (which needs the extended point at non-negative coordinates, where the
+//     reference's truncation equals floor).  When the endpoint cell itself is occupied the steps are never looked at.
+// An evaluation that is not certain contributes nothing here and sets its bit in the lane's mask; the second pass
+// (score_deferred_kernel) re-evaluates exactly those with the literal restatement (score_beam).  Results are
+// therefore identical to the reference's whatever the inputs: eps only moves work between the passes.
+struct __align__(16) FastBeam {
+    float ratio;     // (float)Beam::ratio
+    float theta;
+    float rc;        // range * cells_per_meter
+    float pad;
+};
+
+struct FastPlan {
+    int enabled;
+    int fmask;           // (bits & fmask) == 0  <=>  the coordinate is within the uncertain band of an integer
+    float magic;         // 1.5*2^13 + kb/1024: a float add leaves round(v*1024) + kb in the low mantissa bits
+    float t_dir;         // 3(1 + eps) + slack: octant decisions are certain beyond this
+    float rho_lo, rho_hi;   // range of the scan's interpolation ratios
+    float max_shift;     // largest |dS| (cells) a particle may have and still take the fast pass
+    float coord_hi;      // largest robot cell coordinate the error budget covers
+    float mid_x, half_x; // certain-interior test on the endpoint: |e - mid| < half  <=>  cell inside [lc, hc)
+    float mid_y, half_y;
+    float pitch_f;       // window pitch as a float (the step offset is assembled in float)
+    int idx_bias;        // folds the fixed-point bias and the window origin into the cell index
+    int safe_idx;        // window cell (1,1): read by evaluations whose endpoint is not certain (value discarded)
+};
+
+constexpr int kFastMagicBits = 0x46400000;      // bit pattern of 12288.0f = 1.5 * 2^13
+constexpr int kFastFracBits = 10;
+// Absolute error bound of fast_sincos for |a| <= 9.5 (measured on B200 over every float in the range by
+// mcl_debug_fast_trig_error: 1.27e-6; tests/test_gpu_parity.py::test_fast_trig_error_bound re-measures it).
+constexpr float kFastTrigErr = 2.0e-6f;
+
+// Per-particle constants of the fast pass, in GLOBAL cell coordinates.
+struct FastBase {
+    float sxb, syb, thb;     // robot cell coordinate / heading at rho = 0 (or the pose itself when !INTERP)
+    float dsx, dsy, dth;     // change over rho = 0..1
+    bool ok;                 // false: every beam of this particle goes to the exact pass
+};
+
+template <bool INTERP>
+__device__ __forceinline__ FastBase make_fast_base(float xa, float ya, float tha, float xb, float yb, float thb,
+                                                   double gx, double gy, double cpm_d, const FastPlan& fp)
+{
+    FastBase f;
+    if (INTERP) {
+        f.sxb = (float)__dmul_rn(__dsub_rn((double)xb, gx), cpm_d);
+        f.syb = (float)__dmul_rn(__dsub_rn((double)yb, gy), cpm_d);
+        f.thb = thb;
+        f.dsx = (float)__dmul_rn((double)__fsub_rn(xa, xb), cpm_d);     // the reference's float difference (interpolation.hpp:39)
+        f.dsy = (float)__dmul_rn((double)__fsub_rn(ya, yb), cpm_d);
+        f.dth = (float)fold_pi(__dsub_rn((double)tha, (double)thb));    // angle_diff (:41)
+    } else {
+        f.sxb = (float)__dmul_rn(__dsub_rn((double)xa, gx), cpm_d);
+        f.syb = (float)__dmul_rn(__dsub_rn((double)ya, gy), cpm_d);
+        f.thb = tha;
+        f.dsx = 0.0f; f.dsy = 0.0f; f.dth = 0.0f;
+    }
+    // The robot's cell coordinate must stay in [1, coord_hi] over the whole sweep (truncation == floor, fixed-point
+    // range), the headings must be wrapped ones, and the particle must not jump: everything else (NaN included: the
+    // comparisons fail) is left to the exact pass.
+    const float x0 = __fmaf_rn(f.dsx, fp.rho_lo, f.sxb), x1 = __fmaf_rn(f.dsx, fp.rho_hi, f.sxb);
+    const float y0 = __fmaf_rn(f.dsy, fp.rho_lo, f.syb), y1 = __fmaf_rn(f.dsy, fp.rho_hi, f.syb);
+    const float lo = fminf(fminf(x0, x1), fminf(y0, y1)), hi = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
+    f.ok = lo >= 1.0f && hi <= fp.coord_hi && fabsf(f.dsx) <= fp.max_shift && fabsf(f.dsy) <= fp.max_shift &&
+           fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f;
+    return f;
+}
+
+// SFU sine and cosine of an angle |a| <= 9.5 rad (MUFU.SIN/COS after scaling to revolutions).
+__device__ __forceinline__ void fast_sincos(float a, float* s, float* c)
+{
+    *s = __sinf(a);
+    *c = __cosf(a);
+}
+
+// Window cell read for the fast pass: shared-memory reads go through ld.shared.s8 on a 32-bit shared address (one LDS
+// with the sign extension built in; keeps the compiler from re-deriving the value through packed 16-bit selects).
+template <bool SMEM>
+__device__ __forceinline__ int fast_read(const int8_t* __restrict__ cells, unsigned sbase, int idx)
+{
+    if (SMEM) {
+        int v;
+        asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(sbase + (unsigned)idx));
+        return v;
+    }
+    return (int)__ldg(cells + idx);
+}
+
+// One certified evaluation.  Returns true when certain; v2 is then the ray's score in half units (else 0).
+// Straight-line on purpose (bitwise &, no short-circuit): every lane runs the same ~60 instructions.
+template <bool INTERP, bool SMEM, bool COUNT>
+__device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBeam& b, const FastPlan& fp,
+                                                const int8_t* __restrict__ cells, unsigned sbase, int pitch, int& v2,
+                                                int& gathers)
+{
+    const float sx = INTERP ? __fmaf_rn(p.dsx, b.ratio, p.sxb) : p.sxb;
+    const float sy = INTERP ? __fmaf_rn(p.dsy, b.ratio, p.syb) : p.syb;
+    const float thr = INTERP ? __fmaf_rn(p.dth, b.ratio, p.thb) : p.thb;
+    float s, c;
+    fast_sincos(__fsub_rn(thr, b.theta), &s, &c);
+    const float px = __fmul_rn(b.rc, c), py = __fmul_rn(b.rc, s);
+    const float ex = __fadd_rn(px, sx), ey = __fadd_rn(py, sy);
+    // fixed point: low 10 bits = fraction (+ the band offset), the rest = cell (+ bias)
+    const int bx = __float_as_int(__fadd_rn(ex, fp.magic)), by = __float_as_int(__fadd_rn(ey, fp.magic));
+    // endpoint cell certain: not within eps of a cell boundary, interior to the window and inside the grid
+    const bool frac_ok = min((unsigned)(bx & fp.fmask), (unsigned)(by & fp.fmask)) != 0u;
+    const bool in_x = fabsf(__fsub_rn(ex, fp.mid_x)) < fp.half_x;
+    const bool in_y = fabsf(__fsub_rn(ey, fp.mid_y)) < fp.half_y;
+    const bool cell_ok = frac_ok & in_x & in_y;
+    // octant class of the direction; the extended point must not have a negative coordinate
+    const float ax = fabsf(px), ay = fabsf(py);
+    const float d1 = __fsub_rn(__fadd_rn(ax, ax), ay);      // step x iff 2|ddx| >= |ddy|
+    const float d2 = __fsub_rn(__fadd_rn(ay, ay), ax);      // step y iff |ddx| <= 2|ddy|
+    const bool dir_ok = (fminf(fabsf(d1), fabsf(d2)) > fp.t_dir) &
+                        (fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= 0.01f);
+    // step toward the extended point, assembled in float: (+-1 or 0) + (+-1 or 0) * pitch, then to an integer by a
+    // magic-number add (no conversion unit)
+    const float ux = __uint_as_float((__float_as_uint(px) & 0x80000000u) | 0x3f800000u);
+    const float uy = __uint_as_float((__float_as_uint(py) & 0x80000000u) | 0x3f800000u);
+    const float offf = __fmaf_rn(d2 > 0.0f ? uy : 0.0f, fp.pitch_f, d1 > 0.0f ? ux : 0.0f);
+    const int off = __float_as_int(__fadd_rn(offf, 12582912.0f)) - 0x4b400000;
+    const int cidx = (int)((unsigned)(by >> kFastFracBits) * (unsigned)pitch + (unsigned)(bx >> kFastFracBits) -
+                           (unsigned)fp.idx_bias);
+    const int idx = cell_ok ? cidx : fp.safe_idx;
+    const int odds = fast_read<SMEM>(cells, sbase, idx);
+    const int o1 = fast_read<SMEM>(cells, sbase, idx - off);      // toward the robot
+    const int o2 = fast_read<SMEM>(cells, sbase, idx + off);      // toward the extended point
+    const bool certain = cell_ok & ((odds > 0) | dir_ok);
+    if (COUNT) gathers += certain ? (odds > 0 ? 1 : 3) : 0;
+    const int v = odds > 0 ? 2 * odds : (o1 > 0 ? o1 : max(o2, 0));
+    v2 = certain ? v : 0;
+    return certain;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

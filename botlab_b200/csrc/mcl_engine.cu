@@ -71,6 +71,9 @@ struct mcl_engine {
     long long *q0 = nullptr, *q1 = nullptr, *g0 = nullptr, *g1 = nullptr, *fallbacks = nullptr;
     unsigned long long* overruns = nullptr;
     unsigned long long* gather_counter = nullptr;
+    unsigned long long* deferred_counter = nullptr;
+    uint32_t* masks = nullptr;          // two-pass sensor path: uncertain-beam bits, [word][virtual lane]
+    size_t masks_bytes = 0;
     double* ess_acc = nullptr;
     int* bbox = nullptr;
 
@@ -92,6 +95,8 @@ struct mcl_engine {
     Beam* beams_host = nullptr;        // pinned
     int beams_cap = 0, num_beams = 0;
     float max_range = 0.0f;
+    float max_abs_theta = 0.0f;
+    double ratio_lo = 0.0, ratio_hi = 1.0;
     bool scan_interp = false;
     bool have_scan = false;
 
@@ -104,6 +109,7 @@ struct mcl_engine {
 
     // stats
     mcl_stats stats{};
+    mutable double stats_eps = 0.0;
     bool count_gathers = false;
     uint64_t seed = 0x5eedULL;
     uint32_t update_no = 0;
@@ -267,7 +273,9 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
     const bool interp = t_begin != t_end;
     const double denom = (double)(t_end - t_begin);
     int k = 0;
-    float mx = 0.0f;
+    float mx = 0.0f, mth = 0.0f;
+    double rlo = 1.0, rhi = 1.0;
+    bool finite = true;
     for (int i = 0; i < nb; ++i) {
         if (ranges[i] > h->params.min_range) {                 // moving_laser_scan.cpp:24
             Beam b;
@@ -276,10 +284,16 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
             b.ratio = interp ? (double)(times[i] - t_begin) / denom : 1.0;
             h->beams_host[k++] = b;
             if (std::isfinite(ranges[i])) mx = std::max(mx, ranges[i]);
+            finite = finite && std::isfinite(thetas[i]);
+            mth = std::max(mth, std::fabs(thetas[i]));
+            rlo = (k == 1) ? b.ratio : std::min(rlo, b.ratio);
+            rhi = (k == 1) ? b.ratio : std::max(rhi, b.ratio);
         }
     }
     h->num_beams = k;
     h->max_range = mx;
+    h->max_abs_theta = finite ? mth : INFINITY;
+    h->ratio_lo = rlo; h->ratio_hi = rhi;
     h->scan_interp = interp;
     if (k > 0) CK(cudaMemcpyAsync(h->beams, h->beams_host, sizeof(Beam) * k, cudaMemcpyHostToDevice, h->stream));
     h->have_scan = true;
@@ -288,36 +302,110 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
 }
 
 // ---- sensor-model launch ---------------------------------------------------------------------------------------------
-template <int G, bool INTERP, bool TILE>
-int launch_score_g(mcl_engine* h, const ScoreArgs& a, size_t smem, long long want_blocks)
+// Persistent CTAs: exactly one resident wave (SMs x CTAs that really fit: registers and shared memory).
+template <class K>
+int launch_persistent(mcl_engine* h, K kernel, const ScoreArgs& a, int threads, size_t smem, long long want_blocks)
 {
-    // persistent CTAs: exactly one resident wave (SMs x CTAs that really fit: registers and shared memory)
-    auto launch = [&](auto kernel) -> int {
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem));
-        per_sm = std::max(per_sm, 1);
-        const int blocks = (int)std::max<long long>(1, std::min<long long>(want_blocks, (long long)h->sm_count * per_sm));
-        kernel<<<blocks, 256, smem, h->stream>>>(a);
-        return MCL_OK;
-    };
-    int rc = h->count_gathers ? launch(score_kernel<G, INTERP, TILE, true>) : launch(score_kernel<G, INTERP, TILE, false>);
-    if (rc) return rc;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    per_sm = std::max(per_sm, 1);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(want_blocks, (long long)h->sm_count * per_sm));
+    kernel<<<blocks, threads, smem, h->stream>>>(a);
     CKL(h);
     return MCL_OK;
 }
 
+// which: 0 = literal restatement for every beam, 1 = certified float pass, 2 = exact pass over the deferred beams
+template <int G, bool INTERP, bool TILE>
+int launch_score_g(mcl_engine* h, const ScoreArgs& a, int which, size_t smem, long long local)
+{
+    const bool cnt = h->count_gathers;
+    if (which == 1) {
+        const long long blocks = (local + MCL_FAST_THREADS / G - 1) / (MCL_FAST_THREADS / G);
+        return cnt ? launch_persistent(h, score_fast_kernel<G, INTERP, TILE, true>, a, MCL_FAST_THREADS, smem, blocks)
+                   : launch_persistent(h, score_fast_kernel<G, INTERP, TILE, false>, a, MCL_FAST_THREADS, smem, blocks);
+    }
+    const long long blocks = (local + MCL_SCORE_THREADS / G - 1) / (MCL_SCORE_THREADS / G);
+    if (which == 2)
+        return cnt ? launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, true>, a, MCL_SCORE_THREADS, smem, blocks)
+                   : launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, false>, a, MCL_SCORE_THREADS, smem, blocks);
+    return cnt ? launch_persistent(h, score_kernel<G, INTERP, TILE, true>, a, MCL_SCORE_THREADS, smem, blocks)
+               : launch_persistent(h, score_kernel<G, INTERP, TILE, false>, a, MCL_SCORE_THREADS, smem, blocks);
+}
+
 template <bool INTERP, bool TILE>
-int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, size_t smem, long long blocks)
+int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, int which, size_t smem, long long local)
 {
     switch (G) {
-        case 1: return launch_score_g<1, INTERP, TILE>(h, a, smem, blocks);
-        case 2: return launch_score_g<2, INTERP, TILE>(h, a, smem, blocks);
-        case 4: return launch_score_g<4, INTERP, TILE>(h, a, smem, blocks);
-        case 8: return launch_score_g<8, INTERP, TILE>(h, a, smem, blocks);
-        case 16: return launch_score_g<16, INTERP, TILE>(h, a, smem, blocks);
-        default: return launch_score_g<32, INTERP, TILE>(h, a, smem, blocks);
+        case 1: return launch_score_g<1, INTERP, TILE>(h, a, which, smem, local);
+        case 2: return launch_score_g<2, INTERP, TILE>(h, a, which, smem, local);
+        case 4: return launch_score_g<4, INTERP, TILE>(h, a, which, smem, local);
+        case 8: return launch_score_g<8, INTERP, TILE>(h, a, which, smem, local);
+        case 16: return launch_score_g<16, INTERP, TILE>(h, a, which, smem, local);
+        default: return launch_score_g<32, INTERP, TILE>(h, a, which, smem, local);
     }
+}
+
+int launch_score(mcl_engine* h, int G, bool tile, const ScoreArgs& a, int which, size_t smem, long long local)
+{
+    if (h->scan_interp)
+        return tile ? launch_score_it<true, true>(h, G, a, which, smem, local) : launch_score_it<true, false>(h, G, a, which, smem, local);
+    return tile ? launch_score_it<false, true>(h, G, a, which, smem, local) : launch_score_it<false, false>(h, G, a, which, smem, local);
+}
+
+// Error budget of the certified fast pass (mcl_device.cuh: score_beam_fast) for a window [x0, x0+w) x [y0, y0+hh) of
+// global cells.  All terms in cells; u = 2^-24 is the float unit roundoff; every bound is for |coordinates| <= Cm,
+// |world metres| <= Xm, ray length <= Rc cells, |dS| <= max_shift, |rho| <= rho_max, |theta_beam| <= 6.3.
+//   reference vs the real-valued model:  ox rounding (x cpm) + sx rounding + endpoint-add rounding + two product
+//     roundings + Rc x (angle roundings: theta_r, the subtraction, two wrap steps = 20u; glibc sincosf <= 1 ulp)
+//   fast pass vs the same model:  S_b rounding + fma rounding + endpoint-add rounding + dS and rho roundings + rc and
+//     product roundings + Rc x (angle roundings 32u + measured SFU error kFastTrigErr)
+// eps = 1.25 x the sum.  A coordinate is certain when it is further than eps + 2^-11 (fixed-point rounding) from an
+// integer; a direction when both octant discriminants exceed 3(1 + eps).
+FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w, long long hh, long long pitch)
+{
+    FastPlan fp{};
+    const double cpm = h->grid.cells_per_meter;
+    const double Rc = (double)h->max_range * cpm;
+    const double rho_max = std::max(std::fabs(h->ratio_lo), std::fabs(h->ratio_hi));
+    const double Cm = (double)std::max(x0 + w, y0 + hh) + 1.0;
+    // min_range * cpm >= 2.5: the endpoint is never the robot's own cell (the reference's zero-difference step rule
+    // is then out of play); pitch < 2^20: the float-assembled step offset is exact
+    const bool usable = h->params.sensor_path != 1 && h->num_beams > 0 && std::isfinite(Rc) && cpm > 0.0 &&
+                        (double)h->params.min_range * cpm >= 2.5 && h->max_abs_theta <= 6.3f && h->ratio_lo >= -1.0 &&
+                        h->ratio_hi <= 2.0 && w >= 3 && hh >= 3 && Cm <= 4090.0 && x0 >= -4 && y0 >= -4 &&
+                        pitch < (1 << 20);
+    if (!usable) return fp;
+    const double u = 5.9604644775390625e-08;
+    const double Xm = Cm / cpm + std::max(std::fabs((double)h->grid.origin_x), std::fabs((double)h->grid.origin_y));
+    const double max_shift = 64.0;
+    const double e_ref = cpm * u * Xm + 2.0 * u * Cm + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
+    const double e_apx = 3.0 * u * Cm + (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
+                         Rc * ((M_PI * (3.0 * rho_max + 1.0) + 9.5) * u + (double)kFastTrigErr);
+    const double eps = 1.25 * (e_ref + e_apx) + 1e-6;
+    const int k = (int)std::ceil(1024.0 * eps + 0.5);
+    if (k > 32) return fp;                       // the uncertain band would cover > 6 % of every cell: not worth it
+    int kb = 1;
+    while (kb < k) kb <<= 1;                     // power-of-two band: "within the band" becomes one AND
+    fp.enabled = 1;
+    fp.fmask = 1023 & ~(2 * kb - 1);
+    fp.magic = 12288.0f + (float)kb / 1024.0f;
+    fp.t_dir = (float)(3.0 * (1.0 + eps) + 4.0 * u * Rc + 1e-4);
+    fp.rho_lo = (float)h->ratio_lo; fp.rho_hi = (float)h->ratio_hi;
+    fp.max_shift = (float)max_shift;
+    fp.coord_hi = (float)(Cm - 1.0);
+    const long long lcx = std::max<long long>(x0 + 1, 0), hcx = x0 + w - 1;    // certain-interior cells [lc, hc)
+    const long long lcy = std::max<long long>(y0 + 1, 0), hcy = y0 + hh - 1;
+    if (hcx <= lcx || hcy <= lcy) { fp.enabled = 0; return fp; }
+    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = 0.5f * (float)(hcx - lcx);
+    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = 0.5f * (float)(hcy - lcy);
+    fp.pitch_f = (float)pitch;
+    const unsigned mb = (unsigned)kFastMagicBits >> kFastFracBits;
+    fp.idx_bias = (int)((mb + (unsigned)(int)y0) * (unsigned)pitch + mb + (unsigned)(int)x0);
+    fp.safe_idx = (int)pitch + 1;
+    h->stats_eps = eps;
+    return fp;
 }
 
 int run_score(mcl_engine* h)
@@ -335,7 +423,9 @@ int run_score(mcl_engine* h)
     a.beams = h->beams; a.num_beams = h->num_beams;
     a.grid = h->grid;
     a.gather_counter = h->gather_counter;
+    a.deferred_counter = h->deferred_counter;
     if (h->count_gathers) CK(cudaMemsetAsync(h->gather_counter, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->deferred_counter, 0, sizeof(unsigned long long), h->stream));
 
     // lanes per particle: enough particle groups to fill the machine (148 SMs x 8 CTAs x (256/G) slots)
     int G = h->params.lanes_per_particle;
@@ -345,7 +435,7 @@ int run_score(mcl_engine* h)
     }
 
     // shared-memory map tile: window = bounding box of the cloud (poses and parents) +- (max range + 2 cells)
-    size_t smem = (size_t)h->num_beams * sizeof(Beam);
+    size_t smem = (size_t)h->num_beams * sizeof(Beam);          // == sizeof(FastBeam) per beam
     bool tile = false;
     if (h->params.map_tile != 1 && local > 0 && h->num_beams > 0) {
         int* box = h->bbox;
@@ -377,7 +467,10 @@ int run_score(mcl_engine* h)
                 long long pitch = (tw + 3) & ~3ll;
                 if (((pitch >> 2) & 1) == 0) pitch += 4;     // odd number of 4-byte words per row: spreads rows over banks
                 const size_t bytes = (size_t)pitch * th;
-                const size_t budget = (size_t)h->max_smem_optin - smem - 1024;
+                // the exact pass of the two-pass path also holds its compaction queues in shared memory
+                const size_t extra2 = h->params.sensor_path != 1
+                                          ? deferred_smem_bytes(h->num_beams, MCL_SCORE_THREADS / 32) - smem : 0;
+                const size_t budget = (size_t)h->max_smem_optin - smem - extra2 - 1024;
                 if (bytes <= budget / (h->params.map_tile == 2 ? 1 : 2) || (h->params.map_tile == 2 && bytes <= budget)) {
                     tile = true;
                     a.tile_x0 = (int)x0; a.tile_y0 = (int)y0; a.tile_w = (int)tw; a.tile_h = (int)th;
@@ -389,15 +482,29 @@ int run_score(mcl_engine* h)
         if (h->params.map_tile == 2 && !tile)
             return fail(h, MCL_ERR_INVALID, "map_tile=2 forced but the cloud's window does not fit in shared memory");
     }
-
-    const int ppb = 256 / G;
-    const long long blocks = (local + ppb - 1) / ppb;      // upper bound; the launcher clamps to one resident wave
-
+    if (h->params.sensor_path != 1 && local > 0)
+        a.fast = tile ? fast_plan(h, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch)
+                      : fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch);
+    const bool fast = a.fast.enabled != 0;
     int rc;
-    if (h->scan_interp)
-        rc = tile ? launch_score_it<true, true>(h, G, a, smem, blocks) : launch_score_it<true, false>(h, G, a, smem, blocks);
-    else
-        rc = tile ? launch_score_it<false, true>(h, G, a, smem, blocks) : launch_score_it<false, false>(h, G, a, smem, blocks);
+    if (fast) {
+        // two passes: certified float evaluation, then the literal restatement for the beams it deferred
+        const int iters = (h->num_beams + G - 1) / G;
+        const size_t need = (size_t)((iters + 31) / 32) * (size_t)(local * G) * sizeof(uint32_t);
+        if (need > h->masks_bytes) {
+            if (h->masks) cudaFree(h->masks);
+            h->masks = nullptr; h->masks_bytes = 0;
+            CK(cudaMalloc((void**)&h->masks, need));
+            h->masks_bytes = need;
+        }
+        a.masks = h->masks;
+        rc = launch_score(h, G, tile, a, 1, smem, local);
+        if (rc) return rc;
+        const size_t smem2 = smem - (size_t)h->num_beams * sizeof(Beam) + deferred_smem_bytes(h->num_beams, MCL_SCORE_THREADS / 32);
+        rc = launch_score(h, G, tile, a, 2, smem2, local);
+    } else {
+        rc = launch_score(h, G, tile, a, 0, smem, local);
+    }
     if (rc) return rc;
     rc = join_pushes(h);
     if (rc) return rc;
@@ -405,6 +512,8 @@ int run_score(mcl_engine* h)
     if (rc) return rc;
     h->stats.lanes_per_particle = G;
     h->stats.map_tile_used = tile ? 2 : 1;
+    h->stats.sensor_path = fast ? 2 : 1;
+    h->stats.fast_eps = fast ? h->stats_eps : 0.0;
     h->stats.evals = local * (long long)h->num_beams;
     h->have_scores = true;
     return MCL_OK;
@@ -510,7 +619,9 @@ int read_counters(mcl_engine* h)
     CK(cudaMemcpyAsync(&h->host_counters[2], h->fallbacks, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->host_counters[3], h->total, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->host_counters[4], h->ess_acc, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[5], h->deferred_counter, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->stats.deferred_evals = (int64_t)h->host_counters[5];
     h->stats.resample_overruns = (int64_t)h->host_counters[0];
     h->stats.gathers = h->count_gathers ? (int64_t)h->host_counters[1] : -1;
     h->stats.seq_fallback_chunks = (int64_t)h->host_counters[2];
@@ -577,7 +688,7 @@ void free_all(mcl_engine* h)
     if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
     F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
-    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter);
+    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks);
     F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
@@ -601,6 +712,7 @@ void mcl_default_params(mcl_params* p)
     p->legacy_equal_utime = 0;
     p->lanes_per_particle = 0;
     p->map_tile = 0;
+    p->sensor_path = 0;
 }
 
 const char* mcl_last_error(const mcl_engine* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
@@ -670,6 +782,7 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMalloc((void**)&h->g1, 8 * n2));
     CKB(cudaMalloc((void**)&h->total, 8)); CKB(cudaMalloc((void**)&h->fallbacks, 8));
     CKB(cudaMalloc((void**)&h->overruns, 8)); CKB(cudaMalloc((void**)&h->gather_counter, 8));
+    CKB(cudaMalloc((void**)&h->deferred_counter, 8)); CKB(cudaMemset(h->deferred_counter, 0, 8));
     CKB(cudaMalloc((void**)&h->ess_acc, 8)); CKB(cudaMalloc((void**)&h->bbox, 16));
     CKB(cudaMemset(h->total, 0, 8)); CKB(cudaMemset(h->fallbacks, 0, 8)); CKB(cudaMemset(h->overruns, 0, 8));
     CKB(cudaMemset(h->gather_counter, 0, 8)); CKB(cudaMemset(h->ess_acc, 0, 8));
@@ -1160,6 +1273,22 @@ int mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t read
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
     *sectors_per_s_out = (double)per_thread * blocks * threads / ((double)ms * 1e-3);
+    return MCL_OK;
+}
+
+int mcl_debug_fast_trig_error(mcl_engine* h, float lo, float hi, double* max_sin_err, double* max_cos_err)
+{
+    if (!h || !max_sin_err || !max_cos_err || !(lo <= hi)) return fail(h, MCL_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    { int rc = ensure_staging(h, 16); if (rc) return rc; }
+    CK(cudaMemsetAsync(h->staging, 0, 16, h->stream));
+    fast_trig_error_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(lo, hi, (unsigned long long*)h->staging);
+    CKL(h);
+    unsigned long long bits[2];
+    CK(cudaMemcpyAsync(bits, h->staging, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(max_sin_err, &bits[0], 8);
+    std::memcpy(max_cos_err, &bits[1], 8);
     return MCL_OK;
 }
 

@@ -10,6 +10,9 @@
 #ifndef MCL_SCORE_MIN_CTAS
 #define MCL_SCORE_MIN_CTAS 2
 #endif
+#ifndef MCL_SCORE_THREADS
+#define MCL_SCORE_THREADS 256
+#endif
 
 namespace mcl {
 
@@ -31,45 +34,59 @@ struct ScoreArgs {
     DevGrid grid;
     int tile_x0, tile_y0, tile_w, tile_h, tile_pitch;   // TILE only
     unsigned long long* gather_counter;                  // COUNT only
+    FastPlan fast;                                       // two-pass path only
+    uint32_t* masks;                                     // two-pass path: [word][virtual lane] uncertain-beam bits
+    unsigned long long* deferred_counter;                // two-pass path: evaluations re-done by the exact pass
 };
 
-template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(256, MCL_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a)
+// Stages the map window of a CTA in shared memory (4-byte granules; tile_pitch and tile_x0 are multiples of 4, the
+// mirror's pitch is a multiple of 16; mirror rows are zero-padded to the pitch; outside the grid reads as 0).
+__device__ __forceinline__ void stage_tile(const ScoreArgs& a, int8_t* stile)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    Beam* sbeams = reinterpret_cast<Beam*>(smem);
-    int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(Beam));
-
-    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
-    if (TILE) {
-        // 4-byte granules; tile_pitch and tile_x0 are multiples of 4, the mirror's pitch is a multiple of 16.
-        const int words_per_row = a.tile_pitch >> 2;
-        const int total = words_per_row * a.tile_h;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int ty = i / words_per_row, tw = i - ty * words_per_row;
-            const int gx = a.tile_x0 + (tw << 2), gy = a.tile_y0 + ty;
-            uint32_t v = 0;
-            if ((unsigned)gy < (unsigned)a.grid.height && gx >= 0 && gx < a.grid.pitch)
-                v = __ldg(reinterpret_cast<const uint32_t*>(a.grid.cells + (size_t)gy * a.grid.pitch + gx));
-            reinterpret_cast<uint32_t*>(stile)[i] = v;   // mirror rows are zero-padded to the pitch
-        }
+    const int words_per_row = a.tile_pitch >> 2;
+    const int total = words_per_row * a.tile_h;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int ty = i / words_per_row, tw = i - ty * words_per_row;
+        const int gx = a.tile_x0 + (tw << 2), gy = a.tile_y0 + ty;
+        uint32_t v = 0;
+        if ((unsigned)gy < (unsigned)a.grid.height && gx >= 0 && gx < a.grid.pitch)
+            v = __ldg(reinterpret_cast<const uint32_t*>(a.grid.cells + (size_t)gy * a.grid.pitch + gx));
+        reinterpret_cast<uint32_t*>(stile)[i] = v;
     }
-    __syncthreads();
+}
 
+__device__ __forceinline__ Window make_window(const ScoreArgs& a, const int8_t* stile, bool tile)
+{
     Window win;
-    if (TILE) {
+    if (tile) {
         win.base = stile; win.x0 = a.tile_x0; win.y0 = a.tile_y0; win.w = a.tile_w; win.h = a.tile_h;
         win.pitch = a.tile_pitch;
     } else {
         win.base = a.grid.cells; win.x0 = 0; win.y0 = 0; win.w = a.grid.width; win.h = a.grid.height;
         win.pitch = a.grid.pitch;
     }
+    return win;
+}
+
+// ---- the literal restatement for every evaluation (sensor_path = 1, and whenever the fast pass is not applicable) ------
+template <int G, bool INTERP, bool TILE, bool COUNT>
+__global__ void __launch_bounds__(MCL_SCORE_THREADS, MCL_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    Beam* sbeams = reinterpret_cast<Beam*>(smem);
+    int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(Beam));
+
+    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
+    if (TILE) stage_tile(a, stile);
+    __syncthreads();
+
+    const Window win = make_window(a, stile, TILE);
     GridConst gc;
     gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
     gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
     gc.trig = gs_load_consts();
 
-    constexpr int PPB = 256 / G;                 // particles per CTA per iteration
+    constexpr int PPB = MCL_SCORE_THREADS / G;   // particles per CTA per iteration
     const int sub = threadIdx.x % G;
     const int slot = threadIdx.x / G;
     int gathers = 0;
@@ -91,6 +108,202 @@ MCL_UNROLL(MCL_BEAM_UNROLL)
         for (int off = 16; off > 0; off >>= 1) gathers += __shfl_xor_sync(0xffffffffu, gathers, off);
         if ((threadIdx.x & 31) == 0) atomicAdd(a.gather_counter, (unsigned long long)gathers);
     }
+}
+
+// ---- two-pass path, pass 1: certified float evaluation (mcl_device.cuh: score_beam_fast) ------------------------------
+// Writes the sum over the certain beams to score2[p] and one bit per uncertain beam to masks[word][virtual lane], where
+// virtual lane = (p - lo)*G + sub and a lane's k-th beam is j = sub + k*G.
+#ifndef MCL_FAST_THREADS
+#define MCL_FAST_THREADS 256
+#endif
+#ifndef MCL_FAST_MIN_CTAS
+#define MCL_FAST_MIN_CTAS 4
+#endif
+#ifndef MCL_FAST_UNROLL
+#define MCL_FAST_UNROLL 2
+#endif
+template <int G, bool INTERP, bool TILE, bool COUNT>
+__global__ void __launch_bounds__(MCL_FAST_THREADS, MCL_FAST_MIN_CTAS) score_fast_kernel(const ScoreArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    FastBeam* sfast = reinterpret_cast<FastBeam*>(smem);
+    int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(FastBeam));
+
+    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) {
+        const Beam b = a.beams[i];
+        FastBeam f;
+        f.ratio = (float)b.ratio; f.theta = b.theta; f.rc = __fmul_rn(b.range, a.grid.cells_per_meter); f.pad = 0.0f;
+        sfast[i] = f;
+    }
+    if (TILE) stage_tile(a, stile);
+    __syncthreads();
+
+    const int8_t* cells = TILE ? stile : a.grid.cells;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stile);
+    const int pitch = TILE ? a.tile_pitch : a.grid.pitch;
+    const FastPlan fp = a.fast;
+    const double gx = (double)a.grid.origin_x, gy = (double)a.grid.origin_y, cpm_d = (double)a.grid.cells_per_meter;
+    const int iters = (a.num_beams + G - 1) / G;                 // beams per lane
+    const int nwords = (iters + 31) / 32;
+    const long long vlanes = (a.hi - a.lo) * G;
+
+    constexpr int PPB = MCL_FAST_THREADS / G;
+    const int sub = threadIdx.x % G;
+    const int slot = threadIdx.x / G;
+    int gathers = 0;
+    for (long long base = a.lo + (long long)blockIdx.x * PPB; base < a.hi; base += (long long)gridDim.x * PPB) {
+        const long long p = base + slot;
+        int acc = 0;
+        if (p < a.hi) {
+            const FastBase fb = make_fast_base<INTERP>(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p], gx, gy, cpm_d, fp);
+            uint32_t* mrow = a.masks + ((p - a.lo) * G + sub);
+            for (int w = 0; w < nwords; ++w) {
+                uint32_t m = 0;
+                const int kend = min(32, iters - w * 32);
+                if (fb.ok) {
+                    uint32_t bit = 1u;
+MCL_UNROLL(MCL_FAST_UNROLL)
+                    for (int k = 0; k < kend; ++k) {
+                        const int j = sub + (w * 32 + k) * G;
+                        const bool inb = G == 1 || j < a.num_beams;      // G == 1: kend already bounds j
+                        int v = 0, g = 0;
+                        const bool certain =
+                            score_beam_fast<INTERP, TILE, COUNT>(fb, sfast[inb ? j : 0], fp, cells, sbase, pitch, v, g);
+                        acc += inb ? v : 0;
+                        if (COUNT) gathers += inb ? g : 0;
+                        if (inb & !certain) m |= bit;
+                        bit += bit;
+                    }
+                } else {
+                    for (int k = 0; k < kend; ++k) m |= (uint32_t)(sub + (w * 32 + k) * G < a.num_beams) << k;
+                }
+                mrow[(long long)w * vlanes] = m;
+            }
+        }
+#pragma unroll
+        for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (sub == 0 && p < a.hi) a.score2[p] = acc;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gathers += __shfl_xor_sync(0xffffffffu, gathers, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.gather_counter, (unsigned long long)gathers);
+    }
+}
+
+// ---- two-pass path, pass 2: the literal restatement for the beams pass 1 could not certify ------------------------------
+// Warp-level compaction: a warp takes 32 consecutive virtual lanes at a time, turns their mask words into a queue of
+// (word, lane, bit) entries in shared memory and evaluates the queue 32 entries at a time, so every lane of the warp
+// does useful work whatever the distribution of uncertain beams over particles.  The raw poses of the 32 lanes'
+// particles are staged in shared memory (coalesced) and each evaluation rebuilds its RayBase from them; results are
+// accumulated with shared-memory integer atomics (exact, order-independent) and added to score2[p].
+constexpr int kDefQueue = 1024 + 32;          // one word of 32 lanes can add up to 1024 entries to < 32 left over
+struct __align__(16) DefParticle { float xa, ya, tha, xb, yb, thb; int acc; int pad; };
+
+__host__ __device__ inline size_t deferred_smem_bytes(int num_beams, int warps)
+{
+    return (size_t)num_beams * sizeof(Beam) + (size_t)warps * (kDefQueue * sizeof(uint16_t) + 32 * sizeof(DefParticle));
+}
+
+template <int G, bool INTERP, bool TILE, bool COUNT>
+__global__ void __launch_bounds__(MCL_SCORE_THREADS, MCL_SCORE_MIN_CTAS) score_deferred_kernel(const ScoreArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int WARPS = MCL_SCORE_THREADS / 32;
+    Beam* sbeams = reinterpret_cast<Beam*>(smem);
+    DefParticle* spart_all = reinterpret_cast<DefParticle*>(smem + (size_t)a.num_beams * sizeof(Beam));
+    uint16_t* squeue_all = reinterpret_cast<uint16_t*>(spart_all + WARPS * 32);
+    int8_t* stile = reinterpret_cast<int8_t*>(smem + deferred_smem_bytes(a.num_beams, WARPS));
+
+    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
+    if (TILE) stage_tile(a, stile);
+    __syncthreads();
+
+    const Window win = make_window(a, stile, TILE);
+    GridConst gc;
+    gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
+    gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
+    gc.trig = gs_load_consts();
+    const int iters = (a.num_beams + G - 1) / G;
+    const int nwords = (iters + 31) / 32;
+    const long long vlanes = (a.hi - a.lo) * G;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DefParticle* spart = spart_all + warp * 32;
+    uint16_t* squeue = squeue_all + warp * kDefQueue;
+    int gathers = 0;
+    unsigned deferred = 0;
+
+    auto evaluate = [&](unsigned e) {
+        const int k = e & 31, src = (e >> 5) & 31, w = e >> 10;
+        const DefParticle dp = spart[src / G];
+        const RayBase rb = make_ray_base(dp.xa, dp.ya, dp.tha, dp.xb, dp.yb, dp.thb);
+        const int j = (src % G) + (w * 32 + k) * G;
+        const int v = score_beam<INTERP, TILE, COUNT>(rb, sbeams[j], gc, win, a.grid, gathers);
+        if (v) atomicAdd(&spart[src / G].acc, v);
+        ++deferred;
+    };
+
+    const long long nblocks = (vlanes + 31) / 32;
+    for (long long blk = (long long)blockIdx.x * WARPS + warp; blk < nblocks; blk += (long long)gridDim.x * WARPS) {
+        const long long v0 = blk * 32;
+        const long long v = v0 + lane;
+        // stage the particles of this block (32/G of them)
+        if (lane < 32 / G) {
+            const long long p = a.lo + v0 / G + lane;
+            DefParticle dp;
+            dp.acc = 0; dp.pad = 0;
+            if (p < a.hi) {
+                dp.xa = a.x[p]; dp.ya = a.y[p]; dp.tha = a.th[p]; dp.xb = a.px[p]; dp.yb = a.py[p]; dp.thb = a.pth[p];
+            } else {
+                dp.xa = dp.ya = dp.tha = dp.xb = dp.yb = dp.thb = 0.0f;
+            }
+            spart[lane] = dp;
+        }
+        __syncwarp();
+        int qn = 0;
+        for (int w = 0; w < nwords; ++w) {
+            uint32_t m = v < vlanes ? a.masks[(long long)w * vlanes + v] : 0u;
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            int pos = qn + incl - c;
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                squeue[pos++] = (uint16_t)((w << 10) | (lane << 5) | k);
+            }
+            qn += total;
+            __syncwarp();
+            while (qn >= 32) {
+                qn -= 32;
+                evaluate(squeue[qn + lane]);
+            }
+            __syncwarp();
+        }
+        if (lane < qn) evaluate(squeue[lane]);
+        __syncwarp();
+        if (lane < 32 / G) {
+            const long long p = a.lo + v0 / G + lane;
+            const int add = spart[lane].acc;
+            if (p < a.hi && add != 0) a.score2[p] += add;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gathers += __shfl_xor_sync(0xffffffffu, gathers, off);
+        if (lane == 0) atomicAdd(a.gather_counter, (unsigned long long)gathers);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) deferred += __shfl_xor_sync(0xffffffffu, deferred, off);
+    if (lane == 0 && deferred) atomicAdd(a.deferred_counter, (unsigned long long)deferred);
 }
 
 // =================================================================================================================
@@ -705,6 +918,37 @@ __global__ void gather_peak_kernel(const int8_t* buf, unsigned long long mask, l
         acc += (int)__ldcg(buf + (s & mask));
     }
     if (acc == 0x7fffffff) *sink = (unsigned long long)acc;
+}
+
+// Largest |fast_sincos - sin/cos in double| over every float in [lo, hi] (walks the bit patterns: both signs).
+__global__ void fast_trig_error_kernel(float lo, float hi, unsigned long long* out_bits /* [2]: max errs as double bits */)
+{
+    double es = 0.0, ec = 0.0;
+    // non-negative floats up to max(|lo|, |hi|), each tried with both signs where inside [lo, hi]
+    const unsigned top = __float_as_uint(fmaxf(fabsf(lo), fabsf(hi)));
+    for (unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b <= top;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float v = __uint_as_float((unsigned)b);
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const float a = sgn ? -v : v;
+            if (a < lo || a > hi) continue;
+            float s, c;
+            fast_sincos(a, &s, &c);
+            double sd, cd;
+            sincos((double)a, &sd, &cd);
+            es = fmax(es, fabs((double)s - sd));
+            ec = fmax(ec, fabs((double)c - cd));
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        es = fmax(es, __shfl_xor_sync(0xffffffffu, es, off));
+        ec = fmax(ec, __shfl_xor_sync(0xffffffffu, ec, off));
+    }
+    if ((threadIdx.x & 31) == 0) {      // non-negative doubles order like their bit patterns
+        atomicMax(out_bits + 0, (unsigned long long)__double_as_longlong(es));
+        atomicMax(out_bits + 1, (unsigned long long)__double_as_longlong(ec));
+    }
 }
 
 __global__ void debug_sincosf_kernel(const float* x, long long n, float* s, float* c)

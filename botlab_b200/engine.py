@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcl_cuda.so")
+# MCL_LIB selects another build of the same library (kernel tuning sweeps); the default is the in-tree product build
+LIB_PATH = os.environ.get("MCL_LIB") or os.path.join(_HERE, "libmcl_cuda.so")
 
 POSE_DTYPE = np.dtype([("utime", "<i8"), ("x", "<f4"), ("y", "<f4"), ("theta", "<f4")], align=True)
 PARTICLE_DTYPE = np.dtype([("pose", POSE_DTYPE), ("parent_pose", POSE_DTYPE), ("weight", "<f8")], align=True)
@@ -22,14 +23,14 @@ SYMBOLS = [
     "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
-    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf",
+    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error",
 ]
 
 
 class Params(C.Structure):
     _fields_ = [("min_range", C.c_float), ("weight_floor", C.c_double), ("init_std", C.c_double),
                 ("legacy_equal_utime", C.c_int), ("lanes_per_particle", C.c_int), ("map_tile", C.c_int),
-                ("reserved", C.c_int * 8)]
+                ("sensor_path", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class Pose(C.Structure):
@@ -49,7 +50,8 @@ class Stats(C.Structure):
                 ("effective_sample_size", C.c_double), ("ms_resample", C.c_float), ("ms_action", C.c_float),
                 ("ms_score", C.c_float), ("ms_normalize", C.c_float), ("ms_estimate", C.c_float),
                 ("ms_total", C.c_float), ("lanes_per_particle", C.c_int), ("map_tile_used", C.c_int),
-                ("kernel_launches", C.c_int), ("collectives", C.c_int), ("peer_push", C.c_int), ("reserved", C.c_int * 3)]
+                ("kernel_launches", C.c_int), ("collectives", C.c_int), ("peer_push", C.c_int), ("sensor_path", C.c_int), ("reserved", C.c_int * 2),
+                ("deferred_evals", C.c_int64), ("fast_eps", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -105,6 +107,7 @@ def lib():
         L.mcl_set_gather_counting.argtypes = [vp, ip]
         L.mcl_measure_gather_peak.argtypes = [vp, i64, i64, vp]
         L.mcl_debug_sincosf.argtypes = [vp, vp, i64, vp, vp]
+        L.mcl_debug_fast_trig_error.argtypes = [vp, fp, fp, vp, vp]
         _lib = L
     return _lib
 
@@ -285,6 +288,12 @@ class Engine:
         c = np.zeros_like(x)
         self._ck(self._L.mcl_debug_sincosf(self.h, _p(x), x.shape[0], _p(s), _p(c)))
         return s, c
+
+    def fast_trig_error(self, lo, hi):
+        """max |SFU sin/cos - double sin/cos| over every float in [lo, hi] -> (sin_err, cos_err)."""
+        es, ec = C.c_double(), C.c_double()
+        self._ck(self._L.mcl_debug_fast_trig_error(self.h, lo, hi, C.addressof(es), C.addressof(ec)))
+        return es.value, ec.value
 
     def comm_init(self, unique_id, rank, world):
         buf = (C.c_byte * 128).from_buffer_copy(bytes(unique_id))

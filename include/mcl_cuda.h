@@ -44,7 +44,9 @@ typedef struct {
                                    pose.utime = odometry utime, real per-ray interpolation (the evident intent). */
     int    lanes_per_particle;  /* sensor kernel mapping: 0 = auto, else 1, 2, 4, 8, 16 or 32 lanes share one particle */
     int    map_tile;            /* 0 = auto, 1 = force L2/global gathers, 2 = force shared-memory map tile */
-    int    reserved[8];
+    int    sensor_path;         /* 0 = auto: certified float pass, then the literal restatement for every evaluation it
+                                   could not certify (identical results); 1 = literal restatement only */
+    int    reserved[7];
 } mcl_params;
 
 /* ActionModel state + per-update parameters (action_model.hpp:66-76). */
@@ -73,7 +75,10 @@ typedef struct {
     int     kernel_launches;      /* kernels launched by the last mcl_update */
     int     collectives;          /* slice exchanges enqueued by the last mcl_update (0 on one GPU) */
     int     peer_push;            /* 1: pose slices travel by copy-engine peer writes (CUDA IPC), else NCCL all-gather */
-    int     reserved[3];
+    int     sensor_path;          /* path of the last scoring pass: 2 = certified float pass + exact re-evaluation, 1 = exact only */
+    int     reserved[2];
+    int64_t deferred_evals;       /* evaluations of the last scoring pass the float pass could not certify (re-done exactly) */
+    double  fast_eps;             /* error bound (cells) the certification used, 0 when the exact path ran alone */
 } mcl_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
@@ -161,6 +166,9 @@ int  mcl_set_gather_counting(mcl_engine* h, int on);   /* debug counter of map r
 int  mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t reads, double* sectors_per_s_out);
 /* glibc-sincosf restatement evaluated on the device for n floats (test hook for the trig parity contract). */
 int  mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* sin_out, float* cos_out);
+/* Largest absolute error of the SFU sine / cosine the certified float pass uses, over EVERY float in [lo, hi] against
+ * double-precision sin/cos (test hook: the certification's error budget assumes a bound on it). */
+int  mcl_debug_fast_trig_error(mcl_engine* h, float lo, float hi, double* max_sin_err, double* max_cos_err);
 
 #ifdef __cplusplus
 }
