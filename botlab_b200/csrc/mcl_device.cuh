@@ -277,6 +277,10 @@ struct FastPlan {
     int fmask;           // (bits & fmask) == 0  <=>  the coordinate is within the uncertain band of an integer
     float magic;         // 1.5*2^13 + kb/1024: a float add leaves round(v*1024) + kb in the low mantissa bits
     float t_dir;         // 3(1 + eps) + slack: octant decisions are certain beyond this
+    float t_dir_neg;     // 5(1 + eps) + slack: the same when the extended point has a negative coordinate
+    float x2_min;        // extended-point coordinates at or above this are certainly non-negative in the reference
+    float gmid_x, ghalf_x;   // |e - gmid| >= ghalf  =>  the endpoint is certainly two or more cells outside the grid
+    float gmid_y, ghalf_y;
     float rho_lo, rho_hi;   // range of the scan's interpolation ratios
     float max_shift;     // largest |dS| (cells) a particle may have and still take the fast pass
     float coord_hi;      // largest robot cell coordinate the error budget covers
@@ -336,6 +340,9 @@ __device__ __forceinline__ void fast_sincos(float a, float* s, float* c)
     *c = __cosf(a);
 }
 
+#ifdef MCL_FAST_DIAG
+__device__ unsigned long long g_fast_diag[8];
+#endif
 // Window cell read for the fast pass: shared-memory reads go through ld.shared.s8 on a 32-bit shared address (one LDS
 // with the sign extension built in; keeps the compiler from re-deriving the value through packed 16-bit selects).
 template <bool SMEM>
@@ -374,8 +381,12 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const float ax = fabsf(px), ay = fabsf(py);
     const float d1 = __fsub_rn(__fadd_rn(ax, ax), ay);      // step x iff 2|ddx| >= |ddy|
     const float d2 = __fsub_rn(__fadd_rn(ay, ay), ax);      // step y iff |ddx| <= 2|ddy|
-    const bool dir_ok = (fminf(fabsf(d1), fabsf(d2)) > fp.t_dir) &
-                        (fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= 0.01f);
+    // an extended point at a negative coordinate is truncated toward zero by the reference (not floored), which
+    // widens the band of its differences from 3 to 5 cells
+    const float t_dir = fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= fp.x2_min ? fp.t_dir : fp.t_dir_neg;
+    const bool dir_ok = fminf(fabsf(d1), fabsf(d2)) > t_dir;
+    // endpoint certainly two or more cells outside the grid: it and both neighbours read 0 (occupancy_grid.cpp:65-70)
+    const bool outside = (fabsf(__fsub_rn(ex, fp.gmid_x)) >= fp.ghalf_x) | (fabsf(__fsub_rn(ey, fp.gmid_y)) >= fp.ghalf_y);
     // step toward the extended point, assembled in float: (+-1 or 0) + (+-1 or 0) * pitch, then to an integer by a
     // magic-number add (no conversion unit)
     const float ux = __uint_as_float((__float_as_uint(px) & 0x80000000u) | 0x3f800000u);
@@ -388,10 +399,22 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const int odds = fast_read<SMEM>(cells, sbase, idx);
     const int o1 = fast_read<SMEM>(cells, sbase, idx - off);      // toward the robot
     const int o2 = fast_read<SMEM>(cells, sbase, idx + off);      // toward the extended point
-    const bool certain = cell_ok & ((odds > 0) | dir_ok);
-    if (COUNT) gathers += certain ? (odds > 0 ? 1 : 3) : 0;
+    const bool certain = outside | (cell_ok & ((odds > 0) | dir_ok));
+#ifdef MCL_FAST_DIAG
+    {   // why evaluations are deferred (diagnostic build only)
+        const bool dirband = !(fminf(fabsf(d1), fabsf(d2)) > fp.t_dir);
+        const bool x2neg = !dir_ok;
+        atomicAdd(&g_fast_diag[0], 1ull);
+        if (!frac_ok) atomicAdd(&g_fast_diag[1], 1ull);
+        if (!(in_x & in_y) && !outside) atomicAdd(&g_fast_diag[2], 1ull);
+        if (cell_ok && odds <= 0 && dirband) atomicAdd(&g_fast_diag[3], 1ull);
+        if (cell_ok && odds <= 0 && !dirband && x2neg) atomicAdd(&g_fast_diag[4], 1ull);
+        if (!certain) atomicAdd(&g_fast_diag[5], 1ull);
+    }
+#endif
+    if (COUNT) gathers += certain ? (cell_ok & (odds > 0) ? 1 : 3) : 0;
     const int v = odds > 0 ? 2 * odds : (o1 > 0 ? o1 : max(o2, 0));
-    v2 = certain ? v : 0;
+    v2 = cell_ok & certain ? v : 0;       // outside (cell_ok is then false): score 0
     return certain;
 }
 

@@ -392,6 +392,11 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     fp.fmask = 1023 & ~(2 * kb - 1);
     fp.magic = 12288.0f + (float)kb / 1024.0f;
     fp.t_dir = (float)(3.0 * (1.0 + eps) + 4.0 * u * Rc + 1e-4);
+    fp.t_dir_neg = (float)(5.0 * (1.0 + eps) + 4.0 * u * Rc + 1e-4);
+    fp.x2_min = (float)(3.0 * eps + 1e-3);       // the extended point's error is below 2 eps (twice the ray term)
+    // reference: score 0 when trunc(e) <= -2 or >= W + 1 on either axis, i.e. e <= -2 or e >= W + 1
+    fp.gmid_x = 0.5f * (float)(h->grid.width - 1); fp.ghalf_x = (float)(0.5 * (h->grid.width + 3) + eps + 1e-3);
+    fp.gmid_y = 0.5f * (float)(h->grid.height - 1); fp.ghalf_y = (float)(0.5 * (h->grid.height + 3) + eps + 1e-3);
     fp.rho_lo = (float)h->ratio_lo; fp.rho_hi = (float)h->ratio_hi;
     fp.max_shift = (float)max_shift;
     fp.coord_hi = (float)(Cm - 1.0);
@@ -804,6 +809,16 @@ void mcl_destroy(mcl_engine* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+#ifdef MCL_FAST_DIAG
+    {
+        unsigned long long d[8];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(d, g_fast_diag, sizeof(d));
+        if (d[0])
+            fprintf(stderr, "fast-pass diag: evals %llu  frac %.4f  outside-window %.4f  dir-band %.4f  x2-negative %.4f  deferred %.4f\n",
+                    d[0], (double)d[1] / d[0], (double)d[2] / d[0], (double)d[3] / d[0], (double)d[4] / d[0], (double)d[5] / d[0]);
+    }
+#endif
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
 #ifdef MCL_WITH_NCCL
