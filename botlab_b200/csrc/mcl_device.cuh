@@ -175,9 +175,11 @@ __device__ __forceinline__ int step_offset(int x1, int y1, int x2, int y2, int p
 #ifndef MCL_EAGER_NEIGHBOURS
 #define MCL_EAGER_NEIGHBOURS 1
 #endif
-template <bool INTERP, bool SMEM, bool COUNT>
-__device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const GridConst& gc, const Window& win,
-                                          const DevGrid& grid, int& gathers)
+// Ray construction + endpoint of one evaluation, with the reference's exact rounding sequence: sx, sy = robot cell
+// coordinate (grid_utils.hpp:50-55), px, py = (range*cos)*cpm, (range*sin)*cpm, e1 = p + s before truncation.
+template <bool INTERP>
+__device__ __forceinline__ void exact_endpoint(const RayBase& p, const Beam& b, const GridConst& gc, float& sx, float& sy,
+                                               float& px, float& py, float& e1x, float& e1y)
 {
     float ox, oy, thr;
     if (INTERP) {
@@ -189,14 +191,22 @@ __device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const
     }
     const float th = wrap_to_pi_fast(__fsub_rn(thr, b.theta));                 // moving_laser_scan.cpp:33
     // grid_utils.hpp:50-55: double math, stored into Point<float>
-    const float sx = (float)__dmul_rn(__dsub_rn((double)ox, gc.gx), gc.cpm_d);
-    const float sy = (float)__dmul_rn(__dsub_rn((double)oy, gc.gy), gc.cpm_d);
+    sx = (float)__dmul_rn(__dsub_rn((double)ox, gc.gx), gc.cpm_d);
+    sy = (float)__dmul_rn(__dsub_rn((double)oy, gc.gy), gc.cpm_d);
     float s, c;
     glibc_sincosf_regs(gc.trig, th, &s, &c);
-    const float px = __fmul_rn(__fmul_rn(b.range, c), gc.cpm);                 // (range*cos)*cpm, float
-    const float py = __fmul_rn(__fmul_rn(b.range, s), gc.cpm);
-    const float e1x = __fadd_rn(px, sx);                                       // sensor_model.cpp:34 (before truncation)
-    const float e1y = __fadd_rn(py, sy);                                       // :35
+    px = __fmul_rn(__fmul_rn(b.range, c), gc.cpm);                             // (range*cos)*cpm, float
+    py = __fmul_rn(__fmul_rn(b.range, s), gc.cpm);
+    e1x = __fadd_rn(px, sx);                                                   // sensor_model.cpp:34 (before truncation)
+    e1y = __fadd_rn(py, sy);                                                   // :35
+}
+
+template <bool INTERP, bool SMEM, bool COUNT>
+__device__ __forceinline__ int score_beam(const RayBase& p, const Beam& b, const GridConst& gc, const Window& win,
+                                          const DevGrid& grid, int& gathers)
+{
+    float sx, sy, px, py, e1x, e1y;
+    exact_endpoint<INTERP>(p, b, gc, sx, sy, px, py, e1x, e1y);
     // One guard for every conversion below: the robot cell and the endpoint must be non-negative and below 2^22.
     // As unsigned bit patterns that is a single compare (negative values, -0, NaN and infinities all exceed it).
     const unsigned gmax = max(max(__float_as_uint(sx), __float_as_uint(sy)), max(__float_as_uint(e1x), __float_as_uint(e1y)));
@@ -343,6 +353,20 @@ __device__ __forceinline__ void fast_sincos(float a, float* s, float* c)
 #ifdef MCL_FAST_DIAG
 __device__ unsigned long long g_fast_diag[8];
 #endif
+// The float model of one evaluation: p = range*cpm*(cos, sin), e = robot cell coordinate + p.
+template <bool INTERP>
+__device__ __forceinline__ void fast_endpoint(const FastBase& p, const FastBeam& b, float& px, float& py, float& ex,
+                                              float& ey)
+{
+    const float sx = INTERP ? __fmaf_rn(p.dsx, b.ratio, p.sxb) : p.sxb;
+    const float sy = INTERP ? __fmaf_rn(p.dsy, b.ratio, p.syb) : p.syb;
+    const float thr = INTERP ? __fmaf_rn(p.dth, b.ratio, p.thb) : p.thb;
+    float s, c;
+    fast_sincos(__fsub_rn(thr, b.theta), &s, &c);
+    px = __fmul_rn(b.rc, c); py = __fmul_rn(b.rc, s);
+    ex = __fadd_rn(px, sx); ey = __fadd_rn(py, sy);
+}
+
 // Window cell read for the fast pass: shared-memory reads go through ld.shared.s8 on a 32-bit shared address (one LDS
 // with the sign extension built in; keeps the compiler from re-deriving the value through packed 16-bit selects).
 template <bool SMEM>
@@ -363,13 +387,8 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
                                                 const int8_t* __restrict__ cells, unsigned sbase, int pitch, int& v2,
                                                 int& gathers)
 {
-    const float sx = INTERP ? __fmaf_rn(p.dsx, b.ratio, p.sxb) : p.sxb;
-    const float sy = INTERP ? __fmaf_rn(p.dsy, b.ratio, p.syb) : p.syb;
-    const float thr = INTERP ? __fmaf_rn(p.dth, b.ratio, p.thb) : p.thb;
-    float s, c;
-    fast_sincos(__fsub_rn(thr, b.theta), &s, &c);
-    const float px = __fmul_rn(b.rc, c), py = __fmul_rn(b.rc, s);
-    const float ex = __fadd_rn(px, sx), ey = __fadd_rn(py, sy);
+    float px, py, ex, ey;
+    fast_endpoint<INTERP>(p, b, px, py, ex, ey);
     // fixed point: low 10 bits = fraction (+ the band offset), the rest = cell (+ bias)
     const int bx = __float_as_int(__fadd_rn(ex, fp.magic)), by = __float_as_int(__fadd_rn(ey, fp.magic));
     // endpoint cell certain: not within eps of a cell boundary, interior to the window and inside the grid

@@ -380,8 +380,9 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     const double u = 5.9604644775390625e-08;
     const double Xm = Cm / cpm + std::max(std::fabs((double)h->grid.origin_x), std::fabs((double)h->grid.origin_y));
     const double max_shift = 64.0;
-    const double e_ref = cpm * u * Xm + 2.0 * u * Cm + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
-    const double e_apx = 3.0 * u * Cm + (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
+    const double Ce = Cm + Rc;            // endpoints beyond the grid (certified as "outside") reach this far
+    const double e_ref = cpm * u * Xm + 2.0 * u * Ce + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
+    const double e_apx = 3.0 * u * Ce + (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
                          Rc * ((M_PI * (3.0 * rho_max + 1.0) + 9.5) * u + (double)kFastTrigErr);
     const double eps = 1.25 * (e_ref + e_apx) + 1e-6;
     const int k = (int)std::ceil(1024.0 * eps + 0.5);
@@ -1288,6 +1289,41 @@ int mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t read
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
     *sectors_per_s_out = (double)per_thread * blocks * threads / ((double)ms * 1e-3);
+    return MCL_OK;
+}
+
+int mcl_debug_fast_margin(mcl_engine* h, double* max_dev_endpoint, double* max_dev_extended, double* eps_out)
+{
+    if (!h || !max_dev_endpoint || !max_dev_extended || !eps_out) return fail(h, MCL_ERR_INVALID, "bad arguments");
+    if (!h->have_map || !h->have_particles || !h->have_scan) return fail(h, MCL_ERR_STATE, "needs a map, particles and a scan");
+    CK(cudaSetDevice(h->device));
+    ScoreArgs a{};
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    a.x = p.x; a.y = p.y; a.th = p.th; a.px = q.x; a.py = q.y; a.pth = q.th;
+    a.lo = h->lo; a.hi = h->hi;
+    a.beams = h->beams; a.num_beams = h->num_beams;
+    a.grid = h->grid;
+    a.fast = fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch);
+    *eps_out = a.fast.enabled ? h->stats_eps : 0.0;
+    *max_dev_endpoint = *max_dev_extended = 0.0;
+    if (!a.fast.enabled || h->num_beams == 0) return MCL_OK;
+    { int rc = ensure_staging(h, 8); if (rc) return rc; }
+    CK(cudaMemsetAsync(h->staging, 0, 8, h->stream));
+    const size_t smem = (size_t)h->num_beams * sizeof(Beam);
+    if (h->scan_interp) {
+        CK(cudaFuncSetAttribute(fast_margin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fast_margin_kernel<true><<<grid_for(h, h->hi - h->lo, 128), 128, smem, h->stream>>>(a, (unsigned*)h->staging);
+    } else {
+        CK(cudaFuncSetAttribute(fast_margin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fast_margin_kernel<false><<<grid_for(h, h->hi - h->lo, 128), 128, smem, h->stream>>>(a, (unsigned*)h->staging);
+    }
+    CKL(h);
+    float dev[2];
+    CK(cudaMemcpyAsync(dev, h->staging, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *max_dev_endpoint = dev[0];
+    *max_dev_extended = dev[1];
     return MCL_OK;
 }
 

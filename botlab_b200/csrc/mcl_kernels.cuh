@@ -920,6 +920,52 @@ __global__ void gather_peak_kernel(const int8_t* buf, unsigned long long mask, l
     if (acc == 0x7fffffff) *sink = (unsigned long long)acc;
 }
 
+// Certification margin probe: over every (particle, beam) the fast pass would evaluate, the largest deviation between
+// the float model and the reference's exactly-rounded values, for the endpoint (dev[0]) and for the extended point
+// (dev[1]); the host compares them with the eps the certification assumes.  Floats >= 0 order like their bit patterns.
+template <bool INTERP>
+__global__ void fast_margin_kernel(const ScoreArgs a, unsigned* dev_bits)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    Beam* sbeams = reinterpret_cast<Beam*>(smem);
+    for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
+    __syncthreads();
+    GridConst gc;
+    gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
+    gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
+    gc.trig = gs_load_consts();
+    float de = 0.0f, d2 = 0.0f;
+    for (long long p = a.lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; p < a.hi;
+         p += (long long)gridDim.x * blockDim.x) {
+        const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
+        const FastBase fb = make_fast_base<INTERP>(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p], gc.gx, gc.gy,
+                                                   gc.cpm_d, a.fast);
+        if (!fb.ok) continue;
+        for (int j = 0; j < a.num_beams; ++j) {
+            const Beam b = sbeams[j];
+            FastBeam f;
+            f.ratio = (float)b.ratio; f.theta = b.theta; f.rc = __fmul_rn(b.range, gc.cpm); f.pad = 0.0f;
+            float fpx, fpy, fex, fey, sx, sy, px, py, e1x, e1y;
+            fast_endpoint<INTERP>(fb, f, fpx, fpy, fex, fey);
+            exact_endpoint<INTERP>(rb, b, gc, sx, sy, px, py, e1x, e1y);
+            // the budget covers endpoints the fast pass can certify: inside the window's certain-interior box, or
+            // beyond the grid (there only the side of the boundary matters, checked with the same eps)
+            if (!(fabsf(fex) <= 8192.0f && fabsf(fey) <= 8192.0f)) continue;
+            de = fmaxf(de, fmaxf(fabsf(fex - e1x), fabsf(fey - e1y)));
+            const float x2 = __fadd_rn(__fmul_rn(2.0f, px), sx), y2 = __fadd_rn(__fmul_rn(2.0f, py), sy);
+            d2 = fmaxf(d2, fmaxf(fabsf(__fadd_rn(fex, fpx) - x2), fabsf(__fadd_rn(fey, fpy) - y2)));
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        de = fmaxf(de, __shfl_xor_sync(0xffffffffu, de, off));
+        d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(dev_bits + 0, __float_as_uint(de));
+        atomicMax(dev_bits + 1, __float_as_uint(d2));
+    }
+}
+
 // Largest |fast_sincos - sin/cos in double| over every float in [lo, hi] (walks the bit patterns: both signs).
 __global__ void fast_trig_error_kernel(float lo, float hi, unsigned long long* out_bits /* [2]: max errs as double bits */)
 {

@@ -23,7 +23,7 @@ SYMBOLS = [
     "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
-    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error",
+    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error", "mcl_debug_fast_margin",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.mcl_measure_gather_peak.argtypes = [vp, i64, i64, vp]
         L.mcl_debug_sincosf.argtypes = [vp, vp, i64, vp, vp]
         L.mcl_debug_fast_trig_error.argtypes = [vp, fp, fp, vp, vp]
+        L.mcl_debug_fast_margin.argtypes = [vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -294,6 +295,12 @@ class Engine:
         es, ec = C.c_double(), C.c_double()
         self._ck(self._L.mcl_debug_fast_trig_error(self.h, lo, hi, C.addressof(es), C.addressof(ec)))
         return es.value, ec.value
+
+    def fast_margin(self):
+        """(max endpoint deviation, max extended-point deviation, eps) of the float pass on the current inputs, cells."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._L.mcl_debug_fast_margin(self.h, C.addressof(a), C.addressof(b), C.addressof(c)))
+        return a.value, b.value, c.value
 
     def comm_init(self, unique_id, rank, world):
         buf = (C.c_byte * 128).from_buffer_copy(bytes(unique_id))

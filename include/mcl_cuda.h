@@ -169,6 +169,10 @@ int  mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* sin_out,
 /* Largest absolute error of the SFU sine / cosine the certified float pass uses, over EVERY float in [lo, hi] against
  * double-precision sin/cos (test hook: the certification's error budget assumes a bound on it). */
 int  mcl_debug_fast_trig_error(mcl_engine* h, float lo, float hi, double* max_sin_err, double* max_cos_err);
+/* Certification margin probe for the current map, particles and scan: the largest deviation (cells) between the float
+ * pass's endpoint / extended point and the reference's exactly-rounded ones, and the eps the certification would assume
+ * for a whole-grid window (0 when the float pass is not applicable).  Test hook: deviations must stay below eps. */
+int  mcl_debug_fast_margin(mcl_engine* h, double* max_dev_endpoint, double* max_dev_extended, double* eps_out);
 
 #ifdef __cplusplus
 }

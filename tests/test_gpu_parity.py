@@ -456,3 +456,116 @@ def test_config1_replay_follows_the_reference_filter(legacy, real_map):
         assert abs(est.x - pose[0]) < 0.25 and abs(est.y - pose[1]) < 0.25
     assert worst_pose <= POSE_TOL and worst_w <= WEIGHT_TOL
     e.close()
+
+
+# ------------------------------------------------------------------------ two-pass sensor path (certified float pass)
+# The default sensor path scores every beam first with a float model whose result it can certify, and re-evaluates the
+# rest with the literal restatement.  These tests pin: (a) identical scores to the exact-only
+# path at scale and on hostile inputs, (b) the measured inputs of the certification's error budget.
+def _scores_both_paths(grid, cloud, r, th, t, **params):
+    out = []
+    for path in (0, 1):
+        e = make_engine(len(cloud), grid, sensor_path=path, **params)
+        e.import_particles(cloud)
+        e.set_gather_counting(True)
+        s = e.score(r, th, t)
+        out.append((s, e.stats()))
+        e.close()
+    return out
+
+
+@pytest.mark.parametrize("side,n,kind,variant", [
+    (1000, 600_000, "tracking", "interp"), (1000, 300_000, "tracking", "degen"), (1000, 400_000, "uniform", "interp"),
+    (200, 100_000, "tracking", "interp"), (200, 50_000, "uniform", "degen"), (3000, 300_000, "tracking", "interp"),
+])
+def test_two_pass_equals_exact_at_scale(side, n, kind, variant):
+    rng = np.random.default_rng(side + n)
+    grid = synth.make_map(side, seed=side)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=n)
+    pu = int(t[0]) if variant == "interp" else int(t[-1])
+    if kind == "tracking":
+        cloud = synth.make_particles(n, truth, seed=7, parent_utime=pu, pose_utime=int(t[-1]))
+    else:
+        cloud = synth.make_uniform_particles(n, grid, seed=7, utime=int(t[-1]))
+        if variant == "interp":
+            cloud["parent_pose"]["utime"] = pu
+            cloud["parent_pose"]["x"] += np.float32(0.013)
+            cloud["parent_pose"]["theta"] = np.clip(cloud["parent_pose"]["theta"] - np.float32(0.02), -3.14, 3.14)
+    (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t)
+    assert st2["sensor_path"] == 2 and st1["sensor_path"] == 1
+    assert np.array_equal(s2, s1)
+    assert st2["gathers"] == st1["gathers"] and st2["evals"] == st1["evals"]
+    assert 0 < st2["deferred_evals"] < 0.5 * st2["evals"]
+
+
+def test_two_pass_hostile_particles(real_map):
+    """NaN / infinite / huge / off-map positions, unwrapped headings, jumps between parent and pose: the float pass must
+    hand every one of them to the exact pass."""
+    r, th, t = synth.make_scan(real_map, (0.0, 0.0, 0.3), seed=4)
+    cloud = synth.make_particles(4096, (0.0, 0.0, 0.3), seed=4, parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    x, px, h = cloud["pose"]["x"], cloud["parent_pose"]["x"], cloud["pose"]["theta"]
+    x[0] = np.nan; x[1] = np.inf; x[2] = -np.inf; x[3] = 1e9; x[4] = -1e9; x[5] = 5.01; x[6] = -5.2; x[7] = 4.99
+    px[8] = np.nan; px[9] = 40.0; px[10] = -4.999
+    h[11] = 4.0; h[12] = -7.0; h[13] = np.nan; h[14] = 3.1415927; h[15] = -3.1415927
+    cloud["pose"]["y"][16] = -4.9999; cloud["pose"]["y"][17] = 4.9999; cloud["parent_pose"]["y"][18] = 1e30
+    (s2, st2), (s1, st1) = _scores_both_paths(real_map, cloud, r, th, t)
+    assert st2["sensor_path"] == 2
+    assert np.array_equal(s2, s1)
+    want, gathers, _ = port.likelihood(port_grid(real_map), cloud, r, th, t)
+    assert np.array_equal(s2, want) and st2["gathers"] == gathers
+
+
+def test_two_pass_hostile_scans(real_map):
+    """Scans outside the float pass's domain (beam angles beyond 2*pi, interpolation ratios far outside [0,1], infinite
+    ranges) fall back to the exact path or defer; results stay identical to the oracle."""
+    cloud = synth.make_particles(2000, (0.5, -0.25, 0.3), seed=5, parent_utime=1_000_000, pose_utime=1_100_000)
+    r, th, t = synth.make_scan(real_map, (0.5, -0.25, 0.3), seed=5)
+    cases = {
+        "big_theta": (r, (th + np.float32(7.0)).astype(np.float32), t),
+        "late_times": (r, th, t + 1_000_000),                 # ratios around 10: extrapolation
+        "inf_range": (np.where(np.arange(len(r)) % 50 == 0, np.float32(np.inf), r).astype(np.float32), th, t),
+        "short_ranges": (np.full_like(r, 0.16), th, t),
+    }
+    for name, (rr, tt, ti) in cases.items():
+        e = make_engine(len(cloud), real_map)
+        e.import_particles(cloud)
+        s = e.score(rr, tt, ti)
+        st = e.stats()
+        want, _, _ = port.likelihood(port_grid(real_map), cloud, rr, tt, ti)
+        assert np.array_equal(s, want), name
+        if name in ("big_theta", "late_times"):
+            assert st["sensor_path"] == 1, name               # the float pass declared itself not applicable
+        e.close()
+
+
+def test_fast_trig_error_bound():
+    """kFastTrigErr (mcl_device.cuh) must bound the SFU sine/cosine error over EVERY float the float pass can feed it."""
+    e = engine.Engine(16)
+    es, ec = e.fast_trig_error(-9.5, 9.5)
+    e.close()
+    assert 0 < max(es, ec) <= 2.0e-6
+
+
+@pytest.mark.parametrize("side,kind", [(200, "tracking"), (2000, "tracking"), (4000, "uniform"), (1000, "uniform")])
+def test_certification_margin(side, kind):
+    """The float model's endpoint and extended point stay within the eps the certification assumes of the reference's
+    exactly-rounded values, with margin to spare, on every evaluation of a 50 k-particle cloud."""
+    rng = np.random.default_rng(side)
+    grid = synth.make_map(side, seed=side + 1)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=side)
+    if kind == "tracking":
+        cloud = synth.make_particles(50_000, truth, seed=3, parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    else:
+        cloud = synth.make_uniform_particles(50_000, grid, seed=3, utime=int(t[-1]))
+        cloud["parent_pose"]["utime"] = int(t[0])
+        cloud["parent_pose"]["y"] -= np.float32(0.021)
+    e = make_engine(len(cloud), grid)
+    e.import_particles(cloud)
+    e.score(r, th, t)
+    dev_e, dev_x2, eps = e.fast_margin()
+    e.close()
+    assert eps > 0
+    assert dev_e <= 0.6 * eps, (dev_e, eps)
+    assert dev_x2 <= 1.2 * eps, (dev_x2, eps)             # the extended point doubles the ray term; certified at 3 eps
