@@ -326,10 +326,12 @@ int launch_score_g(mcl_engine* h, const ScoreArgs& a, int which, size_t smem, lo
         return cnt ? launch_persistent(h, score_fast_kernel<G, INTERP, TILE, true>, a, MCL_FAST_THREADS, smem, blocks)
                    : launch_persistent(h, score_fast_kernel<G, INTERP, TILE, false>, a, MCL_FAST_THREADS, smem, blocks);
     }
+    if (which == 2) {
+        const long long blocks = (local * G + MCL_DEF_THREADS - 1) / MCL_DEF_THREADS;
+        return cnt ? launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, true>, a, MCL_DEF_THREADS, smem, blocks)
+                   : launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, false>, a, MCL_DEF_THREADS, smem, blocks);
+    }
     const long long blocks = (local + MCL_SCORE_THREADS / G - 1) / (MCL_SCORE_THREADS / G);
-    if (which == 2)
-        return cnt ? launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, true>, a, MCL_SCORE_THREADS, smem, blocks)
-                   : launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, false>, a, MCL_SCORE_THREADS, smem, blocks);
     return cnt ? launch_persistent(h, score_kernel<G, INTERP, TILE, true>, a, MCL_SCORE_THREADS, smem, blocks)
                : launch_persistent(h, score_kernel<G, INTERP, TILE, false>, a, MCL_SCORE_THREADS, smem, blocks);
 }
@@ -475,7 +477,7 @@ int run_score(mcl_engine* h)
                 const size_t bytes = (size_t)pitch * th;
                 // the exact pass of the two-pass path also holds its compaction queues in shared memory
                 const size_t extra2 = h->params.sensor_path != 1
-                                          ? deferred_smem_bytes(h->num_beams, MCL_SCORE_THREADS / 32) - smem : 0;
+                                          ? deferred_smem_bytes(h->num_beams, MCL_DEF_THREADS / 32) - smem : 0;
                 const size_t budget = (size_t)h->max_smem_optin - smem - extra2 - 1024;
                 if (bytes <= budget / (h->params.map_tile == 2 ? 1 : 2) || (h->params.map_tile == 2 && bytes <= budget)) {
                     tile = true;
@@ -506,7 +508,7 @@ int run_score(mcl_engine* h)
         a.masks = h->masks;
         rc = launch_score(h, G, tile, a, 1, smem, local);
         if (rc) return rc;
-        const size_t smem2 = smem - (size_t)h->num_beams * sizeof(Beam) + deferred_smem_bytes(h->num_beams, MCL_SCORE_THREADS / 32);
+        const size_t smem2 = smem - (size_t)h->num_beams * sizeof(Beam) + deferred_smem_bytes(h->num_beams, MCL_DEF_THREADS / 32);
         rc = launch_score(h, G, tile, a, 2, smem2, local);
     } else {
         rc = launch_score(h, G, tile, a, 0, smem, local);

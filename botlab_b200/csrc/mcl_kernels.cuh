@@ -197,6 +197,12 @@ MCL_UNROLL(MCL_FAST_UNROLL)
 // does useful work whatever the distribution of uncertain beams over particles.  The raw poses of the 32 lanes'
 // particles are staged in shared memory (coalesced) and each evaluation rebuilds its RayBase from them; results are
 // accumulated with shared-memory integer atomics (exact, order-independent) and added to score2[p].
+#ifndef MCL_DEF_THREADS
+#define MCL_DEF_THREADS 384
+#endif
+#ifndef MCL_DEF_MIN_CTAS
+#define MCL_DEF_MIN_CTAS 2
+#endif
 constexpr int kDefQueue = 1024 + 32;          // one word of 32 lanes can add up to 1024 entries to < 32 left over
 struct __align__(16) DefParticle { float xa, ya, tha, xb, yb, thb; int acc; int pad; };
 
@@ -206,10 +212,10 @@ __host__ __device__ inline size_t deferred_smem_bytes(int num_beams, int warps)
 }
 
 template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(MCL_SCORE_THREADS, MCL_SCORE_MIN_CTAS) score_deferred_kernel(const ScoreArgs a)
+__global__ void __launch_bounds__(MCL_DEF_THREADS, MCL_DEF_MIN_CTAS) score_deferred_kernel(const ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int WARPS = MCL_SCORE_THREADS / 32;
+    constexpr int WARPS = MCL_DEF_THREADS / 32;
     Beam* sbeams = reinterpret_cast<Beam*>(smem);
     DefParticle* spart_all = reinterpret_cast<DefParticle*>(smem + (size_t)a.num_beams * sizeof(Beam));
     uint16_t* squeue_all = reinterpret_cast<uint16_t*>(spart_all + WARPS * 32);
@@ -262,8 +268,15 @@ __global__ void __launch_bounds__(MCL_SCORE_THREADS, MCL_SCORE_MIN_CTAS) score_d
         }
         __syncwarp();
         int qn = 0;
+        uint32_t mbuf[4];                        // mask words are fetched four at a time: one exposed latency per four
         for (int w = 0; w < nwords; ++w) {
-            uint32_t m = v < vlanes ? a.masks[(long long)w * vlanes + v] : 0u;
+            if ((w & 3) == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    mbuf[q] = (v < vlanes && w + q < nwords) ? __ldcs(a.masks + ((long long)(w + q) * vlanes + v)) : 0u;
+            }
+            uint32_t m = mbuf[0];
+            mbuf[0] = mbuf[1]; mbuf[1] = mbuf[2]; mbuf[2] = mbuf[3];
             const int c = __popc(m);
             int incl = c;
 #pragma unroll
