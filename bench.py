@@ -11,9 +11,10 @@ is sharded across N GPUs (strong scaling) with the map replicated.
              engine's stream, max over ranks).
 `e2e`        the same metric through the reference-facing C-ABI call mcl_update() with HOST scan buffers: per step the
              scan is prepared and copied H2D, the pose estimate copied D2H, and the call blocks.
-`roofline`   sensor kernel (the dominant launch): algorithmic bytes per launch (32 B x map reads +
-             36 B x particles + map bytes) / its mean CUDA-event duration, against MEASURED_PEAKS.json's HBM copy rate;
-             plus the L2-gather microbenchmark measured on this device in this run as a second denominator.
+`roofline`   sensor stage (the dominant launches: score_fast_kernel + score_deferred_kernel, back to back on one
+             stream): algorithmic bytes per update (32 B x map reads + 36 B x particles + map bytes) / the
+             stage's mean CUDA-event duration, against MEASURED_PEAKS.json's HBM copy rate; plus the L2-gather
+             microbenchmark measured on this device in this run as a second denominator.
 `cpu_baseline` the reference's ParticleFilter::updateFilter (oracle/_ref when built, else the C port), 1 thread, on a
              bounded particle sub-sample of the same workload.
 """
@@ -172,6 +173,7 @@ def run_reference(args):
         return
     n, grid, truth, scans = build_workload(args.config)
     n_sample = min(n, CPU_SAMPLE_PARTICLES)
+    valid = int((scans[0][1] > np.float32(0.15)).sum())
     for _ in range(min(args.warmup, 1)):
         cpu_reference_update(grid, truth, scans, min(n_sample, 20_000), 1)
     t0 = time.perf_counter()
@@ -182,8 +184,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps * (n / n_sample), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic)", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {n} particles x 360 beams, {grid.width}x{grid.height} grid",
-                   "note": "ms_per_step extrapolated linearly from the sub-sample to the full cloud"},
+        "config": {"workload": f"{args.config}: {n} particles x 360 beams ({valid} valid), "
+                               f"{grid.width}x{grid.height} int8 grid, tracking cloud",
+                   "note": "ms_per_step extrapolated linearly from the sub-sample to the full cloud; the reference's "
+                           "ParticleFilter is single-threaded (no threads anywhere in src/slam), so 1 core is all it can use"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -344,7 +348,10 @@ def run_engine(args):
                     "updates_per_sec": args.steps / (e2e_ms * 1e-3)},
             "gpu_launches": launches,
             "clocks": clock_info,
-            "roofline": {"bound": "hbm", "kernel": "score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("score_fast_kernel + score_deferred_kernel (sensor stage)" if st["sensor_path"] == 2
+                                    else "score_kernel (sensor stage)"),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(args.config, world, n),
                          "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "map_reads_per_launch": gathers,

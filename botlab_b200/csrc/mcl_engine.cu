@@ -72,6 +72,8 @@ struct mcl_engine {
     unsigned long long* overruns = nullptr;
     unsigned long long* gather_counter = nullptr;
     unsigned long long* deferred_counter = nullptr;
+    BatchWindow* windows = nullptr;     // per-batch map windows (global localisation)
+    size_t windows_cap = 0;
     uint32_t* masks = nullptr;          // two-pass sensor path: uncertain-beam bits, [word][virtual lane]
     size_t masks_bytes = 0;
     double* ess_acc = nullptr;
@@ -323,17 +325,17 @@ int launch_score_g(mcl_engine* h, const ScoreArgs& a, int which, size_t smem, lo
     const bool cnt = h->count_gathers;
     if (which == 1) {
         const long long blocks = (local + MCL_FAST_THREADS / G - 1) / (MCL_FAST_THREADS / G);
-        return cnt ? launch_persistent(h, score_fast_kernel<G, INTERP, TILE, true>, a, MCL_FAST_THREADS, smem, blocks)
-                   : launch_persistent(h, score_fast_kernel<G, INTERP, TILE, false>, a, MCL_FAST_THREADS, smem, blocks);
+        return cnt ? launch_persistent(h, score_fast_kernel<G, INTERP, TILE, true, false>, a, MCL_FAST_THREADS, smem, blocks)
+                   : launch_persistent(h, score_fast_kernel<G, INTERP, TILE, false, false>, a, MCL_FAST_THREADS, smem, blocks);
     }
     if (which == 2) {
         const long long blocks = (local * G + MCL_DEF_THREADS - 1) / MCL_DEF_THREADS;
-        return cnt ? launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, true>, a, MCL_DEF_THREADS, smem, blocks)
-                   : launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, false>, a, MCL_DEF_THREADS, smem, blocks);
+        return cnt ? launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, true, false>, a, MCL_DEF_THREADS, smem, blocks)
+                   : launch_persistent(h, score_deferred_kernel<G, INTERP, TILE, false, false>, a, MCL_DEF_THREADS, smem, blocks);
     }
     const long long blocks = (local + MCL_SCORE_THREADS / G - 1) / (MCL_SCORE_THREADS / G);
-    return cnt ? launch_persistent(h, score_kernel<G, INTERP, TILE, true>, a, MCL_SCORE_THREADS, smem, blocks)
-               : launch_persistent(h, score_kernel<G, INTERP, TILE, false>, a, MCL_SCORE_THREADS, smem, blocks);
+    return cnt ? launch_persistent(h, score_kernel<G, INTERP, TILE, true, false>, a, MCL_SCORE_THREADS, smem, blocks)
+               : launch_persistent(h, score_kernel<G, INTERP, TILE, false, false>, a, MCL_SCORE_THREADS, smem, blocks);
 }
 
 template <bool INTERP, bool TILE>
@@ -349,8 +351,25 @@ int launch_score_it(mcl_engine* h, int G, const ScoreArgs& a, int which, size_t 
     }
 }
 
-int launch_score(mcl_engine* h, int G, bool tile, const ScoreArgs& a, int which, size_t smem, long long local)
+// per-batch windows: one lane per particle, shared-memory tiles, fixed CTA shapes (mcl_kernels.cuh: kBatch*)
+template <bool INTERP>
+int launch_score_batch(mcl_engine* h, const ScoreArgs& a, int which, size_t smem)
 {
+    const bool cnt = h->count_gathers;
+    const long long blocks = a.num_batches;
+    if (which == 1)
+        return cnt ? launch_persistent(h, score_fast_kernel<1, INTERP, true, true, true>, a, kBatchFastThreads, smem, blocks)
+                   : launch_persistent(h, score_fast_kernel<1, INTERP, true, false, true>, a, kBatchFastThreads, smem, blocks);
+    if (which == 2)
+        return cnt ? launch_persistent(h, score_deferred_kernel<1, INTERP, true, true, true>, a, kBatchDefThreads, smem, blocks)
+                   : launch_persistent(h, score_deferred_kernel<1, INTERP, true, false, true>, a, kBatchDefThreads, smem, blocks);
+    return cnt ? launch_persistent(h, score_kernel<1, INTERP, true, true, true>, a, kBatchExactThreads, smem, blocks)
+               : launch_persistent(h, score_kernel<1, INTERP, true, false, true>, a, kBatchExactThreads, smem, blocks);
+}
+
+int launch_score(mcl_engine* h, int G, bool tile, bool batch, const ScoreArgs& a, int which, size_t smem, long long local)
+{
+    if (batch) return h->scan_interp ? launch_score_batch<true>(h, a, which, smem) : launch_score_batch<false>(h, a, which, smem);
     if (h->scan_interp)
         return tile ? launch_score_it<true, true>(h, G, a, which, smem, local) : launch_score_it<true, false>(h, G, a, which, smem, local);
     return tile ? launch_score_it<false, true>(h, G, a, which, smem, local) : launch_score_it<false, false>(h, G, a, which, smem, local);
@@ -403,15 +422,8 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     fp.rho_lo = (float)h->ratio_lo; fp.rho_hi = (float)h->ratio_hi;
     fp.max_shift = (float)max_shift;
     fp.coord_hi = (float)(Cm - 1.0);
-    const long long lcx = std::max<long long>(x0 + 1, 0), hcx = x0 + w - 1;    // certain-interior cells [lc, hc)
-    const long long lcy = std::max<long long>(y0 + 1, 0), hcy = y0 + hh - 1;
-    if (hcx <= lcx || hcy <= lcy) { fp.enabled = 0; return fp; }
-    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = 0.5f * (float)(hcx - lcx);
-    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = 0.5f * (float)(hcy - lcy);
-    fp.pitch_f = (float)pitch;
-    const unsigned mb = (unsigned)kFastMagicBits >> kFastFracBits;
-    fp.idx_bias = (int)((mb + (unsigned)(int)y0) * (unsigned)pitch + mb + (unsigned)(int)x0);
-    fp.safe_idx = (int)pitch + 1;
+    plan_set_window(fp, x0, y0, w, hh, pitch);
+    if (fp.half_x <= 0.0f || fp.half_y <= 0.0f) { fp.enabled = 0; return fp; }
     h->stats_eps = eps;
     return fp;
 }
@@ -444,7 +456,8 @@ int run_score(mcl_engine* h)
 
     // shared-memory map tile: window = bounding box of the cloud (poses and parents) +- (max range + 2 cells)
     size_t smem = (size_t)h->num_beams * sizeof(Beam);          // == sizeof(FastBeam) per beam
-    bool tile = false;
+    bool tile = false, batch = false;
+    size_t batch_tile_bytes = 0;
     if (h->params.map_tile != 1 && local > 0 && h->num_beams > 0) {
         int* box = h->bbox;
         const int init_box[4] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000};
@@ -487,6 +500,39 @@ int run_score(mcl_engine* h)
                 }
             }
         }
+        // The cloud as a whole does not fit one tile: try one window per batch of consecutive particles (they are
+        // spatial neighbours after mcl_init_uniform, and systematic resampling preserves the order).
+        if (!tile && G == 1 && h->params.map_tile != 2 && std::isfinite(h->max_range)) {
+            const long long nb = (local + kBatchParticles - 1) / kBatchParticles;
+            if ((size_t)nb > h->windows_cap) {
+                if (h->windows) cudaFree(h->windows);
+                h->windows = nullptr; h->windows_cap = 0;
+                CK(cudaMalloc((void**)&h->windows, sizeof(BatchWindow) * (size_t)nb));
+                h->windows_cap = (size_t)nb;
+            }
+            const size_t base2 = std::max(smem, deferred_smem_bytes(h->num_beams, kBatchDefThreads / 32));
+            const long long budget = (long long)h->max_smem_optin - (long long)base2 - 1024;
+            if (budget > 4096) {
+                h->host_bbox[0] = 0; h->host_bbox[1] = 0;
+                CK(cudaMemcpyAsync(h->bbox, h->host_bbox, 8, cudaMemcpyHostToDevice, h->stream));
+                batch_window_kernel<<<(int)nb, 256, 0, h->stream>>>(p.x, p.y, q.x, q.y, h->lo, h->hi, h->grid,
+                                                                   (double)h->max_range * h->grid.cells_per_meter + 3.0,
+                                                                   (int)budget, h->windows, h->bbox);
+                CKL(h);
+                CK(cudaMemcpyAsync(h->host_bbox, h->bbox, 8, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                const int max_bytes = h->host_bbox[0], misfits = h->host_bbox[1];
+                if (max_bytes > 0 && (long long)misfits * 50 <= nb) {     // at most 2 % of the batches without a tile
+                    batch = true;
+                    tile = true;
+                    a.windows = h->windows;
+                    a.num_batches = nb;
+                    batch_tile_bytes = (size_t)max_bytes;
+                    a.tile_x0 = -4; a.tile_y0 = -4; a.tile_w = h->grid.width + 8; a.tile_h = h->grid.height + 8;   // eps only
+                    a.tile_pitch = 4;
+                }
+            }
+        }
         if (h->params.map_tile == 2 && !tile)
             return fail(h, MCL_ERR_INVALID, "map_tile=2 forced but the cloud's window does not fit in shared memory");
     }
@@ -506,12 +552,13 @@ int run_score(mcl_engine* h)
             h->masks_bytes = need;
         }
         a.masks = h->masks;
-        rc = launch_score(h, G, tile, a, 1, smem, local);
+        rc = launch_score(h, G, tile, batch, a, 1, smem + batch_tile_bytes, local);
         if (rc) return rc;
-        const size_t smem2 = smem - (size_t)h->num_beams * sizeof(Beam) + deferred_smem_bytes(h->num_beams, MCL_DEF_THREADS / 32);
-        rc = launch_score(h, G, tile, a, 2, smem2, local);
+        const size_t smem2 = smem - (size_t)h->num_beams * sizeof(Beam) +
+                             deferred_smem_bytes(h->num_beams, (batch ? kBatchDefThreads : MCL_DEF_THREADS) / 32);
+        rc = launch_score(h, G, tile, batch, a, 2, smem2 + batch_tile_bytes, local);
     } else {
-        rc = launch_score(h, G, tile, a, 0, smem, local);
+        rc = launch_score(h, G, tile, batch, a, 0, smem + batch_tile_bytes, local);
     }
     if (rc) return rc;
     rc = join_pushes(h);
@@ -519,7 +566,7 @@ int run_score(mcl_engine* h)
     rc = exchange_slices(h, h->score2, sizeof(int32_t));
     if (rc) return rc;
     h->stats.lanes_per_particle = G;
-    h->stats.map_tile_used = tile ? 2 : 1;
+    h->stats.map_tile_used = batch ? 3 : (tile ? 2 : 1);
     h->stats.sensor_path = fast ? 2 : 1;
     h->stats.fast_eps = fast ? h->stats_eps : 0.0;
     h->stats.evals = local * (long long)h->num_beams;
@@ -696,7 +743,7 @@ void free_all(mcl_engine* h)
     if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
     F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
-    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks);
+    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows);
     F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
@@ -975,9 +1022,14 @@ int mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed)
     h->update_no = 0;
     const PoseSoA& p = h->pose[h->cur];
     const PoseSoA& q = h->parent[h->cur];
+    // blocks of about kBatchParticles particles each, as square as the map allows
+    const double target = std::max(1.0, (double)h->n / (double)kBatchParticles);
+    const double side = std::sqrt((double)h->grid.width * (double)h->grid.height / target);
+    const int nbx = (int)std::max(1.0, std::floor((double)h->grid.width / side));
+    const int nby = (int)std::max(1.0, std::floor((double)h->grid.height / side));
     init_uniform_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(
         p.x, p.y, p.th, q.x, q.y, q.th, h->n, h->grid.origin_x, h->grid.origin_y,
-        h->grid.width * h->meters_per_cell, h->grid.height * h->meters_per_cell, seed);
+        h->grid.width * h->meters_per_cell, h->grid.height * h->meters_per_cell, seed, nbx, nby);
     CKL(h);
     fill_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->weight[h->wcur], h->n, 1.0 / (double)h->n);
     CKL(h);

@@ -24,6 +24,15 @@ namespace mcl {
 // outside the grid, which is exactly OccupancyGrid::logOdds' out-of-grid value); reads outside the window fall back to
 // the global mirror, so the result never depends on the window choice.
 // =================================================================================================================
+// Per-batch map windows (global localisation: the cloud as a whole does not fit one shared-memory tile, but consecutive
+// particles are spatial neighbours -- mcl_init_uniform lays them out block by block and systematic resampling keeps
+// the order -- so every batch of kBatchParticles particles gets its own window, staged by the CTA that scores it).
+constexpr int kBatchParticles = 1024;
+constexpr int kBatchFastThreads = 1024;      // pass 1: one particle per thread, one CTA per SM
+constexpr int kBatchExactThreads = 512;      // exact-only kernel
+constexpr int kBatchDefThreads = 512;        // pass 2: 16 warps x 2 rounds of 32 particles
+struct __align__(16) BatchWindow { int x0, y0, w, h, pitch, bytes, pad0, pad1; };
+
 struct ScoreArgs {
     const float *x, *y, *th;        // pose (SoA)
     const float *px, *py, *pth;     // parent pose
@@ -37,22 +46,28 @@ struct ScoreArgs {
     FastPlan fast;                                       // two-pass path only
     uint32_t* masks;                                     // two-pass path: [word][virtual lane] uncertain-beam bits
     unsigned long long* deferred_counter;                // two-pass path: evaluations re-done by the exact pass
+    const BatchWindow* windows;                          // BATCH only: one map window per kBatchParticles particles
+    long long num_batches;
 };
 
-// Stages the map window of a CTA in shared memory (4-byte granules; tile_pitch and tile_x0 are multiples of 4, the
-// mirror's pitch is a multiple of 16; mirror rows are zero-padded to the pitch; outside the grid reads as 0).
-__device__ __forceinline__ void stage_tile(const ScoreArgs& a, int8_t* stile)
+// Stages a map window in shared memory (4-byte granules; pitch and x0 are multiples of 4, the mirror's pitch is a
+// multiple of 16; mirror rows are zero-padded to the pitch; outside the grid reads as 0).
+__device__ __forceinline__ void stage_window(const DevGrid& grid, int x0, int y0, int hgt, int pitch, int8_t* stile)
 {
-    const int words_per_row = a.tile_pitch >> 2;
-    const int total = words_per_row * a.tile_h;
+    const int words_per_row = pitch >> 2;
+    const int total = words_per_row * hgt;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int ty = i / words_per_row, tw = i - ty * words_per_row;
-        const int gx = a.tile_x0 + (tw << 2), gy = a.tile_y0 + ty;
+        const int gx = x0 + (tw << 2), gy = y0 + ty;
         uint32_t v = 0;
-        if ((unsigned)gy < (unsigned)a.grid.height && gx >= 0 && gx < a.grid.pitch)
-            v = __ldg(reinterpret_cast<const uint32_t*>(a.grid.cells + (size_t)gy * a.grid.pitch + gx));
+        if ((unsigned)gy < (unsigned)grid.height && gx >= 0 && gx < grid.pitch)
+            v = __ldg(reinterpret_cast<const uint32_t*>(grid.cells + (size_t)gy * grid.pitch + gx));
         reinterpret_cast<uint32_t*>(stile)[i] = v;
     }
+}
+__device__ __forceinline__ void stage_tile(const ScoreArgs& a, int8_t* stile)
+{
+    stage_window(a.grid, a.tile_x0, a.tile_y0, a.tile_h, a.tile_pitch, stile);
 }
 
 __device__ __forceinline__ Window make_window(const ScoreArgs& a, const int8_t* stile, bool tile)
@@ -68,40 +83,155 @@ __device__ __forceinline__ Window make_window(const ScoreArgs& a, const int8_t* 
     return win;
 }
 
-// ---- the literal restatement for every evaluation (sensor_path = 1, and whenever the fast pass is not applicable) ------
-template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(MCL_SCORE_THREADS, MCL_SCORE_MIN_CTAS) score_kernel(const ScoreArgs a)
+// The window-dependent fields of the fast plan (the eps-dependent ones are set by the host: mcl_engine.cu fast_plan).
+__host__ __device__ inline void plan_set_window(FastPlan& fp, long long x0, long long y0, long long w, long long hh,
+                                                long long pitch)
 {
+    const long long lcx = (x0 + 1 > 0 ? x0 + 1 : 0), hcx = x0 + w - 1;      // certain-interior cells [lc, hc)
+    const long long lcy = (y0 + 1 > 0 ? y0 + 1 : 0), hcy = y0 + hh - 1;
+    const bool empty = hcx <= lcx || hcy <= lcy;
+    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = empty ? -1.0f : 0.5f * (float)(hcx - lcx);
+    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = empty ? -1.0f : 0.5f * (float)(hcy - lcy);
+    fp.pitch_f = (float)pitch;
+    const unsigned mb = (unsigned)kFastMagicBits >> kFastFracBits;
+    fp.idx_bias = (int)((mb + (unsigned)(int)y0) * (unsigned)pitch + mb + (unsigned)(int)x0);
+    fp.safe_idx = (int)pitch + 1;          // an empty window still has (pitch >= 4) bytes of shared memory behind it
+}
+
+// Bounding box of a batch's poses and parents -> its map window, with the same rule as the single-tile path
+// (bbox +- (max range + 3 cells), clipped to the grid plus a 2-cell zero margin, 4-byte aligned, odd word pitch).
+// summary[0] = largest window in bytes among batches that fit the budget, summary[1] = batches that do not fit
+// (they get an empty window: pass 1 defers everything, the exact pass reads the global mirror).
+__device__ __forceinline__ int float_order_i(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__global__ void __launch_bounds__(256) batch_window_kernel(const float* x, const float* y, const float* px,
+                                                           const float* py, long long lo, long long hi, DevGrid grid,
+                                                           double reach, int budget_bytes, BatchWindow* out, int* summary)
+{
+    __shared__ int red[4][8];
+    const long long first = lo + (long long)blockIdx.x * kBatchParticles;
+    const long long last = first + kBatchParticles < hi ? first + kBatchParticles : hi;
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+    for (long long i = first + threadIdx.x; i < last; i += blockDim.x) {
+        const int a = float_order_i(x[i]), b = float_order_i(y[i]), c = float_order_i(px[i]), d = float_order_i(py[i]);
+        mnx = min(mnx, min(a, c)); mxx = max(mxx, max(a, c));
+        mny = min(mny, min(b, d)); mxy = max(mxy, max(b, d));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mny;
+        red[2][threadIdx.x >> 5] = mxx; red[3][threadIdx.x >> 5] = mxy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            mnx = min(mnx, red[0][k]); mny = min(mny, red[1][k]); mxx = max(mxx, red[2][k]); mxy = max(mxy, red[3][k]);
+        }
+        auto unorder = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
+        const float fx0 = unorder(mnx), fy0 = unorder(mny), fx1 = unorder(mxx), fy1 = unorder(mxy);
+        BatchWindow bw = {0, 0, 0, 0, 4, 0, 0, 0};
+        bool fits = false;
+        if (isfinite(fx0) && isfinite(fy0) && isfinite(fx1) && isfinite(fy1)) {
+            const double cpm = (double)grid.cells_per_meter;
+            const double cx0 = floor(((double)fx0 - (double)grid.origin_x) * cpm - reach);
+            const double cy0 = floor(((double)fy0 - (double)grid.origin_y) * cpm - reach);
+            const double cx1 = ceil(((double)fx1 - (double)grid.origin_x) * cpm + reach);
+            const double cy1 = ceil(((double)fy1 - (double)grid.origin_y) * cpm + reach);
+            long long x0 = (long long)fmax(cx0, -2.0), y0 = (long long)fmax(cy0, -2.0);
+            const long long x1 = (long long)fmin(cx1, (double)grid.width + 1);
+            const long long y1 = (long long)fmin(cy1, (double)grid.height + 1);
+            if (x1 >= x0 && y1 >= y0) {
+                x0 = (x0 >= 0) ? (x0 & ~3ll) : -(((-x0) + 3) & ~3ll);
+                const long long tw = x1 - x0 + 1, th = y1 - y0 + 1;
+                long long pitch = (tw + 3) & ~3ll;
+                if (((pitch >> 2) & 1) == 0) pitch += 4;
+                const long long bytes = pitch * th;
+                if (bytes <= (long long)budget_bytes) {
+                    bw.x0 = (int)x0; bw.y0 = (int)y0; bw.w = (int)tw; bw.h = (int)th; bw.pitch = (int)pitch;
+                    bw.bytes = (int)bytes;
+                    fits = true;
+                }
+            }
+        }
+        out[blockIdx.x] = bw;
+        if (fits) atomicMax(summary + 0, bw.bytes); else atomicAdd(summary + 1, 1);
+    }
+}
+
+// Work units of the three sensor kernels.  Single window (BATCH = false): one unit, the CTA strides over the whole
+// slice.  Per-batch windows (BATCH = true): CTA c takes batches c, c + gridDim.x, ...; before each it stages that
+// batch's window.  unit_range() gives the particle range and stride of the current unit.
+template <bool BATCH>
+__device__ __forceinline__ void unit_range(const ScoreArgs& a, long long unit, int ppb, long long& first, long long& last,
+                                           long long& stride)
+{
+    if (BATCH) {
+        first = a.lo + unit * kBatchParticles;
+        last = first + kBatchParticles < a.hi ? first + kBatchParticles : a.hi;
+        stride = ppb;
+    } else {
+        first = a.lo + (long long)blockIdx.x * ppb;
+        last = a.hi;
+        stride = (long long)gridDim.x * ppb;
+    }
+}
+
+// ---- the literal restatement for every evaluation (sensor_path = 1, and whenever the fast pass is not applicable) ------
+template <int G, bool INTERP, bool TILE, bool COUNT, bool BATCH>
+__global__ void __launch_bounds__(BATCH ? kBatchExactThreads : MCL_SCORE_THREADS, BATCH ? 1 : MCL_SCORE_MIN_CTAS)
+score_kernel(const ScoreArgs a)
+{
+    constexpr int T = BATCH ? kBatchExactThreads : MCL_SCORE_THREADS;
     extern __shared__ __align__(16) unsigned char smem[];
     Beam* sbeams = reinterpret_cast<Beam*>(smem);
     int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(Beam));
 
     for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
-    if (TILE) stage_tile(a, stile);
+    if (TILE && !BATCH) stage_tile(a, stile);
     __syncthreads();
 
-    const Window win = make_window(a, stile, TILE);
+    Window win = make_window(a, stile, TILE);
     GridConst gc;
     gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
     gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
     gc.trig = gs_load_consts();
 
-    constexpr int PPB = MCL_SCORE_THREADS / G;   // particles per CTA per iteration
+    constexpr int PPB = T / G;                   // particles per CTA per iteration
     const int sub = threadIdx.x % G;
     const int slot = threadIdx.x / G;
     int gathers = 0;
-    for (long long base = a.lo + (long long)blockIdx.x * PPB; base < a.hi; base += (long long)gridDim.x * PPB) {
-        const long long p = base + slot;
-        int acc = 0;
-        if (p < a.hi) {
-            const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
-MCL_UNROLL(MCL_BEAM_UNROLL)
-            for (int j = sub; j < a.num_beams; j += G)
-                acc += score_beam<INTERP, TILE, COUNT>(rb, sbeams[j], gc, win, a.grid, gathers);
+    const long long nunits = BATCH ? a.num_batches : 1;
+    for (long long unit = BATCH ? blockIdx.x : 0; unit < nunits; unit += BATCH ? gridDim.x : 1) {
+        if (BATCH) {
+            const BatchWindow bw = a.windows[unit];
+            __syncthreads();
+            stage_window(a.grid, bw.x0, bw.y0, bw.h, bw.pitch, stile);
+            __syncthreads();
+            win.x0 = bw.x0; win.y0 = bw.y0; win.w = bw.w; win.h = bw.h; win.pitch = bw.pitch;
         }
+        long long first, last, stride;
+        unit_range<BATCH>(a, unit, PPB, first, last, stride);
+        for (long long base = first; base < last; base += stride) {
+            const long long p = base + slot;
+            int acc = 0;
+            if (p < last) {
+                const RayBase rb = make_ray_base(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p]);
+MCL_UNROLL(MCL_BEAM_UNROLL)
+                for (int j = sub; j < a.num_beams; j += G)
+                    acc += score_beam<INTERP, TILE, COUNT>(rb, sbeams[j], gc, win, a.grid, gathers);
+            }
 #pragma unroll
-        for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (sub == 0 && p < a.hi) a.score2[p] = acc;
+            for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (sub == 0 && p < last) a.score2[p] = acc;
+        }
     }
     if (COUNT) {
 #pragma unroll
@@ -122,9 +252,11 @@ MCL_UNROLL(MCL_BEAM_UNROLL)
 #ifndef MCL_FAST_UNROLL
 #define MCL_FAST_UNROLL 2
 #endif
-template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(MCL_FAST_THREADS, MCL_FAST_MIN_CTAS) score_fast_kernel(const ScoreArgs a)
+template <int G, bool INTERP, bool TILE, bool COUNT, bool BATCH>
+__global__ void __launch_bounds__(BATCH ? kBatchFastThreads : MCL_FAST_THREADS, BATCH ? 1 : MCL_FAST_MIN_CTAS)
+score_fast_kernel(const ScoreArgs a)
 {
+    constexpr int T = BATCH ? kBatchFastThreads : MCL_FAST_THREADS;
     extern __shared__ __align__(16) unsigned char smem[];
     FastBeam* sfast = reinterpret_cast<FastBeam*>(smem);
     int8_t* stile = reinterpret_cast<int8_t*>(smem + (size_t)a.num_beams * sizeof(FastBeam));
@@ -135,54 +267,68 @@ __global__ void __launch_bounds__(MCL_FAST_THREADS, MCL_FAST_MIN_CTAS) score_fas
         f.ratio = (float)b.ratio; f.theta = b.theta; f.rc = __fmul_rn(b.range, a.grid.cells_per_meter); f.pad = 0.0f;
         sfast[i] = f;
     }
-    if (TILE) stage_tile(a, stile);
+    if (TILE && !BATCH) stage_tile(a, stile);
     __syncthreads();
 
     const int8_t* cells = TILE ? stile : a.grid.cells;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stile);
-    const int pitch = TILE ? a.tile_pitch : a.grid.pitch;
-    const FastPlan fp = a.fast;
+    int pitch = TILE ? a.tile_pitch : a.grid.pitch;
+    FastPlan fp = a.fast;
     const double gx = (double)a.grid.origin_x, gy = (double)a.grid.origin_y, cpm_d = (double)a.grid.cells_per_meter;
     const int iters = (a.num_beams + G - 1) / G;                 // beams per lane
     const int nwords = (iters + 31) / 32;
     const long long vlanes = (a.hi - a.lo) * G;
 
-    constexpr int PPB = MCL_FAST_THREADS / G;
+    constexpr int PPB = T / G;
     const int sub = threadIdx.x % G;
     const int slot = threadIdx.x / G;
     int gathers = 0;
-    for (long long base = a.lo + (long long)blockIdx.x * PPB; base < a.hi; base += (long long)gridDim.x * PPB) {
-        const long long p = base + slot;
-        int acc = 0;
-        if (p < a.hi) {
-            const FastBase fb = make_fast_base<INTERP>(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p], gx, gy, cpm_d, fp);
-            uint32_t* mrow = a.masks + ((p - a.lo) * G + sub);
-            for (int w = 0; w < nwords; ++w) {
-                uint32_t m = 0;
-                const int kend = min(32, iters - w * 32);
-                if (fb.ok) {
-                    uint32_t bit = 1u;
-MCL_UNROLL(MCL_FAST_UNROLL)
-                    for (int k = 0; k < kend; ++k) {
-                        const int j = sub + (w * 32 + k) * G;
-                        const bool inb = G == 1 || j < a.num_beams;      // G == 1: kend already bounds j
-                        int v = 0, g = 0;
-                        const bool certain =
-                            score_beam_fast<INTERP, TILE, COUNT>(fb, sfast[inb ? j : 0], fp, cells, sbase, pitch, v, g);
-                        acc += inb ? v : 0;
-                        if (COUNT) gathers += inb ? g : 0;
-                        if (inb & !certain) m |= bit;
-                        bit += bit;
-                    }
-                } else {
-                    for (int k = 0; k < kend; ++k) m |= (uint32_t)(sub + (w * 32 + k) * G < a.num_beams) << k;
-                }
-                mrow[(long long)w * vlanes] = m;
-            }
+    const long long nunits = BATCH ? a.num_batches : 1;
+    for (long long unit = BATCH ? blockIdx.x : 0; unit < nunits; unit += BATCH ? gridDim.x : 1) {
+        if (BATCH) {
+            const BatchWindow bw = a.windows[unit];
+            __syncthreads();
+            stage_window(a.grid, bw.x0, bw.y0, bw.h, bw.pitch, stile);
+            __syncthreads();
+            plan_set_window(fp, bw.x0, bw.y0, bw.w, bw.h, bw.pitch);
+            pitch = bw.pitch;
         }
+        long long first, last, stride;
+        unit_range<BATCH>(a, unit, PPB, first, last, stride);
+        for (long long base = first; base < last; base += stride) {
+            const long long p = base + slot;
+            int acc = 0;
+            if (p < last) {
+                const FastBase fb =
+                    make_fast_base<INTERP>(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p], gx, gy, cpm_d, fp);
+                uint32_t* mrow = a.masks + ((p - a.lo) * G + sub);
+                for (int w = 0; w < nwords; ++w) {
+                    uint32_t m = 0;
+                    const int kend = min(32, iters - w * 32);
+                    if (fb.ok) {
+                        uint32_t bit = 1u;
+MCL_UNROLL(MCL_FAST_UNROLL)
+                        for (int k = 0; k < kend; ++k) {
+                            const int j = sub + (w * 32 + k) * G;
+                            const bool inb = G == 1 || j < a.num_beams;      // G == 1: kend already bounds j
+                            int v = 0, g = 0;
+                            const bool certain = score_beam_fast<INTERP, TILE, COUNT>(fb, sfast[inb ? j : 0], fp, cells,
+                                                                                      sbase, pitch, v, g);
+                            acc += inb ? v : 0;
+                            if (COUNT) gathers += inb ? g : 0;
+                            if (inb & !certain) m |= bit;
+                            bit += bit;
+                        }
+                    } else {
+                        for (int k = 0; k < kend; ++k) m |= (uint32_t)(sub + (w * 32 + k) * G < a.num_beams) << k;
+                    }
+                    mrow[(long long)w * vlanes] = m;
+                }
+            }
 #pragma unroll
-        for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (sub == 0 && p < a.hi) a.score2[p] = acc;
+            for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (sub == 0 && p < last) a.score2[p] = acc;
+        }
     }
     if (COUNT) {
 #pragma unroll
@@ -211,21 +357,23 @@ __host__ __device__ inline size_t deferred_smem_bytes(int num_beams, int warps)
     return (size_t)num_beams * sizeof(Beam) + (size_t)warps * (kDefQueue * sizeof(uint16_t) + 32 * sizeof(DefParticle));
 }
 
-template <int G, bool INTERP, bool TILE, bool COUNT>
-__global__ void __launch_bounds__(MCL_DEF_THREADS, MCL_DEF_MIN_CTAS) score_deferred_kernel(const ScoreArgs a)
+template <int G, bool INTERP, bool TILE, bool COUNT, bool BATCH>
+__global__ void __launch_bounds__(BATCH ? kBatchDefThreads : MCL_DEF_THREADS, BATCH ? 1 : MCL_DEF_MIN_CTAS)
+score_deferred_kernel(const ScoreArgs a)
 {
+    constexpr int T = BATCH ? kBatchDefThreads : MCL_DEF_THREADS;
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int WARPS = MCL_DEF_THREADS / 32;
+    constexpr int WARPS = T / 32;
     Beam* sbeams = reinterpret_cast<Beam*>(smem);
     DefParticle* spart_all = reinterpret_cast<DefParticle*>(smem + (size_t)a.num_beams * sizeof(Beam));
     uint16_t* squeue_all = reinterpret_cast<uint16_t*>(spart_all + WARPS * 32);
     int8_t* stile = reinterpret_cast<int8_t*>(smem + deferred_smem_bytes(a.num_beams, WARPS));
 
     for (int i = threadIdx.x; i < a.num_beams; i += blockDim.x) sbeams[i] = a.beams[i];
-    if (TILE) stage_tile(a, stile);
+    if (TILE && !BATCH) stage_tile(a, stile);
     __syncthreads();
 
-    const Window win = make_window(a, stile, TILE);
+    Window win = make_window(a, stile, TILE);
     GridConst gc;
     gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
     gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
@@ -250,64 +398,84 @@ __global__ void __launch_bounds__(MCL_DEF_THREADS, MCL_DEF_MIN_CTAS) score_defer
         ++deferred;
     };
 
-    const long long nblocks = (vlanes + 31) / 32;
-    for (long long blk = (long long)blockIdx.x * WARPS + warp; blk < nblocks; blk += (long long)gridDim.x * WARPS) {
-        const long long v0 = blk * 32;
-        const long long v = v0 + lane;
-        // stage the particles of this block (32/G of them)
-        if (lane < 32 / G) {
-            const long long p = a.lo + v0 / G + lane;
-            DefParticle dp;
-            dp.acc = 0; dp.pad = 0;
-            if (p < a.hi) {
-                dp.xa = a.x[p]; dp.ya = a.y[p]; dp.tha = a.th[p]; dp.xb = a.px[p]; dp.yb = a.py[p]; dp.thb = a.pth[p];
-            } else {
-                dp.xa = dp.ya = dp.tha = dp.xb = dp.yb = dp.thb = 0.0f;
-            }
-            spart[lane] = dp;
+    // work units: blocks of 32 virtual lanes.  BATCH: the blocks of one batch at a time, behind that batch's window.
+    const long long nblocks_all = (vlanes + 31) / 32;
+    constexpr long long kBlocksPerBatch = (long long)kBatchParticles * G / 32;
+    const long long nunits = BATCH ? a.num_batches : 1;
+    for (long long unit = BATCH ? blockIdx.x : 0; unit < nunits; unit += BATCH ? gridDim.x : 1) {
+        long long bfirst, blast, bstride;
+        if (BATCH) {
+            const BatchWindow bw = a.windows[unit];
+            __syncthreads();
+            stage_window(a.grid, bw.x0, bw.y0, bw.h, bw.pitch, stile);
+            __syncthreads();
+            win.x0 = bw.x0; win.y0 = bw.y0; win.w = bw.w; win.h = bw.h; win.pitch = bw.pitch;
+            bfirst = unit * kBlocksPerBatch + warp;
+            blast = (unit + 1) * kBlocksPerBatch < nblocks_all ? (unit + 1) * kBlocksPerBatch : nblocks_all;
+            bstride = WARPS;
+        } else {
+            bfirst = (long long)blockIdx.x * WARPS + warp;
+            blast = nblocks_all;
+            bstride = (long long)gridDim.x * WARPS;
         }
-        __syncwarp();
-        int qn = 0;
-        uint32_t mbuf[4];                        // mask words are fetched four at a time: one exposed latency per four
-        for (int w = 0; w < nwords; ++w) {
-            if ((w & 3) == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    mbuf[q] = (v < vlanes && w + q < nwords) ? __ldcs(a.masks + ((long long)(w + q) * vlanes + v)) : 0u;
-            }
-            uint32_t m = mbuf[0];
-            mbuf[0] = mbuf[1]; mbuf[1] = mbuf[2]; mbuf[2] = mbuf[3];
-            const int c = __popc(m);
-            int incl = c;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            int pos = qn + incl - c;
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                squeue[pos++] = (uint16_t)((w << 10) | (lane << 5) | k);
-            }
-            qn += total;
-            __syncwarp();
-            while (qn >= 32) {
-                qn -= 32;
-                evaluate(squeue[qn + lane]);
+        for (long long blk = bfirst; blk < blast; blk += bstride) {
+            const long long v0 = blk * 32;
+            const long long v = v0 + lane;
+            // stage the particles of this block (32/G of them)
+            if (lane < 32 / G) {
+                const long long p = a.lo + v0 / G + lane;
+                DefParticle dp;
+                dp.acc = 0; dp.pad = 0;
+                if (p < a.hi) {
+                    dp.xa = a.x[p]; dp.ya = a.y[p]; dp.tha = a.th[p]; dp.xb = a.px[p]; dp.yb = a.py[p]; dp.thb = a.pth[p];
+                } else {
+                    dp.xa = dp.ya = dp.tha = dp.xb = dp.yb = dp.thb = 0.0f;
+                }
+                spart[lane] = dp;
             }
             __syncwarp();
+            int qn = 0;
+            uint32_t mbuf[4];                    // mask words are fetched four at a time: one exposed latency per four
+            for (int w = 0; w < nwords; ++w) {
+                if ((w & 3) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        mbuf[q] = (v < vlanes && w + q < nwords) ? __ldcs(a.masks + ((long long)(w + q) * vlanes + v)) : 0u;
+                }
+                uint32_t m = mbuf[0];
+                mbuf[0] = mbuf[1]; mbuf[1] = mbuf[2]; mbuf[2] = mbuf[3];
+                const int c = __popc(m);
+                int incl = c;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total == 0) continue;
+                int pos = qn + incl - c;
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    squeue[pos++] = (uint16_t)((w << 10) | (lane << 5) | k);
+                }
+                qn += total;
+                __syncwarp();
+                while (qn >= 32) {
+                    qn -= 32;
+                    evaluate(squeue[qn + lane]);
+                }
+                __syncwarp();
+            }
+            if (lane < qn) evaluate(squeue[lane]);
+            __syncwarp();
+            if (lane < 32 / G) {
+                const long long p = a.lo + v0 / G + lane;
+                const int add = spart[lane].acc;
+                if (p < a.hi && add != 0) a.score2[p] += add;
+            }
+            __syncwarp();
         }
-        if (lane < qn) evaluate(squeue[lane]);
-        __syncwarp();
-        if (lane < 32 / G) {
-            const long long p = a.lo + v0 / G + lane;
-            const int add = spart[lane].acc;
-            if (p < a.hi && add != 0) a.score2[p] += add;
-        }
-        __syncwarp();
     }
     if (COUNT) {
 #pragma unroll
@@ -845,14 +1013,22 @@ __global__ void init_at_pose_kernel(float* x, float* y, float* th, float* px, fl
 }
 
 __global__ void init_uniform_kernel(float* x, float* y, float* th, float* px, float* py, float* pth, long long n,
-                                    float gx, float gy, float wm, float hm, uint64_t seed)
+                                    float gx, float gy, float wm, float hm, uint64_t seed, int nbx, int nby)
 {
+    // stratified: particle i belongs to block b = floor(i * NB / n); blocks are visited row by row, alternate rows
+    // right-to-left, so consecutive blocks (and therefore consecutive particles) are always neighbours
+    const long long nblk = (long long)nbx * nby;
+    const float bwm = wm / (float)nbx, bhm = hm / (float)nby;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const uint4 w = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0u, 0x554e4946u),
                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const long long b = (long long)(((unsigned __int128)(unsigned long long)i * (unsigned long long)nblk) / (unsigned long long)n);
+        const int by = (int)(b / nbx);
+        int bx = (int)(b - (long long)by * nbx);
+        if (by & 1) bx = nbx - 1 - bx;
         const float k = 2.3283064365386963e-10f;
-        const float xs = gx + wm * ((float)w.x * k);
-        const float ys = gy + hm * ((float)w.y * k);
+        const float xs = gx + bwm * ((float)bx + (float)w.x * k);
+        const float ys = gy + bhm * ((float)by + (float)w.y * k);
         const float ts = wrap_to_pi((float)(((double)w.z * 2.3283064365386963e-10 - 0.5) * kTwoPi));
         x[i] = px[i] = xs; y[i] = py[i] = ys; th[i] = pth[i] = ts;
     }

@@ -71,7 +71,7 @@ typedef struct {
     double  effective_sample_size;
     float   ms_resample, ms_action, ms_score, ms_normalize, ms_estimate, ms_total;  /* last mcl_update, CUDA events */
     int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
-    int     map_tile_used;        /* 1 = L2/global gathers, 2 = shared-memory tile */
+    int     map_tile_used;        /* 1 = L2/global gathers, 2 = one shared-memory tile, 3 = one tile per batch of 1024 particles */
     int     kernel_launches;      /* kernels launched by the last mcl_update */
     int     collectives;          /* slice exchanges enqueued by the last mcl_update (0 on one GPU) */
     int     peer_push;            /* 1: pose slices travel by copy-engine peer writes (CUDA IPC), else NCCL all-gather */
@@ -108,7 +108,10 @@ int  mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const in
 /* ParticleFilter::initializeFilterAtPose (particle_filter.cpp:16-34) with the intended weight 1.0/N and a seeded
  * counter-based generator instead of std::random_device. */
 int  mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime, uint64_t seed);
-/* Extension for global localisation (no reference equivalent): x,y uniform over the map, theta uniform in [-pi,pi). */
+/* Extension for global localisation (no reference equivalent): x,y uniform over the map, theta uniform in [-pi,pi).
+ * The sample is stratified: the map is cut into equal blocks (about 1024 particles each), consecutive particles fill
+ * one block after the other in serpentine order, each uniform inside its block -- so consecutive particles are spatial
+ * neighbours, which systematic resampling preserves and the sensor kernels exploit (one map window per batch). */
 int  mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed);
 /* AoS particle_t in/out (ParticleFilter::particles, particle_filter.cpp:75-81).  All particles must share one
  * pose.utime and one parent_pose.utime (true for every cloud the reference produces).  Export writes

@@ -569,3 +569,69 @@ def test_certification_margin(side, kind):
     assert eps > 0
     assert dev_e <= 0.6 * eps, (dev_e, eps)
     assert dev_x2 <= 1.2 * eps, (dev_x2, eps)             # the extended point doubles the ray term; certified at 3 eps
+
+
+# ------------------------------------------------------------------ per-batch map windows (global localisation clouds)
+def test_init_uniform_is_stratified_and_ordered():
+    """mcl_init_uniform: every particle inside the map, headings in [-pi, pi), equal counts per block, and consecutive
+    particles close together (the order the per-batch windows rely on)."""
+    grid = synth.make_map(2000, seed=3)
+    n = 1 << 20
+    e = make_engine(n, grid)
+    e.init_uniform(utime=5, seed=9)
+    c = e.export_particles()
+    e.close()
+    x, y, th = c["pose"]["x"], c["pose"]["y"], c["pose"]["theta"]
+    ext = grid.width * grid.meters_per_cell
+    assert x.min() >= grid.origin_x and x.max() <= grid.origin_x + ext
+    assert y.min() >= grid.origin_y and y.max() <= grid.origin_y + ext
+    assert th.min() >= -np.pi and th.max() <= np.pi
+    assert np.array_equal(c["pose"]["x"], c["parent_pose"]["x"]) and np.all(c["weight"] == 1.0 / n)
+    # uniform coverage: a 10 x 10 histogram within 3 % of flat
+    hist, _, _ = np.histogram2d(x, y, bins=10)
+    assert np.abs(hist / (n / 100) - 1).max() < 0.03
+    # locality: any 1024 consecutive particles span a few metres, not the 100 m map
+    span = np.maximum(x.reshape(-1, 1024).max(1) - x.reshape(-1, 1024).min(1),
+                      y.reshape(-1, 1024).max(1) - y.reshape(-1, 1024).min(1))
+    assert span.max() < 0.1 * ext
+
+
+@pytest.mark.parametrize("side,n", [(2000, 1_500_000), (1000, 700_001)])
+def test_batch_windows_equal_exact_and_oracle(side, n):
+    """A uniformly initialised cloud over a map far larger than one shared-memory tile is scored behind per-batch
+    windows (stats: map_tile_used == 3).  Scores must equal the exact-only path's, the L2-gather path's, and the
+    oracle's on a sub-sample, before and after a full update."""
+    grid = synth.make_map(side, seed=side + 7)
+    rng = np.random.default_rng(n)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=3)
+    engines = {name: make_engine(n, grid, **kw) for name, kw in
+               {"two_pass": {}, "exact": {"sensor_path": 1}, "l2": {"map_tile": 1}}.items()}
+    scores = {}
+    for name, e in engines.items():
+        e.init_uniform(utime=int(t[0]) - 100_000, seed=11)
+        scores[name] = e.score(r, th, t)
+    st = {k: e.stats() for k, e in engines.items()}
+    assert st["two_pass"]["map_tile_used"] == 3 and st["two_pass"]["sensor_path"] == 2
+    assert st["exact"]["map_tile_used"] == 3 and st["exact"]["sensor_path"] == 1
+    assert st["l2"]["map_tile_used"] == 1
+    assert np.array_equal(scores["two_pass"], scores["exact"]) and np.array_equal(scores["two_pass"], scores["l2"])
+    sub = engines["two_pass"].export_particles(stride=97)
+    want, _, _ = port.likelihood(port_grid(grid), sub, r, th, t)
+    assert np.array_equal(scores["two_pass"][::97], want)
+    # one full update (resample -> action -> score ...) keeps the order, hence the mode, and the paths agree
+    am = engine.ActionModel()
+    am.update(0.0, 0.0, 0.0, int(t[0]) - 100_000)
+    assert am.update(0.02, 0.01, 0.01, int(t[-1]))
+    clouds = {}
+    for name in ("two_pass", "exact"):
+        e = engines[name]
+        e.update(am, int(t[-1]), r, th, t, 0.37 / n)
+        clouds[name] = e.export_particles()
+        assert e.stats()["map_tile_used"] == 3
+    for k in ("pose", "parent_pose"):
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(clouds["two_pass"][k][f], clouds["exact"][k][f])
+    assert np.array_equal(clouds["two_pass"]["weight"], clouds["exact"]["weight"])
+    for e in engines.values():
+        e.close()
