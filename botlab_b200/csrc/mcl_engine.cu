@@ -72,6 +72,13 @@ struct mcl_engine {
     unsigned long long* overruns = nullptr;
     unsigned long long* gather_counter = nullptr;
     unsigned long long* deferred_counter = nullptr;
+    Beam* map_beams = nullptr;          // map update: its own prepared beams (device / pinned), counts window, flag
+    Beam* map_beams_host = nullptr;
+    int map_beams_cap = 0;
+    uint32_t* map_counts = nullptr;
+    size_t map_counts_cap = 0;
+    int* map_flag = nullptr;
+    int* map_flag_host = nullptr;
     BatchWindow* windows = nullptr;     // per-batch map windows (global localisation)
     size_t windows_cap = 0;
     uint32_t* masks = nullptr;          // two-pass sensor path: uncertain-beam bits, [word][virtual lane]
@@ -743,7 +750,9 @@ void free_all(mcl_engine* h)
     if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
     F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
-    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows);
+    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
+    if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
+    if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
     F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
@@ -989,6 +998,120 @@ int mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const int
     CK(cudaMemcpy2DAsync(h->map + (size_t)y0 * h->grid.pitch + x0, h->grid.pitch, src, src_stride, w, hgt,
                          cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+int mcl_read_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, int8_t* dst, int dst_stride)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    if (!dst || w <= 0 || hgt <= 0 || x0 < 0 || y0 < 0 || x0 + w > h->grid.width || y0 + hgt > h->grid.height ||
+        dst_stride < w)
+        return fail(h, MCL_ERR_INVALID, "bad map rectangle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2DAsync(dst, dst_stride, h->map + (size_t)y0 * h->grid.pitch + x0, h->grid.pitch, w, hgt,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+// Mapping::updateMap (mapping.cpp:17-40) applied to the device mirror.
+int mcl_map_update(mcl_engine* h, const mcl_pose_t* previous_pose, const mcl_pose_t* pose, int initialized,
+                   const float* ranges, const float* thetas, const int64_t* times, int num_ranges,
+                   float max_laser_distance, int hit_odds, int miss_odds, int* rect_xywh_out)
+{
+    if (!h || !previous_pose || !pose) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    if (num_ranges < 0 || (num_ranges > 0 && (!ranges || !thetas || !times))) return fail(h, MCL_ERR_INVALID, "bad scan arrays");
+    if (hit_odds < 0 || hit_odds > 127 || miss_odds < 0 || miss_odds > 127)
+        return fail(h, MCL_ERR_INVALID, "hit/miss odds must be in [0, 127] (the parallel form relies on one-signed saturating adds)");
+    if (rect_xywh_out) rect_xywh_out[0] = rect_xywh_out[1] = rect_xywh_out[2] = rect_xywh_out[3] = 0;
+    // mapping.cpp:19-21: the first call latches the pose and changes no cell (increase/decreaseCellOdds test initialized_)
+    if (!initialized || num_ranges == 0) return MCL_OK;
+    if (!std::isfinite(pose->x) || !std::isfinite(pose->y) || !std::isfinite(pose->theta) ||
+        !std::isfinite(previous_pose->x) || !std::isfinite(previous_pose->y) || !std::isfinite(previous_pose->theta))
+        return fail(h, MCL_ERR_INVALID, "non-finite pose");
+    CK(cudaSetDevice(h->device));
+    if (num_ranges > h->map_beams_cap) {
+        if (h->map_beams) cudaFree(h->map_beams);
+        if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
+        h->map_beams = nullptr; h->map_beams_host = nullptr;
+        const int cap = std::max(num_ranges, 1024);
+        CK(cudaMalloc((void**)&h->map_beams, sizeof(Beam) * cap));
+        CK(cudaMallocHost((void**)&h->map_beams_host, sizeof(Beam) * cap));
+        h->map_beams_cap = cap;
+    }
+    if (!h->map_flag) {
+        CK(cudaMalloc((void**)&h->map_flag, sizeof(int)));
+        CK(cudaMallocHost((void**)&h->map_flag_host, sizeof(int)));
+    }
+    // MovingLaserScan(scan, previousPose_, pose): beams with range > 0.15 m, ratio between the two poses' utimes
+    const bool interp = previous_pose->utime != pose->utime;              // interpolation.hpp:29-34
+    const double denom = (double)(pose->utime - previous_pose->utime);
+    int k = 0;
+    float reach_m = 0.0f;
+    for (int i = 0; i < num_ranges; ++i) {
+        if (ranges[i] > h->params.min_range) {                            // moving_laser_scan.cpp:24
+            Beam b;
+            b.range = ranges[i];
+            b.theta = thetas[i];
+            b.ratio = interp ? (double)(times[i] - previous_pose->utime) / denom : 1.0;
+            h->map_beams_host[k++] = b;
+            if (ranges[i] <= max_laser_distance) reach_m = std::max(reach_m, ranges[i]);
+        }
+    }
+    if (k == 0 || reach_m == 0.0f) return MCL_OK;
+    // count window: both poses (and every interpolated / extrapolated origin between them) +- reach, clipped to the grid
+    double rlo = 0.0, rhi = 1.0;
+    for (int i = 0; i < k; ++i) { rlo = std::min(rlo, h->map_beams_host[i].ratio); rhi = std::max(rhi, h->map_beams_host[i].ratio); }
+    const double cpm = h->grid.cells_per_meter;
+    auto cellx = [&](double x) { return (x - h->grid.origin_x) * cpm; };
+    auto celly = [&](double y) { return (y - h->grid.origin_y) * cpm; };
+    const double dxm = (double)pose->x - previous_pose->x, dym = (double)pose->y - previous_pose->y;
+    const double xs[2] = {previous_pose->x + dxm * rlo, previous_pose->x + dxm * rhi};
+    const double ys[2] = {previous_pose->y + dym * rlo, previous_pose->y + dym * rhi};
+    const double reach = (double)reach_m * cpm + 3.0;
+    long long x0 = (long long)std::floor(std::min(cellx(xs[0]), cellx(xs[1])) - reach);
+    long long y0 = (long long)std::floor(std::min(celly(ys[0]), celly(ys[1])) - reach);
+    long long x1 = (long long)std::ceil(std::max(cellx(xs[0]), cellx(xs[1])) + reach);
+    long long y1 = (long long)std::ceil(std::max(celly(ys[0]), celly(ys[1])) + reach);
+    x0 = std::max<long long>(x0, 0); y0 = std::max<long long>(y0, 0);
+    x1 = std::min<long long>(x1, h->grid.width - 1); y1 = std::min<long long>(y1, h->grid.height - 1);
+    if (x1 < x0 || y1 < y0) return MCL_OK;                                // every touched cell is outside the grid
+    const int ww = (int)(x1 - x0 + 1), wh = (int)(y1 - y0 + 1);
+    const size_t need = (size_t)ww * wh;
+    if (need > h->map_counts_cap) {
+        if (h->map_counts) cudaFree(h->map_counts);
+        h->map_counts = nullptr; h->map_counts_cap = 0;
+        CK(cudaMalloc((void**)&h->map_counts, need * sizeof(uint32_t)));
+        h->map_counts_cap = need;
+    }
+    CK(cudaMemcpyAsync(h->map_beams, h->map_beams_host, sizeof(Beam) * k, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->map_counts, 0, need * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->map_flag, 0, sizeof(int), h->stream));
+    MapUpdateArgs a{};
+    a.beams = h->map_beams; a.num_beams = k;
+    a.xa = pose->x; a.ya = pose->y; a.tha = pose->theta;
+    a.xb = previous_pose->x; a.yb = previous_pose->y; a.thb = previous_pose->theta;
+    a.max_laser_distance = max_laser_distance;
+    a.grid = h->grid;
+    a.wx0 = (int)x0; a.wy0 = (int)y0; a.ww = ww; a.wh = wh;
+    a.counts = h->map_counts;
+    a.error_flag = h->map_flag;
+    const int blocks = (k + 127) / 128;
+    if (interp) map_count_kernel<true><<<blocks, 128, 0, h->stream>>>(a);
+    else map_count_kernel<false><<<blocks, 128, 0, h->stream>>>(a);
+    CKL(h);
+    CK(cudaMemcpyAsync(h->map_flag_host, h->map_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (*h->map_flag_host != 0)       // nothing has been written to the map yet
+        return fail(h, MCL_ERR_INVALID, *h->map_flag_host == 1 ? "map update: ray coordinates out of range"
+                                                               : "map update: a ray left the count window");
+    map_apply_kernel<<<grid_for(h, (long long)need, 256), 256, 0, h->stream>>>(h->map, h->grid.pitch, a.wx0, a.wy0, ww, wh,
+                                                                              h->map_counts, hit_odds, miss_odds);
+    CKL(h);
+    CK(cudaStreamSynchronize(h->stream));
+    if (rect_xywh_out) { rect_xywh_out[0] = a.wx0; rect_xywh_out[1] = a.wy0; rect_xywh_out[2] = ww; rect_xywh_out[3] = wh; }
     return MCL_OK;
 }
 

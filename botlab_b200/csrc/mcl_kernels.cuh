@@ -992,6 +992,82 @@ __global__ void resample_search_kernel(const double* cum, long long n, double r,
 }
 
 // =================================================================================================================
+// K5  map update on the device mirror: Mapping::updateMap (mapping.cpp:17-127).
+// The reference raises the endpoint cell of every ray by hitOdds (saturating at 127), THEN lowers every cell of each
+// ray's Bresenham walk (start cell up to, not including, the endpoint cell) by missOdds (saturating at -128), one ray
+// after the other.  Saturating adds of one sign commute, so the parallel form is exact: count, per cell, how many
+// endpoints (high half-word) and how many walk visits (low half-word) it receives, then apply
+//     v = max(-128, min(127, v + hits*hitOdds) - visits*missOdds).
+// The rays are the MovingLaserScan between the previous and the current SLAM pose, built with the same
+// exactly-rounded arithmetic as the sensor model (exact_endpoint).
+// =================================================================================================================
+struct MapUpdateArgs {
+    const Beam* beams;          // valid beams (range > min_range) with ratios between the two poses' utimes
+    int num_beams;
+    float xa, ya, tha, xb, yb, thb;   // current pose (end of sweep) / previous pose
+    float max_laser_distance;
+    DevGrid grid;
+    int wx0, wy0, ww, wh;       // count window (grid cells); every touched in-grid cell must fall inside
+    uint32_t* counts;           // [wh][ww], zeroed
+    int* error_flag;            // set when a ray leaves the count window or has unusable coordinates
+};
+
+template <bool INTERP>
+__global__ void __launch_bounds__(128) map_count_kernel(const MapUpdateArgs a)
+{
+    GridConst gc;
+    gc.gx = (double)a.grid.origin_x; gc.gy = (double)a.grid.origin_y;
+    gc.cpm = a.grid.cells_per_meter; gc.cpm_d = (double)a.grid.cells_per_meter;
+    gc.trig = gs_load_consts();
+    const RayBase rb = make_ray_base(a.xa, a.ya, a.tha, a.xb, a.yb, a.thb);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.num_beams; j += gridDim.x * blockDim.x) {
+        const Beam b = a.beams[j];
+        if (!(b.range <= a.max_laser_distance)) continue;                    // mapping.cpp:43, :60
+        float sx, sy, px, py, e1x, e1y;
+        exact_endpoint<INTERP>(rb, b, gc, sx, sy, px, py, e1x, e1y);
+        const int cx = f2i_x86(e1x), cy = f2i_x86(e1y);                       // :48-49
+        int x = f2i_x86(sx), y = f2i_x86(sy);                                 // bresenham(rayStart.x, ...) :68
+        // the reference would walk (practically) forever on such coordinates; report instead
+        if (abs(cx) > (1 << 20) || abs(cy) > (1 << 20) || abs(x) > (1 << 20) || abs(y) > (1 << 20)) {
+            atomicExch(a.error_flag, 1);
+            continue;
+        }
+        auto bump = [&](int gx, int gy, uint32_t inc) {
+            if ((unsigned)gx >= (unsigned)a.grid.width || (unsigned)gy >= (unsigned)a.grid.height) return;   // isCellInGrid
+            const int tx = gx - a.wx0, ty = gy - a.wy0;
+            if ((unsigned)tx >= (unsigned)a.ww || (unsigned)ty >= (unsigned)a.wh) { atomicExch(a.error_flag, 2); return; }
+            atomicAdd(a.counts + (size_t)ty * a.ww + tx, inc);
+        };
+        bump(cx, cy, 1u << 16);                                               // scoreEndpoint :42-57
+        const int dx = abs(cx - x), dy = abs(cy - y);                         // bresenham :101-127
+        const int stepx = x < cx ? 1 : -1, stepy = y < cy ? 1 : -1;
+        int err = dx - dy;
+        while (x != cx || y != cy) {
+            bump(x, y, 1u);
+            const int e2 = 2 * err;        // the reference compares (float)(2*err): exact below 2^24
+            if (e2 >= -dy) { err -= dy; x += stepx; }
+            if (e2 <= dx) { err += dx; y += stepy; }
+        }
+    }
+}
+
+__global__ void map_apply_kernel(int8_t* cells, int pitch, int wx0, int wy0, int ww, int wh, const uint32_t* counts,
+                                 int hit, int miss)
+{
+    const int total = ww * wh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i];
+        if (c == 0) continue;
+        const int ty = i / ww, tx = i - ty * ww;
+        int8_t* cell = cells + (size_t)(wy0 + ty) * pitch + (wx0 + tx);
+        int v = *cell;
+        v = min(127, v + (int)(c >> 16) * hit);            // increaseCellOdds x hits   (mapping.cpp:73-85)
+        v = max(-128, v - (int)(c & 0xffffu) * miss);      // decreaseCellOdds x visits (:87-99)
+        *cell = (int8_t)v;
+    }
+}
+
+// =================================================================================================================
 // Initialisers and utilities.
 // =================================================================================================================
 // particle_filter.cpp:16-34 with Philox normals: x,y,theta ~ pose + N(0, std); last particle = exact pose (:33).

@@ -19,7 +19,7 @@ assert POSE_DTYPE.itemsize == 24 and PARTICLE_DTYPE.itemsize == 56
 # every symbol include/mcl_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "mcl_default_params", "mcl_create", "mcl_destroy", "mcl_last_error", "mcl_stream", "mcl_sync",
-    "mcl_comm_unique_id", "mcl_comm_init", "mcl_set_map", "mcl_update_map_rect", "mcl_init_at_pose",
+    "mcl_comm_unique_id", "mcl_comm_init", "mcl_set_map", "mcl_update_map_rect", "mcl_read_map_rect", "mcl_map_update", "mcl_init_at_pose",
     "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
@@ -86,6 +86,8 @@ def lib():
         L.mcl_comm_init.argtypes = [vp, vp, ip, ip]
         L.mcl_set_map.argtypes = [vp, vp, ip, ip, fp, fp, fp, fp]
         L.mcl_update_map_rect.argtypes = [vp, ip, ip, ip, ip, vp, ip]
+        L.mcl_read_map_rect.argtypes = [vp, ip, ip, ip, ip, vp, ip]
+        L.mcl_map_update.argtypes = [vp, vp, vp, ip, vp, vp, vp, ip, fp, ip, ip, vp]
         L.mcl_init_at_pose.argtypes = [vp, fp, fp, fp, i64, C.c_uint64]
         L.mcl_init_uniform.argtypes = [vp, i64, C.c_uint64]
         L.mcl_import_particles.argtypes = [vp, vp, i64]
@@ -185,6 +187,25 @@ class Engine:
     def update_map_rect(self, x0, y0, patch):
         patch = np.ascontiguousarray(patch, np.int8)
         self._ck(self._L.mcl_update_map_rect(self.h, x0, y0, patch.shape[1], patch.shape[0], _p(patch), patch.shape[1]))
+
+    def read_map_rect(self, x0, y0, w, h):
+        out = np.zeros((h, w), np.int8)
+        self._ck(self._L.mcl_read_map_rect(self.h, x0, y0, w, h, _p(out), w))
+        return out
+
+    def map_update(self, previous, pose, initialized, ranges, thetas, times, max_laser_distance=5.0, hit_odds=3,
+                   miss_odds=1):
+        """Mapping::updateMap on the device mirror; previous / pose = (x, y, theta, utime).  Returns the rectangle
+        (x0, y0, w, h) of cells that may have changed."""
+        a, b = Pose(previous[3], *previous[:3]), Pose(pose[3], *pose[:3])
+        ranges = np.ascontiguousarray(ranges, np.float32)
+        thetas = np.ascontiguousarray(thetas, np.float32)
+        times = np.ascontiguousarray(times, np.int64)
+        rect = (C.c_int * 4)()
+        self._ck(self._L.mcl_map_update(self.h, C.addressof(a), C.addressof(b), 1 if initialized else 0, _p(ranges),
+                                        _p(thetas), _p(times), len(ranges), max_laser_distance, hit_odds, miss_odds,
+                                        C.addressof(rect)))
+        return tuple(rect)
 
     # ---- particles
     def init_at_pose(self, x, y, theta, utime=0, seed=1):

@@ -103,6 +103,15 @@ int  mcl_comm_init(mcl_engine* h, const void* nccl_unique_id128, int rank, int w
 int  mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float origin_x, float origin_y,
                  float meters_per_cell, float cells_per_meter);
 int  mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const int8_t* src, int src_stride);
+int  mcl_read_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, int8_t* dst, int dst_stride);
+/* Mapping::updateMap (mapping.cpp:17-127) applied to the device mirror: +hit_odds at the endpoint cell of every ray of
+ * the MovingLaserScan between previous_pose and pose (ranges <= max_laser_distance), then -miss_odds along each ray's
+ * Bresenham walk, both saturating in int8; bit-identical to the reference's sequential loops (saturating adds of one
+ * sign commute).  initialized = Mapping::initialized_: 0 reproduces the reference's first call, which changes no cell.
+ * rect_xywh_out (4 ints, may be NULL): the rectangle of cells that may have changed, for mcl_read_map_rect. */
+int  mcl_map_update(mcl_engine* h, const mcl_pose_t* previous_pose, const mcl_pose_t* pose, int initialized,
+                    const float* ranges, const float* thetas, const int64_t* times, int num_ranges,
+                    float max_laser_distance, int hit_odds, int miss_odds, int* rect_xywh_out);
 
 /* ---- particle state -------------------------------------------------------------------------------------------- */
 /* ParticleFilter::initializeFilterAtPose (particle_filter.cpp:16-34) with the intended weight 1.0/N and a seeded

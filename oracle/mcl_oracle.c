@@ -369,3 +369,64 @@ int orc_update(orc_action* a, const orc_grid* g, orc_particle* particles, orc_pa
     pose_io->utime = odom->utime;
     return moved;
 }
+
+/* ---- slam/mapping.cpp:17-127 -- Mapping::updateMap on a writable grid ------------------------------------------
+ * cells is modified in place.  previous / initialized are Mapping's private state (previousPose_, initialized_):
+ * until the first call has latched a previous pose no cell changes (mapping.cpp:73-76, 87-90).  Occupied endpoints
+ * are raised first (:26-30), then every ray lowers the cells of its Bresenham walk from the start cell up to, not
+ * including, the endpoint cell (:32-36, :101-127).  Returns the number of cell writes (diagnostic). */
+static void orc_map_raise(int8_t* c, int hit)            /* mapping.cpp:73-85 */
+{
+    if (127 - (int)*c > hit) *c = (int8_t)((int)*c + hit);
+    else *c = 127;
+}
+static void orc_map_lower(int8_t* c, int miss)           /* mapping.cpp:87-99 */
+{
+    if ((int)*c - miss > -128) *c = (int8_t)((int)*c - miss);
+    else *c = -128;
+}
+long orc_map_update(int8_t* cells, int32_t width, int32_t height, float origin_x, float origin_y, float cells_per_meter,
+                    const orc_pose* previous, const orc_pose* pose, int initialized, const float* ranges,
+                    const float* thetas, const int64_t* times, int nb, float max_laser_distance, int hit_odds,
+                    int miss_odds)
+{
+    if (nb <= 0) return 0;
+    orc_pose prev = initialized ? *previous : *pose;                      /* :19-21 */
+    float* rays = (float*)malloc(sizeof(float) * 4 * (size_t)nb);
+    const int nr = orc_moving_scan(ranges, thetas, times, nb, &prev, pose, rays);   /* :22 */
+    long writes = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int k = 0; k < nr; ++k) {
+            const float ox = rays[4 * k], oy = rays[4 * k + 1], range = rays[4 * k + 2], theta = rays[4 * k + 3];
+            if (!(range <= max_laser_distance)) continue;                 /* :43, :60 */
+            const float sx = (float)(((double)ox - (double)origin_x) * (double)cells_per_meter);   /* grid_utils.hpp:50-55 */
+            const float sy = (float)(((double)oy - (double)origin_y) * (double)cells_per_meter);
+            float s, c;
+            sincosf(theta, &s, &c);
+            const int cx = f2i((range * c) * cells_per_meter + sx);       /* :48, :65 */
+            const int cy = f2i((range * s) * cells_per_meter + sy);
+            if (pass == 0) {                                              /* scoreEndpoint :42-57 */
+                if (initialized && cx >= 0 && cx < width && cy >= 0 && cy < height) {
+                    orc_map_raise(&cells[(size_t)cy * width + cx], hit_odds);
+                    ++writes;
+                }
+            } else {                                                      /* scoreRay -> bresenham :101-127 */
+                int x = f2i(sx), y = f2i(sy);
+                const int dx = abs(cx - x), dy = abs(cy - y);
+                const int stepx = x < cx ? 1 : -1, stepy = y < cy ? 1 : -1;
+                int err = dx - dy;
+                while (x != cx || y != cy) {
+                    if (initialized && x >= 0 && x < width && y >= 0 && y < height) {
+                        orc_map_lower(&cells[(size_t)y * width + x], miss_odds);
+                        ++writes;
+                    }
+                    const float e2 = (float)(2 * err);
+                    if (e2 >= (float)-dy) { err -= dy; x += stepx; }
+                    if (e2 <= (float)dx) { err += dx; y += stepy; }
+                }
+            }
+        }
+    }
+    free(rays);
+    return writes;
+}

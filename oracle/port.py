@@ -62,6 +62,9 @@ def lib():
         L.orc_action_draws.argtypes = [vp, vp, ip, vp]
         L.orc_init_at_pose.argtypes = [vp, vp, vp, ip]
         L.orc_update.argtypes = [vp, vp, vp, vp, ip, vp, C.c_int64, vp, vp, vp, ip, dp, vp, vp]
+        L.orc_map_update.restype = C.c_long
+        L.orc_map_update.argtypes = [vp, ip, ip, C.c_float, C.c_float, C.c_float, vp, vp, ip, vp, vp, vp, ip, C.c_float,
+                                     ip, ip]
         _lib = L
     return _lib
 
@@ -106,6 +109,21 @@ def likelihood(grid, particles, ranges, thetas, times):
     lib().orc_likelihood(grid.ptr, _p(particles), particles.shape[0], _p(ranges), _p(thetas), _p(times), len(ranges),
                          _p(out), C.addressof(g), C.addressof(e))
     return out, g.value, e.value
+
+
+def map_update(cells, origin_x, origin_y, cells_per_meter, previous, pose, initialized, ranges, thetas, times,
+               max_laser_distance=5.0, hit_odds=3, miss_odds=1):
+    """Mapping::updateMap (mapping.cpp:17-127): returns the updated copy of `cells` (int8 [H, W])."""
+    out = np.ascontiguousarray(cells, np.int8).copy()
+    a = np.ascontiguousarray(previous, POSE_DTYPE).reshape(1)
+    b = np.ascontiguousarray(pose, POSE_DTYPE).reshape(1)
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    thetas = np.ascontiguousarray(thetas, np.float32)
+    times = np.ascontiguousarray(times, np.int64)
+    lib().orc_map_update(_p(out), out.shape[1], out.shape[0], origin_x, origin_y, cells_per_meter, _p(a), _p(b),
+                         1 if initialized else 0, _p(ranges), _p(thetas), _p(times), len(ranges), max_laser_distance,
+                         hit_odds, miss_odds)
+    return out
 
 
 class ActionModel:

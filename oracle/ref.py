@@ -63,6 +63,7 @@ def lib():
         L.ref_pf_update_action_only.argtypes = [vp, vp, C.c_int64, vp, vp]
         L.ref_pf_pose_estimate.argtypes = [vp, vp]
         L.ref_pf_action_params.argtypes = [vp, vp]
+        L.ref_map_update.argtypes = [vp, vp, vp, ip, vp, vp, vp, ip, fp, ip, ip]
         _lib = L
     return _lib
 
@@ -130,6 +131,14 @@ def likelihood(grid, particles, scan):
     lib().ref_likelihood(grid.h, _p(particles), particles.shape[0], _p(scan.ranges), _p(scan.thetas), _p(scan.times),
                          scan.n, _p(out))
     return out
+
+
+def map_update(grid, previous, pose, initialized, scan, max_laser_distance=5.0, hit_odds=3, miss_odds=1):
+    """Mapping::updateMap (mapping.cpp:17-40) on `grid` (a RefGrid, modified in place)."""
+    a = np.ascontiguousarray(previous, POSE_DTYPE).reshape(1)
+    b = np.ascontiguousarray(pose, POSE_DTYPE).reshape(1)
+    lib().ref_map_update(grid.h, _p(a), _p(b), 1 if initialized else 0, _p(scan.ranges), _p(scan.thetas),
+                         _p(scan.times), len(scan.ranges), max_laser_distance, hit_odds, miss_odds)
 
 
 def moving_scan(scan, begin, end):

@@ -419,6 +419,19 @@ int ref_replay_run(const int8_t* cells, int w, int h, float ox, float oy, float 
     return 0;
 }
 
+// ---- Mapping::updateMap (mapping.cpp:17-40) on a reference OccupancyGrid, with the private state injected: the
+// previous pose and the initialized_ latch (false = the reference's first call, which changes no cell).
+void ref_map_update(void* gp, const ref_pose* previous, const ref_pose* pose, int initialized, const float* ranges,
+                    const float* thetas, const int64_t* times, int nb, float max_laser_distance, int hit_odds,
+                    int miss_odds)
+{
+    Mapping mapper(max_laser_distance, (int8_t)hit_odds, (int8_t)miss_odds);
+    mapper.previousPose_ = to_pose(*previous);
+    mapper.initialized_ = initialized != 0;
+    const lidar_t scan = make_scan(ranges, thetas, times, nb);
+    mapper.updateMap(scan, to_pose(*pose), *(OccupancyGrid*)gp);
+}
+
 int ref_sizeof_particle(void) { return (int)sizeof(particle_t); }
 int ref_sizeof_pose(void) { return (int)sizeof(pose_xyt_t); }
 int ref_rand_max(void) { return RAND_MAX; }

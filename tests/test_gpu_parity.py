@@ -635,3 +635,61 @@ def test_batch_windows_equal_exact_and_oracle(side, n):
     assert np.array_equal(clouds["two_pass"]["weight"], clouds["exact"]["weight"])
     for e in engines.values():
         e.close()
+
+
+# ------------------------------------------------------------------------------- map update on the device mirror
+@pytest.mark.parametrize("hit,miss,max_laser", [(3, 1, 5.0), (4, 1, 5.0), (127, 100, 8.0), (0, 0, 5.0)])
+def test_map_update_matches_oracle(hit, miss, max_laser):
+    """Mapping::updateMap on the device mirror (mcl_map_update) leaves exactly the cells the reference's sequential
+    loops leave: several scans in a row so cells saturate, moving poses so the rays are interpolated."""
+    grid = synth.make_map(400, seed=9)
+    rng = np.random.default_rng(hit + miss)
+    pose = synth.find_free_pose(grid, rng)
+    cells = grid.cells.copy()
+    e = make_engine(16, grid)
+    prev, t0 = pose, 1_000_000
+    for k in range(6):
+        r, th, t = synth.make_scan(grid, pose, seed=20 + k, t0=t0)
+        cur = (pose[0], pose[1], pose[2], int(t[-1]))
+        prv = (prev[0], prev[1], prev[2], int(t[0]) if k % 2 == 0 else int(t[-1]))      # interpolated / equal-utime rays
+        init = k > 0                                          # the reference's first call changes no cell
+        want = port.map_update(cells, grid.origin_x, grid.origin_y, grid.cells_per_meter,
+                               synth.make_pose(*prv[:3], utime=prv[3]), synth.make_pose(*cur[:3], utime=cur[3]), init,
+                               r, th, t, max_laser, hit, miss)
+        x0, y0, w, h = e.map_update(prv, cur, init, r, th, t, max_laser, hit, miss)
+        got = e.read_map_rect(0, 0, grid.width, grid.height)
+        assert np.array_equal(got, want), k
+        changed = np.nonzero(want != cells)
+        if len(changed[0]):
+            assert x0 <= changed[1].min() and changed[1].max() < x0 + w and y0 <= changed[0].min() and changed[0].max() < y0 + h
+        else:
+            assert not init or hit == miss == 0 or w >= 0
+        cells = want
+        prev, pose, t0 = pose, synth.odometry_step(rng, pose), t0 + 100_000
+    e.close()
+
+
+def test_map_update_edge_cases(real_map):
+    """Robot next to the map border (rays leave the grid), empty and all-invalid scans, bad arguments."""
+    e = make_engine(16, real_map)
+    whole = lambda: e.read_map_rect(0, 0, real_map.width, real_map.height)
+    base = whole()
+    assert np.array_equal(base, real_map.cells)
+    z = np.zeros(0, np.float32)
+    assert e.map_update((0, 0, 0, 1), (0, 0, 0, 2), True, z, z, np.zeros(0, np.int64)) == (0, 0, 0, 0)
+    e.map_update((0, 0, 0, 1), (0, 0, 0, 2), True, np.full(8, 0.1, np.float32), np.zeros(8, np.float32), np.zeros(8, np.int64))
+    assert np.array_equal(whole(), base)
+    pose = (4.9, -4.93, 0.4)                                   # 2 cells from two borders of the 10 m map
+    r = np.full(360, 3.0, np.float32)
+    th = (np.arange(360) * 2 * np.pi / 360).astype(np.float32)
+    t = 1_000_000 + np.arange(360, dtype=np.int64) * 277
+    want = port.map_update(base, real_map.origin_x, real_map.origin_y, real_map.cells_per_meter,
+                           synth.make_pose(4.88, -4.92, 0.38, utime=int(t[0])), synth.make_pose(*pose, utime=int(t[-1])),
+                           True, r, th, t)
+    e.map_update((4.88, -4.92, 0.38, int(t[0])), (*pose, int(t[-1])), True, r, th, t)
+    assert np.array_equal(whole(), want)
+    with pytest.raises(engine.MclError):
+        e.map_update((0, 0, 0, 1), (np.nan, 0, 0, 2), True, r, th, t)
+    with pytest.raises(engine.MclError):
+        e.map_update((0, 0, 0, 1), (0, 0, 0, 2), True, r, th, t, hit_odds=-1)
+    e.close()
