@@ -44,6 +44,8 @@ public:
     bool haveInitializedPoses(void) const { return haveInitializedPoses_; }
     int iterations(void) const { return iterations_; }
     int ignoredScans(void) const { return numIgnoredScans_; }
+    /// Run Mapping::updateMap on the filter's device mirror of the map instead of the host loops (identical cells).
+    void setDeviceMapping(bool on) { mapper_.useDeviceMirror(on ? &filter_ : nullptr); }
 
     /// Called right after initializeFilterAtPose on the first iteration (tests plant a deterministic cloud here).
     void (*onFilterInitialized)(HeadlessSLAM&, void*) = nullptr;

@@ -1,6 +1,8 @@
 #include <slam/mapping.hpp>
 #include <slam/moving_laser_scan.hpp>
 #include <slam/occupancy_grid.hpp>
+#include <slam/particle_filter.hpp>
+#include <slam/cuda/device_filter.hpp>
 #include <lcmtypes/lidar_t.hpp>
 #include <cmath>
 #include <cstdlib>
@@ -15,6 +17,12 @@ Mapping::Mapping(float maxLaserDistance, int8_t hitOdds, int8_t missOdds)
 void Mapping::updateMap(const lidar_t& scan, const pose_xyt_t& pose, OccupancyGrid& map)
 {
     if (!initialized_) previousPose_ = pose;
+    if (deviceFilter_) {
+        updateMapOnDevice(scan, pose, map);
+        initialized_ = true;
+        previousPose_ = pose;
+        return;
+    }
     const MovingLaserScan rays(scan, previousPose_, pose);
     for (const adjusted_ray_t& ray : rays) {           // occupied endpoints first ...
         if (!(ray.range <= kMaxLaserDistance_)) continue;
@@ -72,4 +80,23 @@ void Mapping::clearAlongRay(int x1, int y1, int x2, int y2, OccupancyGrid& map)
         if (e2 >= -dy) { err -= dy; x += sx; }
         if (e2 <= dx) { err += dx; y += sy; }
     }
+}
+
+// The same update on the filter's map mirror: bring the mirror up to date with any host-side writes, run
+// mcl_map_update, read the rectangle that may have changed back into the host grid (without marking it dirty: the
+// mirror already holds those values).
+void Mapping::updateMapOnDevice(const lidar_t& scan, const pose_xyt_t& pose, OccupancyGrid& map)
+{
+    b200::DeviceFilter& dev = deviceFilter_->device();
+    dev.syncMap(map);
+    mcl_pose_t prev, cur;
+    prev.utime = previousPose_.utime; prev.x = previousPose_.x; prev.y = previousPose_.y; prev.theta = previousPose_.theta;
+    cur.utime = pose.utime; cur.x = pose.x; cur.y = pose.y; cur.theta = pose.theta;
+    int rect[4] = {0, 0, 0, 0};
+    dev.check(mcl_map_update(dev.engine(), &prev, &cur, initialized_ ? 1 : 0, scan.ranges.data(), scan.thetas.data(),
+                             scan.times.data(), scan.num_ranges, kMaxLaserDistance_, kHitOdds_, kMissOdds_, rect));
+    if (rect[2] > 0 && rect[3] > 0)
+        dev.check(mcl_read_map_rect(dev.engine(), rect[0], rect[1], rect[2], rect[3],
+                                    map.mirrorData() + static_cast<std::size_t>(rect[1]) * map.widthInCells() + rect[0],
+                                    map.widthInCells()));
 }

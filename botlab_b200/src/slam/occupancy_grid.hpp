@@ -47,6 +47,8 @@ public:
 
     // ---- device-mirror support (not in the reference) ----
     const CellOdds* data(void) const { return cells_.data(); }
+    /// Writable storage for values read back FROM the device mirror: writing through it does not mark cells dirty.
+    CellOdds* mirrorData(void) { return cells_.data(); }
     /// Bumped whenever the geometry or the whole content changes (ctor, reset, setOrigin, fromLCM, loadFromFile).
     uint64_t generation(void) const { return generation_; }
     /// Bounding box [x0,x1] x [y0,y1] of cells written since clearDirty(); false if none.

@@ -50,6 +50,8 @@ public:
     /// Test hook: N x (rot1, trans, rot2) action draws used by the NEXT update instead of the Philox stream
     /// (the reference's recorded std::mt19937 draws).  The pointer must stay valid until that update returns.
     void injectActionNoise(const float* draws3n) { injectedNoise_ = draws3n; }
+    /// The engine behind this filter, for components that work on its map mirror (Mapping::useDeviceMirror).
+    b200::DeviceFilter& device(void) { return *device_; }
 
 private:
     int kNumParticles_;

@@ -3,6 +3,7 @@
 #include <slam/headless_slam.hpp>
 #include <slam/cuda/device_filter.hpp>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,9 @@ extern "C" int b200_replay_run(const int8_t* cells, int w, int h, float ox, floa
         pose_xyt_t init;
         init.x = initial_pose3[0]; init.y = initial_pose3[1]; init.theta = initial_pose3[2];
         slam.setInitialPose(init);
+        // B200_DEVICE_MAPPING=1: Mapping::updateMap runs on the device mirror (tests replay both ways)
+        const char* dm = std::getenv("B200_DEVICE_MAPPING");
+        slam.setDeviceMapping(dm && dm[0] == '1');
         ReplayHooks hooks{static_cast<const mcl_particle_t*>(init_cloud), num_particles, noise_io, num_scans};
         slam.onFilterInitialized = plantCloud;
         slam.beforeLocalization = injectNoise;

@@ -106,3 +106,11 @@ def test_localization_only_replay_matches_the_reference_loop(host_lib, real_map)
     # the map really changed during "localization-only" (slam.cpp:276)
     assert (eng_map != real_map.cells).sum() > 100
     print(f"replay: max |dxy| {d_xy:.2e} m, max |dtheta| {d_th:.2e} rad, differing cells {(ref_map != eng_map).sum()}")
+    # the same replay with Mapping::updateMap running on the device mirror (mcl_map_update): identical poses and map
+    os.environ["B200_DEVICE_MAPPING"] = "1"
+    try:
+        dev_poses, dev_map, dev_iters = run_replay(host_lib.b200_replay_run, real_map, log, n, init_cloud, noise)
+    finally:
+        del os.environ["B200_DEVICE_MAPPING"]
+    assert dev_iters == eng_iters
+    assert np.array_equal(dev_poses, eng_poses) and np.array_equal(dev_map, eng_map)
