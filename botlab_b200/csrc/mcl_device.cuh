@@ -294,6 +294,8 @@ struct FastPlan {
     float rho_lo, rho_hi;   // range of the scan's interpolation ratios
     float max_shift;     // largest |dS| (cells) a particle may have and still take the fast pass
     float coord_hi;      // largest robot cell coordinate the error budget covers
+    float reach;         // longest ray of the scan in cells (+ margin)
+    float grid_min_dim;  // min(W, H)
     float mid_x, half_x; // certain-interior test on the endpoint: |e - mid| < half  <=>  cell inside [lc, hc)
     float mid_y, half_y;
     float pitch_f;       // window pitch as a float (the step offset is assembled in float)
@@ -312,6 +314,8 @@ struct FastBase {
     float sxb, syb, thb;     // robot cell coordinate / heading at rho = 0 (or the pose itself when !INTERP)
     float dsx, dsy, dth;     // change over rho = 0..1
     bool ok;                 // false: every beam of this particle goes to the exact pass
+    int edge;                // 0: every endpoint and doubled endpoint of this particle is inside the grid (no edge tests
+                             // needed); 1: endpoints may leave the grid; 2: doubled endpoints may also turn negative
 };
 
 template <bool INTERP>
@@ -340,6 +344,10 @@ __device__ __forceinline__ FastBase make_fast_base(float xa, float ya, float tha
     const float lo = fminf(fminf(x0, x1), fminf(y0, y1)), hi = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
     f.ok = lo >= 1.0f && hi <= fp.coord_hi && fabsf(f.dsx) <= fp.max_shift && fabsf(f.dsy) <= fp.max_shift &&
            fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f;
+    // how close to the grid's edges the particle's rays can get (reach already carries the margins)
+    const bool inside = lo >= fp.reach && hi <= fp.grid_min_dim - fp.reach;      // no endpoint within 2 cells of an edge
+    const bool x2_pos = lo >= 2.0f * fp.reach;                                   // no doubled endpoint below 3 cells
+    f.edge = x2_pos ? (inside ? 0 : 1) : 2;
     return f;
 }
 
@@ -382,7 +390,9 @@ __device__ __forceinline__ int fast_read(const int8_t* __restrict__ cells, unsig
 
 // One certified evaluation.  Returns true when certain; v2 is then the ray's score in half units (else 0).
 // Straight-line on purpose (bitwise &, no short-circuit): every lane runs the same ~60 instructions.
-template <bool INTERP, bool SMEM, bool COUNT>
+// EDGE (warp-uniform, from FastBase::edge): 2 = all tests; 1 = the doubled endpoint cannot be negative (its test is
+// skipped); 0 = additionally no endpoint can leave the grid (the out-of-grid test is skipped).
+template <bool INTERP, bool SMEM, bool COUNT, int EDGE>
 __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBeam& b, const FastPlan& fp,
                                                 const int8_t* __restrict__ cells, unsigned sbase, int pitch, int& v2,
                                                 int& gathers)
@@ -402,10 +412,11 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const float d2 = __fsub_rn(__fadd_rn(ay, ay), ax);      // step y iff |ddx| <= 2|ddy|
     // an extended point at a negative coordinate is truncated toward zero by the reference (not floored), which
     // widens the band of its differences from 3 to 5 cells
-    const float t_dir = fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= fp.x2_min ? fp.t_dir : fp.t_dir_neg;
+    const float t_dir = (EDGE < 2 || fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= fp.x2_min) ? fp.t_dir : fp.t_dir_neg;
     const bool dir_ok = fminf(fabsf(d1), fabsf(d2)) > t_dir;
     // endpoint certainly two or more cells outside the grid: it and both neighbours read 0 (occupancy_grid.cpp:65-70)
-    const bool outside = (fabsf(__fsub_rn(ex, fp.gmid_x)) >= fp.ghalf_x) | (fabsf(__fsub_rn(ey, fp.gmid_y)) >= fp.ghalf_y);
+    const bool outside = EDGE >= 1 && ((fabsf(__fsub_rn(ex, fp.gmid_x)) >= fp.ghalf_x) |
+                                       (fabsf(__fsub_rn(ey, fp.gmid_y)) >= fp.ghalf_y));
     // step toward the extended point, assembled in float: (+-1 or 0) + (+-1 or 0) * pitch, then to an integer by a
     // magic-number add (no conversion unit)
     const float ux = __uint_as_float((__float_as_uint(px) & 0x80000000u) | 0x3f800000u);

@@ -429,6 +429,8 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     fp.rho_lo = (float)h->ratio_lo; fp.rho_hi = (float)h->ratio_hi;
     fp.max_shift = (float)max_shift;
     fp.coord_hi = (float)(Cm - 1.0);
+    fp.reach = (float)(Rc * (1.0 + 1e-6) + 4.0);
+    fp.grid_min_dim = (float)std::min(h->grid.width, h->grid.height);
     plan_set_window(fp, x0, y0, w, hh, pitch);
     if (fp.half_x <= 0.0f || fp.half_y <= 0.0f) { fp.enabled = 0; return fp; }
     h->stats_eps = eps;

@@ -1,6 +1,7 @@
 // Kernels of the MCL update for sm_100a.  See DESIGN.md for the data layout and the per-kernel rooflines.
 #pragma once
 #include "mcl_device.cuh"
+#include <type_traits>
 
 #ifndef MCL_BEAM_UNROLL
 #define MCL_BEAM_UNROLL 2
@@ -302,23 +303,31 @@ score_fast_kernel(const ScoreArgs a)
                 const FastBase fb =
                     make_fast_base<INTERP>(a.x[p], a.y[p], a.th[p], a.px[p], a.py[p], a.pth[p], gx, gy, cpm_d, fp);
                 uint32_t* mrow = a.masks + ((p - a.lo) * G + sub);
+                // the edge tests a warp needs are those of its most exposed particle
+                const int edge = __reduce_max_sync(__activemask(), fb.ok ? fb.edge : 0);
                 for (int w = 0; w < nwords; ++w) {
                     uint32_t m = 0;
                     const int kend = min(32, iters - w * 32);
                     if (fb.ok) {
-                        uint32_t bit = 1u;
+                        auto run = [&](auto edge_tag) {
+                            constexpr int EDGE = decltype(edge_tag)::value;
+                            uint32_t bit = 1u;
 MCL_UNROLL(MCL_FAST_UNROLL)
-                        for (int k = 0; k < kend; ++k) {
-                            const int j = sub + (w * 32 + k) * G;
-                            const bool inb = G == 1 || j < a.num_beams;      // G == 1: kend already bounds j
-                            int v = 0, g = 0;
-                            const bool certain = score_beam_fast<INTERP, TILE, COUNT>(fb, sfast[inb ? j : 0], fp, cells,
-                                                                                      sbase, pitch, v, g);
-                            acc += inb ? v : 0;
-                            if (COUNT) gathers += inb ? g : 0;
-                            if (inb & !certain) m |= bit;
-                            bit += bit;
-                        }
+                            for (int k = 0; k < kend; ++k) {
+                                const int j = sub + (w * 32 + k) * G;
+                                const bool inb = G == 1 || j < a.num_beams;      // G == 1: kend already bounds j
+                                int v = 0, g = 0;
+                                const bool certain = score_beam_fast<INTERP, TILE, COUNT, EDGE>(
+                                    fb, sfast[inb ? j : 0], fp, cells, sbase, pitch, v, g);
+                                acc += inb ? v : 0;
+                                if (COUNT) gathers += inb ? g : 0;
+                                if (inb & !certain) m |= bit;
+                                bit += bit;
+                            }
+                        };
+                        if (edge == 0) run(std::integral_constant<int, 0>{});
+                        else if (edge == 1) run(std::integral_constant<int, 1>{});
+                        else run(std::integral_constant<int, 2>{});
                     } else {
                         for (int k = 0; k < kend; ++k) m |= (uint32_t)(sub + (w * 32 + k) * G < a.num_beams) << k;
                     }
