@@ -693,3 +693,38 @@ def test_map_update_edge_cases(real_map):
     with pytest.raises(engine.MclError):
         e.map_update((0, 0, 0, 1), (0, 0, 0, 2), True, r, th, t, hit_odds=-1)
     e.close()
+
+
+def test_config4_full_size_two_pass_equals_exact():
+    """BASELINE configs[3] at full size (16 M particles x 360 beams, 2000 x 2000 grid): the default two-pass sensor path
+    and the literal restatement give the same 16 M scores, hence the same weight sum, estimate and resampled cloud."""
+    n, side = synth.CONFIGS["config4"]
+    rng = np.random.default_rng(4)
+    grid = synth.make_map(side, seed=synth.MAP_SEED + 4)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=4)
+    am = engine.ActionModel()
+    am.update(*truth, int(t[0]) - 100_000)
+    assert am.update(truth[0] + 0.02, truth[1] + 0.01, truth[2] + 0.01, int(t[-1]))
+    out = {}
+    for path in (0, 1):
+        e = make_engine(n, grid, sensor_path=path)
+        e.init_at_pose(*truth, utime=int(t[0]) - 100_000, seed=21)
+        est = e.update(am, int(t[-1]), r, th, t, 0.8401877171547095 / n)
+        st = e.stats()
+        assert st["sensor_path"] == (2 if path == 0 else 1)
+        scores = e.score(r, th, t)                   # same cloud, same scan: the stage alone, all 16 M scores
+        am2 = engine.ActionModel()
+        am2.c = type(am.c).from_buffer_copy(am.c)
+        est2 = e.update(am2, int(t[-1]) + 1, r, th, t, 0.3 / n)      # resamples from the weights of the first update
+        out[path] = (scores, st["weight_sum"], (est.x, est.y, est.theta), (est2.x, est2.y, est2.theta),
+                     e.export_particles(stride=1009), st["deferred_evals"], st["evals"])
+        e.close()
+    a, b = out[0], out[1]
+    assert np.array_equal(a[0], b[0])
+    assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+    for k in ("pose", "parent_pose"):
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(a[4][k][f], b[4][k][f])
+    assert np.array_equal(a[4]["weight"], b[4]["weight"])
+    assert 0 < a[5] < 0.2 * a[6] and b[5] == 0
