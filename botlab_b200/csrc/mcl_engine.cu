@@ -46,6 +46,7 @@ struct mcl_engine {
 #endif
     // peer push of pose slices over NVLink by the copy engines (no SMs), overlapped with the sensor kernel
     std::vector<float*> peer_pose_block;         // IPC-mapped pose_block of every rank (own entry = pose_block)
+    std::vector<int32_t*> peer_score2;           // IPC-mapped score_block of every rank (own entry = score_block)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_action_done = nullptr, ev_push_done = nullptr;
     bool peer_push = false;
@@ -58,7 +59,11 @@ struct mcl_engine {
     int cur = 0;
     double* weight[2] = {nullptr, nullptr};
     int wcur = 0;
-    int32_t* score2 = nullptr;
+    int32_t* score_block = nullptr;     // [2][N]: two score arrays; multi-GPU runs alternate between them so a fast
+                                        // rank's direct stores for update k+1 cannot overtake a slow rank still
+                                        // reading update k (the per-update barrier then bounds the skew to one)
+    int32_t* score2 = nullptr;          // the array of the current update (= score_block + score_parity * N)
+    int score_parity = 0;
     int32_t* idx = nullptr;
     long long pose_utime = 0, parent_utime = 0;
     bool have_particles = false, have_scores = false;
@@ -447,6 +452,13 @@ int run_score(mcl_engine* h)
     const PoseSoA& p = h->pose[h->cur];
     const PoseSoA& q = h->parent[h->cur];
     a.x = p.x; a.y = p.y; a.th = p.th; a.px = q.x; a.py = q.y; a.pth = q.th;
+    if (h->world > 1 && h->peer_push) {
+        // every rank scores collectively, so the parities stay in lockstep
+        h->score_parity ^= 1;
+        h->score2 = h->score_block + (size_t)h->score_parity * (size_t)h->n;
+        a.num_peers = h->world;
+        for (int r = 0; r < h->world; ++r) a.peer_score[r] = h->peer_score2[r] + (size_t)h->score_parity * (size_t)h->n;
+    }
     a.score2 = h->score2;
     a.lo = h->lo; a.hi = h->hi;
     a.beams = h->beams; a.num_beams = h->num_beams;
@@ -572,8 +584,16 @@ int run_score(mcl_engine* h)
     if (rc) return rc;
     rc = join_pushes(h);
     if (rc) return rc;
-    rc = exchange_slices(h, h->score2, sizeof(int32_t));
-    if (rc) return rc;
+    if (a.num_peers > 0) {
+        // the sensor kernels already stored every final score into every rank's array; one 4-byte all-reduce makes all
+        // ranks' stores (and pose pushes) complete before anyone reads them
+        rc = rank_barrier(h);
+        if (rc) return rc;
+        ++h->collectives;
+    } else {
+        rc = exchange_slices(h, h->score2, sizeof(int32_t));
+        if (rc) return rc;
+    }
     h->stats.lanes_per_particle = G;
     h->stats.map_tile_used = batch ? 3 : (tile ? 2 : 1);
     h->stats.sensor_path = fast ? 2 : 1;
@@ -746,12 +766,14 @@ void free_all(mcl_engine* h)
     }
     for (size_t r = 0; r < h->peer_pose_block.size(); ++r)
         if (h->peer_pose_block[r] && h->peer_pose_block[r] != h->pose_block) cudaIpcCloseMemHandle(h->peer_pose_block[r]);
+    for (size_t r = 0; r < h->peer_score2.size(); ++r)
+        if (h->peer_score2[r] && h->peer_score2[r] != h->score_block) cudaIpcCloseMemHandle(h->peer_score2[r]);
     F(h->pose_block); F(h->barrier_word);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_action_done) cudaEventDestroy(h->ev_action_done);
     if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
-    F(h->score2); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
+    F(h->score_block); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
     F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
     if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
     if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
@@ -834,7 +856,8 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
         CKB(cudaMalloc((void**)&h->parent[b].th, 4 * n));
         CKB(cudaMalloc((void**)&h->weight[b], 8 * n));
     }
-    CKB(cudaMalloc((void**)&h->score2, 4 * n));
+    CKB(cudaMalloc((void**)&h->score_block, 4 * n * 2));
+    h->score2 = h->score_block;
     CKB(cudaMalloc((void**)&h->idx, 4 * n));
     CKB(cudaMalloc((void**)&h->cum, 8 * n));
     const size_t n1 = (size_t)h->n1, n2 = (size_t)h->n2;
@@ -931,23 +954,27 @@ int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
     // agree: if any mapping fails (or MCL_NO_PEER_PUSH is set) every rank keeps the NCCL all-gather path.
     h->peer_pose_block.assign(world, nullptr);
     h->peer_pose_block[rank] = h->pose_block;
-    int ok = (world > 1 && !std::getenv("MCL_NO_PEER_PUSH")) ? 1 : 0;
+    h->peer_score2.assign(world, nullptr);
+    h->peer_score2[rank] = h->score_block;
+    int ok = (world > 1 && world <= kMaxPeers && !std::getenv("MCL_NO_PEER_PUSH")) ? 1 : 0;
     unsigned char* handles_dev = nullptr;
-    std::vector<cudaIpcMemHandle_t> handles(world);
-    CK(cudaMalloc((void**)&handles_dev, sizeof(cudaIpcMemHandle_t) * world));
-    if (ok && cudaIpcGetMemHandle(&handles[rank], h->pose_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    CK(cudaMemcpyAsync(handles_dev + sizeof(cudaIpcMemHandle_t) * rank, &handles[rank], sizeof(cudaIpcMemHandle_t),
-                       cudaMemcpyHostToDevice, h->stream));
-    if (ncclAllGather(handles_dev + sizeof(cudaIpcMemHandle_t) * rank, handles_dev, sizeof(cudaIpcMemHandle_t), ncclChar,
-                      h->comm, h->stream) != ncclSuccess)
+    const size_t hsz = 2 * sizeof(cudaIpcMemHandle_t);          // per rank: pose block, score array
+    std::vector<cudaIpcMemHandle_t> handles(2 * (size_t)world);
+    CK(cudaMalloc((void**)&handles_dev, hsz * world));
+    if (ok && cudaIpcGetMemHandle(&handles[2 * rank], h->pose_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&handles[2 * rank + 1], h->score_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    CK(cudaMemcpyAsync(handles_dev + hsz * rank, &handles[2 * rank], hsz, cudaMemcpyHostToDevice, h->stream));
+    if (ncclAllGather(handles_dev + hsz * rank, handles_dev, hsz, ncclChar, h->comm, h->stream) != ncclSuccess)
         return fail(h, MCL_ERR_COMM, "NCCL handle exchange failed");
-    CK(cudaMemcpyAsync(handles.data(), handles_dev, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(handles.data(), handles_dev, hsz * world, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int r = 0; r < world && ok; ++r) {
         if (r == rank) continue;
         void* p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        if (cudaIpcOpenMemHandle(&p, handles[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
         h->peer_pose_block[r] = (float*)p;
+        if (cudaIpcOpenMemHandle(&p, handles[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        h->peer_score2[r] = (int32_t*)p;
     }
     CK(cudaMemcpyAsync(h->barrier_word, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (ncclAllReduce(h->barrier_word, h->barrier_word, 1, ncclInt, ncclMin, h->comm, h->stream) != ncclSuccess)

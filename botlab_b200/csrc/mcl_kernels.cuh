@@ -28,6 +28,7 @@ namespace mcl {
 // Per-batch map windows (global localisation: the cloud as a whole does not fit one shared-memory tile, but consecutive
 // particles are spatial neighbours -- mcl_init_uniform lays them out block by block and systematic resampling keeps
 // the order -- so every batch of kBatchParticles particles gets its own window, staged by the CTA that scores it).
+constexpr int kMaxPeers = 8;
 constexpr int kBatchParticles = 1024;
 constexpr int kBatchFastThreads = 1024;      // pass 1: one particle per thread, one CTA per SM
 constexpr int kBatchExactThreads = 512;      // exact-only kernel
@@ -49,6 +50,11 @@ struct ScoreArgs {
     unsigned long long* deferred_counter;                // two-pass path: evaluations re-done by the exact pass
     const BatchWindow* windows;                          // BATCH only: one map window per kBatchParticles particles
     long long num_batches;
+    // Multi-GPU: the kernel that produces a particle's FINAL score stores it straight into every rank's score array
+    // over NVLink (CUDA-IPC-mapped peer memory, own array included), so no all-gather of scores follows the sensor
+    // stage -- only a 4-byte barrier.  num_peers == 0: single GPU (or NCCL fallback), scores go to score2 only.
+    int num_peers;
+    int32_t* peer_score[kMaxPeers];
 };
 
 // Stages a map window in shared memory (4-byte granules; pitch and x0 are multiples of 4, the mirror's pitch is a
@@ -231,7 +237,13 @@ MCL_UNROLL(MCL_BEAM_UNROLL)
             }
 #pragma unroll
             for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (sub == 0 && p < last) a.score2[p] = acc;
+            if (sub == 0 && p < last) {
+                if (a.num_peers > 0) {
+                    for (int r = 0; r < a.num_peers; ++r) a.peer_score[r][p] = acc;     // final: to every rank
+                } else {
+                    a.score2[p] = acc;
+                }
+            }
         }
     }
     if (COUNT) {
@@ -481,7 +493,14 @@ score_deferred_kernel(const ScoreArgs a)
             if (lane < 32 / G) {
                 const long long p = a.lo + v0 / G + lane;
                 const int add = spart[lane].acc;
-                if (p < a.hi && add != 0) a.score2[p] += add;
+                if (p < a.hi) {
+                    if (a.num_peers > 0) {
+                        const int fin = a.score2[p] + add;                       // pass 1's partial + this pass: final
+                        for (int r = 0; r < a.num_peers; ++r) a.peer_score[r][p] = fin;
+                    } else if (add != 0) {
+                        a.score2[p] += add;
+                    }
+                }
             }
             __syncwarp();
         }
