@@ -607,8 +607,17 @@ int run_normalize(mcl_engine* h)
 {
     if (!h->have_scores) return fail(h, MCL_ERR_STATE, "mcl_score has not run");
     double* w = h->weight[h->wcur];
-    floor_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->params.weight_floor);
-    CKL(h);
+    if (h->params.weight_mode == 1) {
+        // extension: w = exp(beta (s - max s)) / sum  (max / log-sum-exp normalisation)
+        CK(cudaMemsetAsync(h->bbox, 0x80, sizeof(int), h->stream));          // 0x80808080: below every score
+        score_max_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, h->n, h->bbox);
+        CKL(h);
+        lse_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->bbox, 0.5 * h->params.lse_beta);
+        CKL(h);
+    } else {
+        floor_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->params.weight_floor);
+        CKL(h);
+    }
     int rc = seq_total(h, w, false);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->ess_acc, 0, sizeof(double), h->stream));
@@ -801,6 +810,8 @@ void mcl_default_params(mcl_params* p)
     p->lanes_per_particle = 0;
     p->map_tile = 0;
     p->sensor_path = 0;
+    p->weight_mode = 0;
+    p->lse_beta = 0.05;
 }
 
 const char* mcl_last_error(const mcl_engine* h) { return h ? h->err.c_str() : g_last_error.c_str(); }

@@ -596,6 +596,24 @@ __global__ void floor_kernel(const int32_t* score2, double* v, long long n, doub
     }
 }
 
+// weight_mode 1 (extension): scores as log-likelihoods.  score_max_kernel finds the largest half-unit score;
+// lse_kernel writes v = exp(beta * (score - max)) <= 1, so the sum cannot overflow and the best particle contributes
+// exactly 1 (the max / log-sum-exp normalisation); the sum and the division then go through the same path as mode 0.
+__global__ void score_max_kernel(const int32_t* score2, long long n, int* out_max)
+{
+    int m = (int)0x80000000;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, score2[i]);
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_max, m);
+}
+__global__ void lse_kernel(const int32_t* score2, double* v, long long n, const int* score_max, double half_beta)
+{
+    const int m = *score_max;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        v[i] = exp(half_beta * (double)(score2[i] - m));        // half units: beta/2 per unit of score2
+}
+
 // particle_filter.cpp:136-138: w /= wSum (IEEE double division, correctly rounded on both sides).
 __global__ void divide_kernel(double* w, long long n, const double* wsum, double* ess_acc)
 {

@@ -30,7 +30,8 @@ SYMBOLS = [
 class Params(C.Structure):
     _fields_ = [("min_range", C.c_float), ("weight_floor", C.c_double), ("init_std", C.c_double),
                 ("legacy_equal_utime", C.c_int), ("lanes_per_particle", C.c_int), ("map_tile", C.c_int),
-                ("sensor_path", C.c_int), ("reserved", C.c_int * 7)]
+                ("sensor_path", C.c_int), ("weight_mode", C.c_int), ("reserved0", C.c_int), ("lse_beta", C.c_double),
+                ("reserved", C.c_int * 4)]
 
 
 class Pose(C.Structure):

@@ -46,7 +46,13 @@ typedef struct {
     int    map_tile;            /* 0 = auto, 1 = force L2/global gathers, 2 = force shared-memory map tile */
     int    sensor_path;         /* 0 = auto: certified float pass, then the literal restatement for every evaluation it
                                    could not certify (identical results); 1 = literal restatement only */
-    int    reserved[7];
+    int    weight_mode;         /* 0 (default) = the reference's linear rule w = max(score, weight_floor) / sum
+                                   (particle_filter.cpp:116-141): the parity mode.  1 = scores as log-likelihoods:
+                                   w = exp(lse_beta (score - max score)) / sum, normalised by a max / log-sum-exp reduction
+                                   (an extension: it changes results, so it is never the default) */
+    int    reserved0;
+    double lse_beta;            /* inverse temperature of weight_mode 1 (default 0.05 per score unit) */
+    int    reserved[4];
 } mcl_params;
 
 /* ActionModel state + per-update parameters (action_model.hpp:66-76). */

@@ -728,3 +728,34 @@ def test_config4_full_size_two_pass_equals_exact():
             assert np.array_equal(a[4][k][f], b[4][k][f])
     assert np.array_equal(a[4]["weight"], b[4]["weight"])
     assert 0 < a[5] < 0.2 * a[6] and b[5] == 0
+
+
+# ------------------------------------------------------------------ extension: log-sum-exp weights (weight_mode = 1)
+@pytest.mark.parametrize("beta", [0.05, 0.5])
+def test_lse_weight_mode(beta, real_map):
+    """Non-default normalisation: w = exp(beta (s - max s)) / sum.  Scores are untouched (same sensor model), weights
+    follow the formula to double rounding, the best particle's unnormalised weight is exactly 1, and the rest of the
+    update (resampling on these weights, estimate) runs unchanged.  The default mode stays the reference's linear rule."""
+    truth = (0.5, -0.25, 0.3)
+    r, th, t = synth.make_scan(real_map, truth, seed=6)
+    cloud = synth.make_particles(20_000, truth, seed=6, parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    e = make_engine(len(cloud), real_map, weight_mode=1, lse_beta=beta)
+    e.import_particles(cloud)
+    s = e.score(r, th, t)
+    want_s, _, _ = port.likelihood(port_grid(real_map), cloud, r, th, t)
+    assert np.array_equal(s, want_s)
+    w = e.normalize()
+    v = np.exp(beta * (s - s.max()))
+    assert np.allclose(w, v / v.sum(), rtol=1e-12, atol=0) and abs(w.sum() - 1.0) < 1e-12
+    st = e.stats()
+    assert abs(st["weight_sum"] - v.sum()) <= 1e-9 * v.sum()
+    assert abs(st["effective_sample_size"] - 1.0 / np.sum(w * w)) <= 1e-6 * st["effective_sample_size"]
+    idx = e.resample(0.37 / len(cloud))
+    want_idx, _ = port.resample(w, 0.37 / len(cloud))
+    assert np.array_equal(idx, want_idx)                       # the exact sequential-sum resampling, on these weights
+    e.close()
+    lin = make_engine(len(cloud), real_map)
+    lin.import_particles(cloud)
+    lin.score(r, th, t)
+    assert np.array_equal(lin.normalize(), np.maximum(s, 0.001) / lin.stats()["weight_sum"])
+    lin.close()
