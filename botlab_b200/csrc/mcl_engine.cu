@@ -201,8 +201,14 @@ int seq_total(mcl_engine* h, const double* w, bool materialize)
     seq_group_maps_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->ebias, h->q0, h->q1, n1, n2, h->gebias,
                                                                           h->g0, h->g1);
     CKL(h);
-    seq_walk_kernel<<<1, 32, 0, h->stream>>>(w, n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2,
-                                             h->cin1, h->opened, h->total, h->fallbacks);
+    {
+        const size_t walk_smem = (size_t)n2 * 20;                    // g0, g1 (8 B each) + gebias (4 B) per group
+        const int staged = walk_smem + 1024 <= (size_t)h->max_smem_optin ? 1 : 0;
+        if (staged) CK(cudaFuncSetAttribute(seq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+        seq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(
+            w, n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2, h->cin1, h->opened, h->total,
+            h->fallbacks, staged);
+    }
     CKL(h);
     if (materialize) {
         seq_group_expand_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->q0, h->q1, n1, n2, h->cin2,
@@ -699,7 +705,7 @@ int run_resample_indices(mcl_engine* h, double r, const double* w)
     int rc = seq_total(h, w, true);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
-    resample_search_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(h->cum, h->n, r, h->lo, h->hi,
+    resample_search_kernel<<<grid_for(h, (h->hi - h->lo + kSearchRun - 1) / kSearchRun, 128), 128, 0, h->stream>>>(h->cum, h->n, r, h->lo, h->hi,
                                                                                  h->idx, h->overruns);
     CKL(h);
     return MCL_OK;

@@ -910,19 +910,30 @@ __device__ __forceinline__ bool seq_apply_warp(double& c, int cnt, int e_l, long
 // adding raw elements where a chunk's does not.  All lanes carry the same c, so shuffles broadcast staged values.
 // Produces the exact running sum at the entry of every level-2 group (cin2), of every level-1 chunk of groups that
 // had to be opened (cin1, flagged in opened[j]), the exact total, and the number of chunks that took raw adds.
-__global__ void __launch_bounds__(32) seq_walk_kernel(const double* w, long long n, long long n1, long long n2,
+__global__ void __launch_bounds__(1024) seq_walk_kernel(const double* w, long long n, long long n1, long long n2,
                                                       const int* ebias, const long long* q0, const long long* q1,
                                                       const int* gebias, const long long* g0, const long long* g1,
                                                       double* cin2, double* cin1, int* opened, double* total,
-                                                      long long* fallback_chunks)
+                                                      long long* fallback_chunks, int staged)
 {
+    // The walk itself is one warp's work, but its loads sit on the critical path: the whole CTA first stages the group
+    // maps in shared memory (staged = 1: they fit), so each step of the walk costs shared-memory, not DRAM, latency.
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    long long* sg0 = reinterpret_cast<long long*>(walk_smem);
+    long long* sg1 = sg0 + (staged ? n2 : 0);
+    int* sge = reinterpret_cast<int*>(sg1 + (staged ? n2 : 0));
+    if (staged) {
+        for (long long j = threadIdx.x; j < n2; j += blockDim.x) { sg0[j] = g0[j]; sg1[j] = g1[j]; sge[j] = gebias[j]; }
+        __syncthreads();
+    }
+    if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     double c = 0.0;
     long long fallbacks = 0;
     for (long long jb = 0; jb < n2; jb += 32) {
         const long long jl = jb + lane;
-        const int ge_l = jl < n2 ? gebias[jl] : 0;
-        const long long g0_l = jl < n2 ? g0[jl] : 0, g1_l = jl < n2 ? g1[jl] : 0;
+        const int ge_l = jl < n2 ? (staged ? sge[jl] : gebias[jl]) : 0;
+        const long long g0_l = jl < n2 ? (staged ? sg0[jl] : g0[jl]) : 0, g1_l = jl < n2 ? (staged ? sg1[jl] : g1[jl]) : 0;
         const int cnt = (int)(n2 - jb < 32 ? n2 - jb : 32);
         double cin_l;
         if (seq_apply_warp(c, cnt, ge_l, g0_l, g1_l, cin_l)) {
@@ -1020,20 +1031,35 @@ __global__ void __launch_bounds__(128) seq_materialize_kernel(const double* w, l
 // Systematic search: child m takes the first i with !(U_m > c_i), U_m = r + m*(1/N) evaluated exactly like the
 // reference (double product, double sum; particle_filter.cpp:89,95-99).  c is non-decreasing, so the reference's
 // forward-only loop equals a lower-bound search.  Past-the-end (the reference's unbounded loop) clamps to N-1.
+constexpr int kSearchRun = 8;       // consecutive children per thread
 __global__ void resample_search_kernel(const double* cum, long long n, double r, long long lo, long long hi,
                                        int32_t* idx, unsigned long long* overruns)
 {
+    // A thread takes kSearchRun consecutive children: one lower-bound search for the first, then the reference's own
+    // forward walk (U grows by 1/N per child and c is non-decreasing, so the next index is the same or a few further);
+    // a walk longer than 32 steps falls back to a search.  Same indices as a search per child, a sixth of the loads.
     const double m_inv = __ddiv_rn(1.0, (double)n);
-    for (long long m = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < hi;
-         m += (long long)gridDim.x * blockDim.x) {
-        const double u = __dadd_rn(r, __dmul_rn((double)m, m_inv));
-        long long a = 0, b = n;
-        while (a < b) {
-            const long long mid = (a + b) >> 1;
-            if (u > cum[mid]) a = mid + 1; else b = mid;
+    const long long runs = (hi - lo + kSearchRun - 1) / kSearchRun;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < runs; t += (long long)gridDim.x * blockDim.x) {
+        const long long m0 = lo + t * kSearchRun;
+        const long long m1 = m0 + kSearchRun < hi ? m0 + kSearchRun : hi;
+        long long a = 0;
+        for (long long m = m0; m < m1; ++m) {
+            const double u = __dadd_rn(r, __dmul_rn((double)m, m_inv));
+            int steps = 0;
+            if (m != m0)
+                while (a < n && u > cum[a] && steps < 32) { ++a; ++steps; }
+            if (m == m0 || steps == 32) {
+                long long b = n;                  // lower bound in [a, n): c is non-decreasing and so is u
+                while (a < b) {
+                    const long long mid = (a + b) >> 1;
+                    if (u > cum[mid]) a = mid + 1; else b = mid;
+                }
+            }
+            long long out = a;
+            if (out >= n) { out = n - 1; atomicAdd(overruns, 1ull); }
+            idx[m] = (int32_t)out;
         }
-        if (a >= n) { a = n - 1; atomicAdd(overruns, 1ull); }
-        idx[m] = (int32_t)a;
     }
 }
 
