@@ -759,3 +759,38 @@ def test_lse_weight_mode(beta, real_map):
     lin.score(r, th, t)
     assert np.array_equal(lin.normalize(), np.maximum(s, 0.001) / lin.stats()["weight_sum"])
     lin.close()
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_two_pass_randomized_geometry(case):
+    """The certification's error budget depends on the map size, the resolution, the world coordinates and the ray
+    length; sweep them: non-square maps, 2.5 / 5 / 10 cm cells (plus a stale cellsPerMeter, occupancy_grid.cpp:151-159),
+    origins hundreds of metres from zero, ranges up to 12 m, 180...720 beams, beam angles in [-pi, pi) or [0, 2 pi),
+    tracking and scattered clouds.  Two-pass scores == exact-only scores == oracle scores, every time."""
+    rng = np.random.default_rng(1000 + case)
+    mpc = [0.05, 0.025, 0.1, 0.05, 0.05][case % 5]
+    w, h = int(rng.integers(150, 900)), int(rng.integers(150, 900))
+    base = synth.make_map(max(w, h), seed=50 + case, meters_per_cell=mpc)
+    cells = base.cells[:h, :w].copy()
+    cells[-2:, :] = 100; cells[:, -2:] = 100
+    ox, oy = [(-w * mpc / 2, -h * mpc / 2), (731.25, -412.5), (0.0, 0.0), (-2000.0, 1500.0), (5.5, 5.5)][case % 5]
+    cpm = None if case != 7 else 1.0 / 0.05 * 1.01                # stale cells-per-metre
+    grid = synth.GridSpec(cells, ox, oy, mpc, cpm)
+    truth = synth.find_free_pose(grid, rng)
+    nb = int(rng.choice([180, 290, 360, 500, 720]))
+    r, th, t = synth.make_scan(grid, truth, num_beams=nb, seed=case, max_range=float(rng.choice([4.0, 8.0, 12.0])))
+    if case % 2:
+        th = np.where(th > np.pi, th - 2 * np.pi, th).astype(np.float32)
+    n = 20_000
+    if case % 3 == 2:
+        cloud = synth.make_uniform_particles(n, grid, seed=case, utime=int(t[-1]))
+        cloud["parent_pose"]["utime"] = int(t[0])
+        cloud["parent_pose"]["x"] += np.float32(0.01)
+    else:
+        cloud = synth.make_particles(n, truth, seed=case, sigma_xy=float(rng.choice([0.05, 0.3, 1.5])),
+                                     sigma_theta=float(rng.choice([0.02, 0.5])), parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t)
+    want, gathers, evals = port.likelihood(port_grid(grid), cloud, r, th, t)
+    assert np.array_equal(s1, want) and np.array_equal(s2, want)
+    assert st1["gathers"] == gathers and st2["gathers"] == gathers and st2["evals"] == evals
+    assert st1["sensor_path"] == 1
