@@ -29,7 +29,38 @@ def part(p, q):
     return a
 
 
+def mapping_golden():
+    """Mapping::updateMap (mapping.cpp:17-127) over five consecutive scans on the real map: inputs and the grid after
+    every call (the first call, with initialized_ false, must change nothing)."""
+    g0 = ref.RefGrid.from_file(REAL_MAP)
+    info = g0.info()
+    # the recorded map is saturated (free cells at -128, walls at 127), where saturating updates change nothing: start
+    # from a third of its log-odds so the sequence exercises both the adds and the saturation
+    start = (g0.cells().astype(np.int32) // 3).astype(np.int8)
+    g = ref.RefGrid.from_cells(start, info["origin_x"], info["origin_y"], info["meters_per_cell"])
+    grid = synth.GridSpec(g0.cells(), info["origin_x"], info["origin_y"], info["meters_per_cell"], info["cells_per_meter"])
+    rng = np.random.default_rng(77)
+    pose = synth.find_free_pose(grid, rng, clearance=8)
+    prev, t0 = pose, 2_000_000
+    out = {"hit": 40, "miss": 25, "max_laser": 5.0, "steps": 5, "start_cells": start}
+    for k in range(5):
+        r, th, t = synth.make_scan(grid, pose, num_beams=290, seed=300 + k, t0=t0)
+        prv = synth.make_pose(*prev, utime=int(t[0]))
+        cur = synth.make_pose(*pose, utime=int(t[-1]))
+        ref.map_update(g, prv, cur, k > 0, ref.Scan(r, th, t), 5.0, 40, 25)
+        out[f"{k}_ranges"], out[f"{k}_thetas"], out[f"{k}_times"] = r, th, t
+        out[f"{k}_previous"], out[f"{k}_pose"] = np.array(prv), np.array(cur)
+        out[f"{k}_cells"] = g.cells()
+        prev, pose, t0 = pose, synth.odometry_step(rng, pose, step=(0.05, 0.02, 0.04)), t0 + 100_000
+    np.savez_compressed(os.path.join(OUT, "mapping.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "mapping":
+        mapping_golden()
+        print("mapping golden written to", OUT)
+        return
+    mapping_golden()
     # ---- the real map fixture (data/obstacle_slam_10mx10m_5cm.map), as parsed by the reference itself
     g = ref.RefGrid.from_file(REAL_MAP)
     info = g.info()

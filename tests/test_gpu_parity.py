@@ -794,3 +794,20 @@ def test_two_pass_randomized_geometry(case):
     assert np.array_equal(s1, want) and np.array_equal(s2, want)
     assert st1["gathers"] == gathers and st2["gathers"] == gathers and st2["evals"] == evals
     assert st1["sensor_path"] == 1
+
+
+def test_map_update_reference_golden(real_map):
+    """mcl_map_update against the grids the EXECUTED reference left after each of five Mapping::updateMap calls
+    (tests/golden/mapping.npz, tests/golden/make_golden.py: mapping_golden)."""
+    g = load_golden("mapping")
+    start = synth.GridSpec(g["start_cells"], real_map.origin_x, real_map.origin_y, real_map.meters_per_cell,
+                           real_map.cells_per_meter)
+    e = make_engine(16, start)
+    for k in range(int(g["steps"])):
+        prv, cur = g[f"{k}_previous"], g[f"{k}_pose"]
+        e.map_update((float(prv["x"]), float(prv["y"]), float(prv["theta"]), int(prv["utime"])),
+                     (float(cur["x"]), float(cur["y"]), float(cur["theta"]), int(cur["utime"])), k > 0,
+                     g[f"{k}_ranges"], g[f"{k}_thetas"], g[f"{k}_times"], float(g["max_laser"]), int(g["hit"]),
+                     int(g["miss"]))
+        assert np.array_equal(e.read_map_rect(0, 0, start.width, start.height), g[f"{k}_cells"]), k
+    e.close()

@@ -174,3 +174,38 @@ def test_port_vs_reference_resample_large():
     pf.set_particles(ps)
     idx, over = port.resample(w, ref.resample_draw(1, n))
     assert over == 0 and np.array_equal(idx, pf.resample(1))
+
+
+# ---- Mapping::updateMap: the C restatement against the executed reference --------------------------
+def test_map_update_golden(real_map):
+    g = load_golden("mapping")
+    cells = g["start_cells"].copy()
+    for k in range(int(g["steps"])):
+        cells = port.map_update(cells, real_map.origin_x, real_map.origin_y, real_map.cells_per_meter,
+                                g[f"{k}_previous"], g[f"{k}_pose"], k > 0, g[f"{k}_ranges"], g[f"{k}_thetas"],
+                                g[f"{k}_times"], float(g["max_laser"]), int(g["hit"]), int(g["miss"]))
+        assert np.array_equal(cells, g[f"{k}_cells"]), k
+        if k == 0:
+            assert np.array_equal(cells, g["start_cells"])         # first call: initialized_ is false, no cell changes
+    assert (cells != g["start_cells"]).sum() > 500
+    assert (cells == 127).sum() > (g["start_cells"] == 127).sum() and (cells == -128).sum() > 100     # saturation reached
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("hit,miss,max_laser", [(3, 1, 5.0), (127, 100, 8.0), (1, 50, 3.0)])
+def test_map_update_matches_live_reference(hit, miss, max_laser):
+    grid = synth.make_map(300, seed=31)
+    rng = np.random.default_rng(hit)
+    pose = synth.find_free_pose(grid, rng)
+    cells = grid.cells.copy()
+    g = ref.RefGrid.from_cells(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell)
+    prev, t0 = pose, 1_000_000
+    for k in range(5):
+        r, th, t = synth.make_scan(grid, pose, seed=40 + k, t0=t0)
+        prv = synth.make_pose(*prev, utime=int(t[0]) if k % 2 == 0 else int(t[-1]))
+        cur = synth.make_pose(*pose, utime=int(t[-1]))
+        cells = port.map_update(cells, grid.origin_x, grid.origin_y, grid.cells_per_meter, prv, cur, k > 0, r, th, t,
+                                max_laser, hit, miss)
+        ref.map_update(g, prv, cur, k > 0, ref.Scan(r, th, t), max_laser, hit, miss)
+        assert np.array_equal(cells, g.cells()), k
+        prev, pose, t0 = pose, synth.odometry_step(rng, pose), t0 + 100_000
