@@ -405,7 +405,8 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const bool frac_ok = min((unsigned)(bx & fp.fmask), (unsigned)(by & fp.fmask)) != 0u;
     const bool in_x = fabsf(__fsub_rn(ex, fp.mid_x)) < fp.half_x;
     const bool in_y = fabsf(__fsub_rn(ey, fp.mid_y)) < fp.half_y;
-    const bool cell_ok = frac_ok & in_x & in_y;
+    const bool in_win = in_x & in_y;
+    const bool cell_ok = frac_ok & in_win;
     // octant class of the direction; the extended point must not have a negative coordinate
     const float ax = fabsf(px), ay = fabsf(py);
     const float d1 = __fsub_rn(__fadd_rn(ax, ax), ay);      // step x iff 2|ddx| >= |ddy|
@@ -425,11 +426,14 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const int off = __float_as_int(__fadd_rn(offf, 12582912.0f)) - 0x4b400000;
     const int cidx = (int)((unsigned)(by >> kFastFracBits) * (unsigned)pitch + (unsigned)(bx >> kFastFracBits) -
                            (unsigned)fp.idx_bias);
-    const int idx = cell_ok ? cidx : fp.safe_idx;
+    const int idx = in_win ? cidx : fp.safe_idx;       // an endpoint near a cell boundary still reads its float-pass cell
     const int odds = fast_read<SMEM>(cells, sbase, idx);
     const int o1 = fast_read<SMEM>(cells, sbase, idx - off);      // toward the robot
     const int o2 = fast_read<SMEM>(cells, sbase, idx + off);      // toward the extended point
-    const bool certain = outside | (cell_ok & ((odds > 0) | dir_ok));
+    // odds == -1 (derived map, mcl_kernels.cuh: derive_fast_map_kernel): nothing positive within two cells of the
+    // float-pass cell, hence within one cell of the reference's endpoint cell: the score is 0 whichever cell and octant
+    const bool val_ok = cell_ok & ((odds > 0) | dir_ok);       // the cell reads below are the reference's
+    const bool certain = val_ok | outside | (in_win & (odds == -1));
 #ifdef MCL_FAST_DIAG
     {   // why evaluations are deferred (diagnostic build only)
         const bool dirband = !(fminf(fabsf(d1), fabsf(d2)) > fp.t_dir);
@@ -442,9 +446,9 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
         if (!certain) atomicAdd(&g_fast_diag[5], 1ull);
     }
 #endif
-    if (COUNT) gathers += certain ? (cell_ok & (odds > 0) ? 1 : 3) : 0;
+    if (COUNT) gathers += certain ? (val_ok & (odds > 0) ? 1 : 3) : 0;
     const int v = odds > 0 ? 2 * odds : (o1 > 0 ? o1 : max(o2, 0));
-    v2 = cell_ok & certain ? v : 0;       // outside (cell_ok is then false): score 0
+    v2 = val_ok ? v : 0;       // outside / empty neighbourhood: score 0 (an empty neighbourhood also gives v == 0)
     return certain;
 }
 

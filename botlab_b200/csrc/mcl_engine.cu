@@ -100,6 +100,7 @@ struct mcl_engine {
 
     // map mirror
     int8_t* map = nullptr;
+    int8_t* map_fast = nullptr;         // the fast pass's derived view of the map (derive_fast_map_kernel), same pitch
     DevGrid grid{};
     float meters_per_cell = 0.05f;
     bool have_map = false;
@@ -272,6 +273,19 @@ int join_pushes(mcl_engine* h)
         CK(cudaStreamWaitEvent(h->stream, h->ev_push_done, 0));
         h->push_pending = false;
     }
+    return MCL_OK;
+}
+
+// Refreshes the fast pass's derived map over the rectangle [x0, x0+w) x [y0, y0+hgt) widened by the 2-cell look-ahead.
+int refresh_fast_map(mcl_engine* h, int x0, int y0, int w, int hgt)
+{
+    const int xa = std::max(0, x0 - 2), ya = std::max(0, y0 - 2);
+    const int xb = std::min(h->grid.width, x0 + w + 2), yb = std::min(h->grid.height, y0 + hgt + 2);
+    if (xb <= xa || yb <= ya) return MCL_OK;
+    const long long total = (long long)(xb - xa) * (yb - ya);
+    derive_fast_map_kernel<<<grid_for(h, total, 256), 256, 0, h->stream>>>(h->map, h->map_fast, h->grid.width, h->grid.height,
+                                                                          h->grid.pitch, xa, ya, xb - xa, yb - ya);
+    CKL(h);
     return MCL_OK;
 }
 
@@ -466,6 +480,7 @@ int run_score(mcl_engine* h)
         for (int r = 0; r < h->world; ++r) a.peer_score[r] = h->peer_score2[r] + (size_t)h->score_parity * (size_t)h->n;
     }
     a.score2 = h->score2;
+    a.fast_cells = h->map_fast;
     a.lo = h->lo; a.hi = h->hi;
     a.beams = h->beams; a.num_beams = h->num_beams;
     a.grid = h->grid;
@@ -792,7 +807,7 @@ void free_all(mcl_engine* h)
     F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
     if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
     if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
-    F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->beams); F(h->noise); F(h->staging);
+    F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->map_fast); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
     if (h->host_bbox) cudaFreeHost(h->host_bbox);
@@ -1020,16 +1035,20 @@ int mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float
     CK(cudaSetDevice(h->device));
     const int pitch = (width + 15) & ~15;     // 16-byte rows: aligned word loads for the tile stager (and TMA-ready)
     if (!h->map || h->grid.pitch != pitch || h->grid.height != height) {
-        if (h->map) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->map); h->map = nullptr; }
+        if (h->map) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->map); cudaFree(h->map_fast); h->map = h->map_fast = nullptr; }
         CK(cudaMalloc((void**)&h->map, (size_t)pitch * height + 16));
+        CK(cudaMalloc((void**)&h->map_fast, (size_t)pitch * height + 16));
     }
     CK(cudaMemsetAsync(h->map, 0, (size_t)pitch * height + 16, h->stream));
+    CK(cudaMemsetAsync(h->map_fast, 0, (size_t)pitch * height + 16, h->stream));
     CK(cudaMemcpy2DAsync(h->map, pitch, cells, width, width, height, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));     // cells is pageable caller memory: finish before returning
     h->grid.cells = h->map; h->grid.width = width; h->grid.height = height; h->grid.pitch = pitch;
     h->grid.origin_x = ox; h->grid.origin_y = oy; h->grid.cells_per_meter = cpm;
     h->meters_per_cell = mpc;
     h->have_map = true;
+    { int rc = refresh_fast_map(h, 0, 0, width, height); if (rc) return rc; }
+    CK(cudaStreamSynchronize(h->stream));
     return MCL_OK;
 }
 
@@ -1043,6 +1062,7 @@ int mcl_update_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, const int
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpy2DAsync(h->map + (size_t)y0 * h->grid.pitch + x0, h->grid.pitch, src, src_stride, w, hgt,
                          cudaMemcpyHostToDevice, h->stream));
+    { int rc = refresh_fast_map(h, x0, y0, w, hgt); if (rc) return rc; }
     CK(cudaStreamSynchronize(h->stream));
     return MCL_OK;
 }
@@ -1156,6 +1176,7 @@ int mcl_map_update(mcl_engine* h, const mcl_pose_t* previous_pose, const mcl_pos
     map_apply_kernel<<<grid_for(h, (long long)need, 256), 256, 0, h->stream>>>(h->map, h->grid.pitch, a.wx0, a.wy0, ww, wh,
                                                                               h->map_counts, hit_odds, miss_odds);
     CKL(h);
+    { int rc = refresh_fast_map(h, a.wx0, a.wy0, ww, wh); if (rc) return rc; }
     CK(cudaStreamSynchronize(h->stream));
     if (rect_xywh_out) { rect_xywh_out[0] = a.wx0; rect_xywh_out[1] = a.wy0; rect_xywh_out[2] = ww; rect_xywh_out[3] = wh; }
     return MCL_OK;

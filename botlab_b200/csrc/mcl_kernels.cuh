@@ -46,6 +46,7 @@ struct ScoreArgs {
     int tile_x0, tile_y0, tile_w, tile_h, tile_pitch;   // TILE only
     unsigned long long* gather_counter;                  // COUNT only
     FastPlan fast;                                       // two-pass path only
+    const int8_t* fast_cells;                            // two-pass path: the fast pass's view of the map (same pitch)
     uint32_t* masks;                                     // two-pass path: [word][virtual lane] uncertain-beam bits
     unsigned long long* deferred_counter;                // two-pass path: evaluations re-done by the exact pass
     const BatchWindow* windows;                          // BATCH only: one map window per kBatchParticles particles
@@ -97,8 +98,12 @@ __host__ __device__ inline void plan_set_window(FastPlan& fp, long long x0, long
     const long long lcx = (x0 + 1 > 0 ? x0 + 1 : 0), hcx = x0 + w - 1;      // certain-interior cells [lc, hc)
     const long long lcy = (y0 + 1 > 0 ? y0 + 1 : 0), hcy = y0 + hh - 1;
     const bool empty = hcx <= lcx || hcy <= lcy;
-    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = empty ? -1.0f : 0.5f * (float)(hcx - lcx);
-    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = empty ? -1.0f : 0.5f * (float)(hcy - lcy);
+    // The cell is read off the fixed-point bits, which carry the band offset kb/1024 (fp.magic): shrink the box by that
+    // much (+ half a fixed-point step) so that the cell taken from the bits is inside [lc, hc) whenever the test passes,
+    // also for endpoints in the uncertain band just below an integer.
+    const float slack = (fp.magic - 12288.0f) + 0.5f / 1024.0f;
+    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = empty ? -1.0f : 0.5f * (float)(hcx - lcx) - slack;
+    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = empty ? -1.0f : 0.5f * (float)(hcy - lcy) - slack;
     fp.pitch_f = (float)pitch;
     const unsigned mb = (unsigned)kFastMagicBits >> kFastFracBits;
     fp.idx_bias = (int)((mb + (unsigned)(int)y0) * (unsigned)pitch + mb + (unsigned)(int)x0);
@@ -280,10 +285,12 @@ score_fast_kernel(const ScoreArgs a)
         f.ratio = (float)b.ratio; f.theta = b.theta; f.rc = __fmul_rn(b.range, a.grid.cells_per_meter); f.pad = 0.0f;
         sfast[i] = f;
     }
-    if (TILE && !BATCH) stage_tile(a, stile);
+    DevGrid fgrid = a.grid;                 // the derived map: positive cells unchanged, non-positive ones 0 or -1
+    fgrid.cells = a.fast_cells;
+    if (TILE && !BATCH) stage_window(fgrid, a.tile_x0, a.tile_y0, a.tile_h, a.tile_pitch, stile);
     __syncthreads();
 
-    const int8_t* cells = TILE ? stile : a.grid.cells;
+    const int8_t* cells = TILE ? stile : fgrid.cells;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stile);
     int pitch = TILE ? a.tile_pitch : a.grid.pitch;
     FastPlan fp = a.fast;
@@ -301,7 +308,7 @@ score_fast_kernel(const ScoreArgs a)
         if (BATCH) {
             const BatchWindow bw = a.windows[unit];
             __syncthreads();
-            stage_window(a.grid, bw.x0, bw.y0, bw.h, bw.pitch, stile);
+            stage_window(fgrid, bw.x0, bw.y0, bw.h, bw.pitch, stile);
             __syncthreads();
             plan_set_window(fp, bw.x0, bw.y0, bw.w, bw.h, bw.pitch);
             pitch = bw.pitch;
@@ -1060,6 +1067,41 @@ __global__ void resample_search_kernel(const double* cum, long long n, double r,
             if (out >= n) { out = n - 1; atomicAdd(overruns, 1ull); }
             idx[m] = (int32_t)out;
         }
+    }
+}
+
+// =================================================================================================================
+// The fast pass's view of the map.  The score only ever distinguishes "cell > 0" (its value matters) from "cell <= 0"
+// (it reads as nothing), so the non-positive cells of this derived copy are free to carry one bit of look-ahead:
+//   -1 : the cell and its whole 5 x 5 neighbourhood are non-positive.  Wherever the float pass lands within one cell of
+//        the reference's endpoint (its error is far below a cell), the reference's endpoint cell and both Bresenham
+//        neighbours lie inside that neighbourhood, so the ray's score is 0 whatever the exact cell and octant are --
+//        certain without the boundary and direction tests;
+//    0 : non-positive, but something positive is within two cells;
+//   >0 : the cell's own value.
+// Recomputed for the rectangle (+2 cells) of every map change (mcl_set_map, mcl_update_map_rect, mcl_map_update).
+// =================================================================================================================
+__global__ void derive_fast_map_kernel(const int8_t* cells, int8_t* out, int width, int height, int pitch, int x0,
+                                       int y0, int w, int h)
+{
+    const int total = w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = y0 + i / w, x = x0 + i % w;
+        const int v = cells[(size_t)y * pitch + x];
+        int r = v;
+        if (v <= 0) {
+            bool any = false;
+            for (int dy = -2; dy <= 2; ++dy) {
+                const int yy = y + dy;
+                if ((unsigned)yy >= (unsigned)height) continue;
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int xx = x + dx;
+                    if ((unsigned)xx < (unsigned)width) any = any || cells[(size_t)yy * pitch + xx] > 0;
+                }
+            }
+            r = any ? 0 : -1;
+        }
+        out[(size_t)y * pitch + x] = (int8_t)r;
     }
 }
 

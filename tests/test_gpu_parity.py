@@ -811,3 +811,41 @@ def test_map_update_reference_golden(real_map):
                      int(g["miss"]))
         assert np.array_equal(e.read_map_rect(0, 0, start.width, start.height), g[f"{k}_cells"]), k
     e.close()
+
+
+def test_scoring_follows_device_map_updates():
+    """The fast pass reads a derived copy of the map (empty-neighbourhood look-ahead); it must follow every mutation of
+    the mirror: mcl_map_update, mcl_update_map_rect, mcl_set_map.  Scores after each equal the oracle's on the same map."""
+    grid = synth.make_map(300, seed=12)
+    rng = np.random.default_rng(12)
+    pose = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, pose, seed=12)
+    cloud = synth.make_particles(20_000, pose, seed=12, sigma_xy=0.4, sigma_theta=0.3, parent_utime=int(t[0]),
+                                 pose_utime=int(t[-1]))
+    e = make_engine(len(cloud), grid)
+    e.import_particles(cloud)
+    cells = grid.cells.copy()
+
+    def check(tag):
+        g = synth.GridSpec(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
+        want, _, _ = port.likelihood(port_grid(g), cloud, r, th, t)
+        assert np.array_equal(e.score(r, th, t), want), tag
+        assert e.stats()["sensor_path"] == 2
+
+    check("initial")
+    prv = (pose[0] - 0.03, pose[1], pose[2], int(t[0]))
+    cur = (pose[0], pose[1], pose[2], int(t[-1]))
+    for k in range(3):                                   # device-side map updates with strong odds: walls appear / vanish
+        cells = port.map_update(cells, grid.origin_x, grid.origin_y, grid.cells_per_meter,
+                                synth.make_pose(*prv[:3], utime=prv[3]), synth.make_pose(*cur[:3], utime=cur[3]), True,
+                                r, th, t, 8.0, 90, 70)
+        e.map_update(prv, cur, True, r, th, t, 8.0, 90, 70)
+        check(f"map_update {k}")
+    patch = rng.integers(-128, 128, (41, 57)).astype(np.int8)
+    cells[100:141, 120:177] = patch
+    e.update_map_rect(120, 100, patch)
+    check("rect")
+    cells = np.where(rng.random(cells.shape) < 0.01, 50, -5).astype(np.int8)
+    e.set_map(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
+    check("set_map")
+    e.close()

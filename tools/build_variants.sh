@@ -4,6 +4,7 @@
 #   tools/build_variants.sh name1="-DFLAG=1 ..." name2="..."
 set -e
 cd "$(dirname "$0")/../botlab_b200/csrc"
+mkdir -p ../variants
 for spec in "$@"; do
   name="${spec%%=*}"; flags="${spec#*=}"
   ( make -s -B OUT=../variants/libmcl_$name.so EXTRA="$flags" >/dev/null 2>&1 && cp build.log ../variants/$name.log \
