@@ -204,7 +204,7 @@ int seq_total(mcl_engine* h, const double* w, bool materialize)
     CKL(h);
     {
         const size_t walk_smem = (size_t)n2 * 20;                    // g0, g1 (8 B each) + gebias (4 B) per group
-        const int staged = walk_smem + 1024 <= (size_t)h->max_smem_optin ? 1 : 0;
+        const int staged = walk_smem + 4096 <= (size_t)h->max_smem_optin ? 1 : 0;
         if (staged) CK(cudaFuncSetAttribute(seq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
         seq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(
             w, n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2, h->cin1, h->opened, h->total,

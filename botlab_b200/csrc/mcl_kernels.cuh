@@ -925,6 +925,7 @@ __global__ void __launch_bounds__(1024) seq_walk_kernel(const double* w, long lo
 {
     // The walk itself is one warp's work, but its loads sit on the critical path: the whole CTA first stages the group
     // maps in shared memory (staged = 1: they fit), so each step of the walk costs shared-memory, not DRAM, latency.
+    __shared__ double fb_chunk[kL1];          // the raw elements of a chunk that has to be added one by one
     extern __shared__ __align__(16) unsigned char walk_smem[];
     long long* sg0 = reinterpret_cast<long long*>(walk_smem);
     long long* sg1 = sg0 + (staged ? n2 : 0);
@@ -982,9 +983,15 @@ __global__ void __launch_bounds__(1024) seq_walk_kernel(const double* w, long lo
                         const long long gi = efirst + q * 32 + lane;
                         v_l[q] = gi < n ? w[gi] : 0.0;
                     }
+                    // the adds are one dependent chain either way; reading the staged values back from shared memory
+                    // (a broadcast, every lane keeps the same c) keeps the chain at DADD latency instead of
+                    // shuffle + DADD latency per element
 #pragma unroll
-                    for (int q = 0; q < kL1 / 32; ++q)
-                        for (int u = 0; u < 32; ++u) c = __dadd_rn(c, __shfl_sync(0xffffffffu, v_l[q], u));
+                    for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
+                    __syncwarp();
+#pragma unroll 16
+                    for (int i = 0; i < kL1; ++i) c = __dadd_rn(c, fb_chunk[i]);
+                    __syncwarp();
                 }
             }
         }
