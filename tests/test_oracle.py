@@ -209,3 +209,30 @@ def test_map_update_matches_live_reference(hit, miss, max_laser):
         ref.map_update(g, prv, cur, k > 0, ref.Scan(r, th, t), max_laser, hit, miss)
         assert np.array_equal(cells, g.cells()), k
         prev, pose, t0 = pose, synth.odometry_step(rng, pose), t0 + 100_000
+
+
+@needs_ref
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 4, 5, 6, 8, 9])
+def test_port_vs_reference_sensor_geometries(case):
+    """The geometries of tests/test_gpu_parity.py::test_two_pass_randomized_geometry (resolutions, non-square maps, far
+    origins, long ranges, beam counts): the C restatement the GPU is compared with equals the executed reference there
+    too.  (Case 7 uses a stale cellsPerMeter, which the reference's constructor cannot produce.)"""
+    rng = np.random.default_rng(1000 + case)
+    mpc = [0.05, 0.025, 0.1, 0.05, 0.05][case % 5]
+    w, h = int(rng.integers(150, 900)), int(rng.integers(150, 900))
+    base = synth.make_map(max(w, h), seed=50 + case, meters_per_cell=mpc)
+    cells = base.cells[:h, :w].copy()
+    cells[-2:, :] = 100; cells[:, -2:] = 100
+    ox, oy = [(-w * mpc / 2, -h * mpc / 2), (731.25, -412.5), (0.0, 0.0), (-2000.0, 1500.0), (5.5, 5.5)][case % 5]
+    grid = synth.GridSpec(cells, ox, oy, mpc)
+    truth = synth.find_free_pose(grid, rng)
+    nb = int(rng.choice([180, 290, 360, 500, 720]))
+    r, th, t = synth.make_scan(grid, truth, num_beams=nb, seed=case, max_range=float(rng.choice([4.0, 8.0, 12.0])))
+    cloud = synth.make_particles(1500, truth, seed=case, sigma_xy=0.3, sigma_theta=0.5, parent_utime=int(t[0]),
+                                 pose_utime=int(t[-1]))
+    rg = ref.RefGrid.from_cells(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell)
+    info = rg.info()
+    assert info["cells_per_meter"] == np.float32(grid.cells_per_meter)
+    a = ref.likelihood(rg, cloud, ref.Scan(r, th, t))
+    b, _, _ = port.likelihood(port_grid(grid), cloud, r, th, t)
+    assert np.array_equal(a, b)
