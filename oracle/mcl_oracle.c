@@ -430,3 +430,16 @@ long orc_map_update(int8_t* cells, int32_t width, int32_t height, float origin_x
     free(rays);
     return writes;
 }
+
+/* Per-ray scores of ONE particle, in scan order of its valid beams (what orc_likelihood sums): test helper for checks
+ * that need to know which evaluation contributed what.  Returns the number of valid beams written to out. */
+int orc_ray_scores(const orc_grid* g, const orc_particle* p, const float* ranges, const float* thetas,
+                   const int64_t* times, int nb, double* out)
+{
+    float* rays = (float*)malloc(sizeof(float) * 4 * (size_t)(nb > 0 ? nb : 1));
+    const int nr = orc_moving_scan(ranges, thetas, times, nb, &p->parent_pose, &p->pose, rays);   /* sensor_model.cpp:16 */
+    for (int k = 0; k < nr; ++k)
+        out[k] = orc_score_ray(g, rays[4 * k], rays[4 * k + 1], rays[4 * k + 2], rays[4 * k + 3], 0);
+    free(rays);
+    return nr;
+}

@@ -59,6 +59,8 @@ void   orc_init_at_pose(orc_rng* g, const orc_pose* pose, orc_particle* out, int
 int    orc_update(orc_action* a, const orc_grid* g, orc_particle* particles, orc_particle* scratch, int n,
                   const orc_pose* odom, int64_t action_utime, const float* ranges, const float* thetas,
                   const int64_t* times, int nb, double r, const float* draws3n, orc_pose* pose_io);
+int    orc_ray_scores(const orc_grid* g, const orc_particle* p, const float* ranges, const float* thetas,
+                      const int64_t* times, int nb, double* out);
 /* Mapping::updateMap (mapping.cpp:17-127) on a writable int8 grid; see mcl_oracle.c. */
 long   orc_map_update(int8_t* cells, int32_t width, int32_t height, float origin_x, float origin_y, float cells_per_meter,
                       const orc_pose* previous, const orc_pose* pose, int initialized, const float* ranges,

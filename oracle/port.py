@@ -62,6 +62,7 @@ def lib():
         L.orc_action_draws.argtypes = [vp, vp, ip, vp]
         L.orc_init_at_pose.argtypes = [vp, vp, vp, ip]
         L.orc_update.argtypes = [vp, vp, vp, vp, ip, vp, C.c_int64, vp, vp, vp, ip, dp, vp, vp]
+        L.orc_ray_scores.argtypes = [vp, vp, vp, vp, vp, ip, vp]
         L.orc_map_update.restype = C.c_long
         L.orc_map_update.argtypes = [vp, ip, ip, C.c_float, C.c_float, C.c_float, vp, vp, ip, vp, vp, vp, ip, C.c_float,
                                      ip, ip]
@@ -124,6 +125,17 @@ def map_update(cells, origin_x, origin_y, cells_per_meter, previous, pose, initi
                          1 if initialized else 0, _p(ranges), _p(thetas), _p(times), len(ranges), max_laser_distance,
                          hit_odds, miss_odds)
     return out
+
+
+def ray_scores(grid, particle, ranges, thetas, times):
+    """Per-ray scores of one particle over its valid beams, in scan order (their sum is likelihood()'s entry)."""
+    part = np.ascontiguousarray(particle, PARTICLE_DTYPE).reshape(1)
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    thetas = np.ascontiguousarray(thetas, np.float32)
+    times = np.ascontiguousarray(times, np.int64)
+    out = np.zeros(len(ranges), np.float64)
+    k = lib().orc_ray_scores(grid.ptr, _p(part), _p(ranges), _p(thetas), _p(times), len(ranges), _p(out))
+    return out[:k]
 
 
 class ActionModel:

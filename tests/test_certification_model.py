@@ -1,0 +1,101 @@
+"""CPU check of the certified float pass's DESIGN, independent of the CUDA code: a numpy model of
+the pass (tests/certification_model.py: same arithmetic, same tests, same error budget) against the oracle's per-ray
+scores.  Whatever the model calls certain must be the oracle's score -- with the sine/cosine perturbed up to the SFU
+error the budget assumes -- and it must call most evaluations certain, or the two-pass path would be pointless."""
+import numpy as np
+import pytest
+
+from botlab_b200 import synth
+from oracle import port
+import certification_model as cm
+
+MIN_RANGE = 0.15
+
+
+def make_case(case):
+    rng = np.random.default_rng(7000 + case)
+    mpc = [0.05, 0.025, 0.05, 0.05][case % 4]
+    w, h = int(rng.integers(160, 700)), int(rng.integers(160, 700))
+    base = synth.make_map(max(w, h), seed=90 + case, meters_per_cell=mpc)
+    cells = base.cells[:h, :w].copy()
+    cells[-2:, :] = 100; cells[:, -2:] = 100
+    ox, oy = [(-w * mpc / 2, -h * mpc / 2), (731.25, -412.5), (3.0, 3.0), (-2000.0, 1500.0)][case % 4]
+    grid = synth.GridSpec(cells, ox, oy, mpc)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, num_beams=int(rng.choice([180, 360, 500])), seed=case,
+                               max_range=float(rng.choice([4.0, 8.0, 12.0])))
+    if case % 2:
+        th = np.where(th > np.pi, th - 2 * np.pi, th).astype(np.float32)
+    n = 150
+    if case % 3 == 2:
+        cloud = synth.make_uniform_particles(n, grid, seed=case, utime=int(t[-1]))
+        cloud["parent_pose"]["utime"] = int(t[0])
+        cloud["parent_pose"]["x"] += np.float32(0.01)
+    else:
+        cloud = synth.make_particles(n, truth, seed=case, sigma_xy=float(rng.choice([0.05, 0.5])),
+                                     sigma_theta=float(rng.choice([0.02, 0.5])), parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    return grid, cloud, r, th, t
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_certain_evaluations_equal_the_oracle(case):
+    grid, cloud, r, th, t = make_case(case)
+    ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
+        int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
+    plan = cm.Plan(grid, r, th, ratios, MIN_RANGE, 0, 0, grid.width, grid.height)
+    assert plan.enabled and plan.eps < 0.02
+    fast_cells = cm.derive_fast_map(grid.cells)
+    pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
+    rng = np.random.default_rng(case)
+    evals = certain_total = wrong = 0
+    for i in range(len(cloud)):
+        v2, certain = cm.fast_pass(grid, plan, cloud[i], r, th, ratios, MIN_RANGE, fast_cells, rng)
+        want2 = np.rint(2.0 * port.ray_scores(pg, cloud[i], r, th, t)).astype(np.int64)     # half units, exact
+        assert len(want2) == len(v2)
+        wrong += int((certain & (v2 != want2)).sum())
+        evals += len(v2)
+        certain_total += int(certain.sum())
+    assert wrong == 0
+    assert certain_total >= 0.5 * evals, (certain_total, evals)
+
+
+def test_derived_map_flags():
+    cells = np.zeros((12, 12), np.int8)
+    cells[5, 6] = 40
+    cells[0, 0] = -7
+    d = cm.derive_fast_map(cells)
+    assert d[5, 6] == 40
+    assert (d[3:8, 4:9] >= 0).all() and d[3, 4] == 0 and d[7, 8] == 0        # within two cells of the wall: no flag
+    assert d[2, 6] == -1 and d[5, 3] == -1 and d[0, 0] == -1 and d[11, 11] == -1
+
+
+def test_budget_grows_with_the_geometry():
+    """eps must grow with the ray length, the map size and the distance of the origin from zero (the terms of the budget)."""
+    def eps(side, origin, max_range):
+        g = synth.GridSpec(np.zeros((side, side), np.int8), origin, origin, 0.05)
+        r = np.full(360, max_range, np.float32)
+        th = (np.arange(360) * 2 * np.pi / 360).astype(np.float32)
+        return cm.Plan(g, r, th, np.linspace(0, 1, 360), MIN_RANGE, 0, 0, side, side).eps
+    base = eps(400, -10.0, 4.0)
+    assert eps(400, -10.0, 8.0) > base and eps(3000, -75.0, 4.0) > base and eps(400, 3000.0, 4.0) > base
+    assert 2e-4 < base < 2e-3
+
+
+def test_the_check_is_sensitive():
+    """Negative control: with the uncertainty bands removed (every evaluation called certain) the same comparison does
+    find wrong scores, so a passing run above means the bands do their job rather than that the check is blind."""
+    grid, cloud, r, th, t = make_case(3)
+    ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
+        int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
+    plan = cm.Plan(grid, r, th, ratios, MIN_RANGE, 0, 0, grid.width, grid.height)
+    plan.fmask, plan.magic = 1023, np.float32(12288.0)
+    plan.t_dir = plan.t_dir_neg = np.float32(0.0)
+    fast_cells = cm.derive_fast_map(grid.cells)
+    pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
+    rng = np.random.default_rng(3)
+    wrong = 0
+    for i in range(len(cloud)):
+        v2, certain = cm.fast_pass(grid, plan, cloud[i], r, th, ratios, MIN_RANGE, fast_cells, rng)
+        want2 = np.rint(2.0 * port.ray_scores(pg, cloud[i], r, th, t)).astype(np.int64)
+        wrong += int((certain & (v2 != want2)).sum())
+    assert wrong > 0
