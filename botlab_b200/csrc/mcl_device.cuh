@@ -284,32 +284,39 @@ struct __align__(16) FastBeam {
 
 struct FastPlan {
     int enabled;
+    // ---- set by the host for the launch (mcl_engine.cu: fast_plan) -------------------------------------------------
+    int frac_bits;       // fixed-point fractional bits FB (10..12: as many as the window's extent leaves room for)
     int fmask;           // (bits & fmask) == 0  <=>  the coordinate is within the uncertain band of an integer
-    float magic;         // 1.5*2^13 + kb/1024: a float add leaves round(v*1024) + kb in the low mantissa bits
+    int mbk;             // bit pattern of the fixed-point magic number >> FB: (bits >> FB) - mbk = cell
+    float magic;         // 1.5*2^(23-FB) + kb/2^FB: a float add leaves round(v*2^FB) + kb in the low mantissa bits
+    float band;          // kb/2^FB + half a fixed-point step: the slack of the certain-interior box
     float t_dir;         // 3(1 + eps) + slack: octant decisions are certain beyond this
     float t_dir_neg;     // 5(1 + eps) + slack: the same when the extended point has a negative coordinate
-    float x2_min;        // extended-point coordinates at or above this are certainly non-negative in the reference
-    float gmid_x, ghalf_x;   // |e - gmid| >= ghalf  =>  the endpoint is certainly two or more cells outside the grid
-    float gmid_y, ghalf_y;
+    float x2_min;        // extended-point (global) coordinates at or above this are certainly non-negative in the reference
+    float ghalf_x, ghalf_y;   // |e - gmid| >= ghalf  =>  the endpoint is certainly two or more cells outside the grid
     float rho_lo, rho_hi;   // range of the scan's interpolation ratios
     float max_shift;     // largest |dS| (cells) a particle may have and still take the fast pass
-    float coord_hi;      // largest robot cell coordinate the error budget covers
+    float coord_hi;      // largest robot cell coordinate (global) the error budget covers
     float reach;         // longest ray of the scan in cells (+ margin)
     float grid_min_dim;  // min(W, H)
+    int grid_w, grid_h;
+    // ---- set per window (mcl_kernels.cuh: plan_set_window).  The float model works in WINDOW-RELATIVE cell
+    // coordinates: its coordinate roundings then happen at the window's magnitude instead of the map's -------------
+    float shift_x, shift_y;  // window origin (global cells)
     float mid_x, half_x; // certain-interior test on the endpoint: |e - mid| < half  <=>  cell inside [lc, hc)
     float mid_y, half_y;
+    float gmid_x, gmid_y;    // grid centre, window-relative
+    float x2_lo_x, x2_lo_y;  // x2_min, window-relative
     float pitch_f;       // window pitch as a float (the step offset is assembled in float)
-    int idx_bias;        // folds the fixed-point bias and the window origin into the cell index
-    int safe_idx;        // window cell (1,1): read by evaluations whose endpoint is not certain (value discarded)
+    int idx_bias;        // folds the fixed-point bias into the cell index
+    int safe_idx;        // window cell (1,1): read by evaluations whose endpoint is not in the window (value discarded)
 };
 
-constexpr int kFastMagicBits = 0x46400000;      // bit pattern of 12288.0f = 1.5 * 2^13
-constexpr int kFastFracBits = 10;
 // Absolute error bound of fast_sincos for |a| <= 9.5 (measured on B200 over every float in the range by
 // mcl_debug_fast_trig_error: 1.27e-6; tests/test_gpu_parity.py::test_fast_trig_error_bound re-measures it).
 constexpr float kFastTrigErr = 2.0e-6f;
 
-// Per-particle constants of the fast pass, in GLOBAL cell coordinates.
+// Per-particle constants of the fast pass, in WINDOW-RELATIVE cell coordinates.
 struct FastBase {
     float sxb, syb, thb;     // robot cell coordinate / heading at rho = 0 (or the pose itself when !INTERP)
     float dsx, dsy, dth;     // change over rho = 0..1
@@ -323,24 +330,28 @@ __device__ __forceinline__ FastBase make_fast_base(float xa, float ya, float tha
                                                    double gx, double gy, double cpm_d, const FastPlan& fp)
 {
     FastBase f;
+    double gsx, gsy;             // robot cell coordinate in GLOBAL cells (double): validity checks, then shifted
     if (INTERP) {
-        f.sxb = (float)__dmul_rn(__dsub_rn((double)xb, gx), cpm_d);
-        f.syb = (float)__dmul_rn(__dsub_rn((double)yb, gy), cpm_d);
+        gsx = __dmul_rn(__dsub_rn((double)xb, gx), cpm_d);
+        gsy = __dmul_rn(__dsub_rn((double)yb, gy), cpm_d);
         f.thb = thb;
         f.dsx = (float)__dmul_rn((double)__fsub_rn(xa, xb), cpm_d);     // the reference's float difference (interpolation.hpp:39)
         f.dsy = (float)__dmul_rn((double)__fsub_rn(ya, yb), cpm_d);
         f.dth = (float)fold_pi(__dsub_rn((double)tha, (double)thb));    // angle_diff (:41)
     } else {
-        f.sxb = (float)__dmul_rn(__dsub_rn((double)xa, gx), cpm_d);
-        f.syb = (float)__dmul_rn(__dsub_rn((double)ya, gy), cpm_d);
+        gsx = __dmul_rn(__dsub_rn((double)xa, gx), cpm_d);
+        gsy = __dmul_rn(__dsub_rn((double)ya, gy), cpm_d);
         f.thb = tha;
         f.dsx = 0.0f; f.dsy = 0.0f; f.dth = 0.0f;
     }
-    // The robot's cell coordinate must stay in [1, coord_hi] over the whole sweep (truncation == floor, fixed-point
-    // range), the headings must be wrapped ones, and the particle must not jump: everything else (NaN included: the
-    // comparisons fail) is left to the exact pass.
-    const float x0 = __fmaf_rn(f.dsx, fp.rho_lo, f.sxb), x1 = __fmaf_rn(f.dsx, fp.rho_hi, f.sxb);
-    const float y0 = __fmaf_rn(f.dsy, fp.rho_lo, f.syb), y1 = __fmaf_rn(f.dsy, fp.rho_hi, f.syb);
+    f.sxb = (float)__dsub_rn(gsx, (double)fp.shift_x);
+    f.syb = (float)__dsub_rn(gsy, (double)fp.shift_y);
+    // The robot's GLOBAL cell coordinate must stay in [1, coord_hi] over the whole sweep (truncation == floor, the
+    // budget's magnitudes), the headings must be wrapped ones, and the particle must not jump: everything else (NaN
+    // included: the comparisons fail) is left to the exact pass.
+    const float gxb = (float)gsx, gyb = (float)gsy;
+    const float x0 = __fmaf_rn(f.dsx, fp.rho_lo, gxb), x1 = __fmaf_rn(f.dsx, fp.rho_hi, gxb);
+    const float y0 = __fmaf_rn(f.dsy, fp.rho_lo, gyb), y1 = __fmaf_rn(f.dsy, fp.rho_hi, gyb);
     const float lo = fminf(fminf(x0, x1), fminf(y0, y1)), hi = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
     f.ok = lo >= 1.0f && hi <= fp.coord_hi && fabsf(f.dsx) <= fp.max_shift && fabsf(f.dsy) <= fp.max_shift &&
            fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f;
@@ -399,7 +410,7 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
 {
     float px, py, ex, ey;
     fast_endpoint<INTERP>(p, b, px, py, ex, ey);
-    // fixed point: low 10 bits = fraction (+ the band offset), the rest = cell (+ bias)
+    // fixed point: low FB bits = fraction (+ the band offset), the rest = cell (+ bias)
     const int bx = __float_as_int(__fadd_rn(ex, fp.magic)), by = __float_as_int(__fadd_rn(ey, fp.magic));
     // endpoint cell certain: not within eps of a cell boundary, interior to the window and inside the grid
     const bool frac_ok = min((unsigned)(bx & fp.fmask), (unsigned)(by & fp.fmask)) != 0u;
@@ -413,7 +424,8 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const float d2 = __fsub_rn(__fadd_rn(ay, ay), ax);      // step y iff |ddx| <= 2|ddy|
     // an extended point at a negative coordinate is truncated toward zero by the reference (not floored), which
     // widens the band of its differences from 3 to 5 cells
-    const float t_dir = (EDGE < 2 || fminf(__fadd_rn(ex, px), __fadd_rn(ey, py)) >= fp.x2_min) ? fp.t_dir : fp.t_dir_neg;
+    const bool x2_pos = EDGE < 2 || ((__fadd_rn(ex, px) >= fp.x2_lo_x) & (__fadd_rn(ey, py) >= fp.x2_lo_y));
+    const float t_dir = x2_pos ? fp.t_dir : fp.t_dir_neg;
     const bool dir_ok = fminf(fabsf(d1), fabsf(d2)) > t_dir;
     // endpoint certainly two or more cells outside the grid: it and both neighbours read 0 (occupancy_grid.cpp:65-70)
     const bool outside = EDGE >= 1 && ((fabsf(__fsub_rn(ex, fp.gmid_x)) >= fp.ghalf_x) |
@@ -424,7 +436,7 @@ __device__ __forceinline__ bool score_beam_fast(const FastBase& p, const FastBea
     const float uy = __uint_as_float((__float_as_uint(py) & 0x80000000u) | 0x3f800000u);
     const float offf = __fmaf_rn(d2 > 0.0f ? uy : 0.0f, fp.pitch_f, d1 > 0.0f ? ux : 0.0f);
     const int off = __float_as_int(__fadd_rn(offf, 12582912.0f)) - 0x4b400000;
-    const int cidx = (int)((unsigned)(by >> kFastFracBits) * (unsigned)pitch + (unsigned)(bx >> kFastFracBits) -
+    const int cidx = (int)((unsigned)(by >> fp.frac_bits) * (unsigned)pitch + (unsigned)(bx >> fp.frac_bits) -
                            (unsigned)fp.idx_bias);
     const int idx = in_win ? cidx : fp.safe_idx;       // an endpoint near a cell boundary still reads its float-pass cell
     const int odds = fast_read<SMEM>(cells, sbase, idx);

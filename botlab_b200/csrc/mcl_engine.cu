@@ -416,41 +416,55 @@ int launch_score(mcl_engine* h, int G, bool tile, bool batch, const ScoreArgs& a
 //     product roundings + Rc x (angle roundings 32u + measured SFU error kFastTrigErr)
 // eps = 1.25 x the sum.  A coordinate is certain when it is further than eps + 2^-11 (fixed-point rounding) from an
 // integer; a direction when both octant discriminants exceed 3(1 + eps).
-FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w, long long hh, long long pitch)
+// max_dim: the largest window width/height the plan has to cover (the window's own for a single window, the largest
+// over the batches for per-batch windows).
+FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w, long long hh, long long pitch,
+                   long long max_dim)
 {
     FastPlan fp{};
     const double cpm = h->grid.cells_per_meter;
     const double Rc = (double)h->max_range * cpm;
     const double rho_max = std::max(std::fabs(h->ratio_lo), std::fabs(h->ratio_hi));
     const double Cm = (double)std::max(x0 + w, y0 + hh) + 1.0;
+    const double We = (double)max_dim + Rc + 8.0;     // magnitude of the window-relative coordinates the budget covers
     // min_range * cpm >= 2.5: the endpoint is never the robot's own cell (the reference's zero-difference step rule
     // is then out of play); pitch < 2^20: the float-assembled step offset is exact
     const bool usable = h->params.sensor_path != 1 && h->num_beams > 0 && std::isfinite(Rc) && cpm > 0.0 &&
                         (double)h->params.min_range * cpm >= 2.5 && h->max_abs_theta <= 6.3f && h->ratio_lo >= -1.0 &&
                         h->ratio_hi <= 2.0 && w >= 3 && hh >= 3 && Cm <= 4090.0 && x0 >= -4 && y0 >= -4 &&
-                        pitch < (1 << 20);
+                        pitch < (1 << 20) && max_dim + 8 < 4096;
     if (!usable) return fp;
+    // v + 1.5*2^(23-FB) must stay in one binade for every coordinate whose bits are used: those inside the window
+    const int fb = max_dim + 8 < 1024 ? 12 : (max_dim + 8 < 2048 ? 11 : 10);
     const double u = 5.9604644775390625e-08;
     const double Xm = Cm / cpm + std::max(std::fabs((double)h->grid.origin_x), std::fabs((double)h->grid.origin_y));
     const double max_shift = 64.0;
     const double Ce = Cm + Rc;            // endpoints beyond the grid (certified as "outside") reach this far
     const double e_ref = cpm * u * Xm + 2.0 * u * Ce + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
-    const double e_apx = 3.0 * u * Ce + (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
+    const double e_apx = 3.0 * u * We + (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
                          Rc * ((M_PI * (3.0 * rho_max + 1.0) + 9.5) * u + (double)kFastTrigErr);
     const double eps = 1.25 * (e_ref + e_apx) + 1e-6;
-    const int k = (int)std::ceil(1024.0 * eps + 0.5);
-    if (k > 32) return fp;                       // the uncertain band would cover > 6 % of every cell: not worth it
+    const int one = 1 << fb;
+    const int k = (int)std::ceil((double)one * eps + 0.5);
+    if (k > one / 32) return fp;                 // the uncertain band would cover > 6 % of every cell: not worth it
     int kb = 1;
     while (kb < k) kb <<= 1;                     // power-of-two band: "within the band" becomes one AND
     fp.enabled = 1;
-    fp.fmask = 1023 & ~(2 * kb - 1);
-    fp.magic = 12288.0f + (float)kb / 1024.0f;
+    fp.frac_bits = fb;
+    fp.fmask = (one - 1) & ~(2 * kb - 1);
+    const float magic_base = (float)(1.5 * (double)(1 << (23 - fb)));
+    int mb_bits;
+    std::memcpy(&mb_bits, &magic_base, 4);
+    fp.mbk = mb_bits >> fb;
+    fp.magic = magic_base + (float)kb / (float)one;
+    fp.band = (float)kb / (float)one + 0.5f / (float)one;
     fp.t_dir = (float)(3.0 * (1.0 + eps) + 4.0 * u * Rc + 1e-4);
     fp.t_dir_neg = (float)(5.0 * (1.0 + eps) + 4.0 * u * Rc + 1e-4);
     fp.x2_min = (float)(3.0 * eps + 1e-3);       // the extended point's error is below 2 eps (twice the ray term)
     // reference: score 0 when trunc(e) <= -2 or >= W + 1 on either axis, i.e. e <= -2 or e >= W + 1
-    fp.gmid_x = 0.5f * (float)(h->grid.width - 1); fp.ghalf_x = (float)(0.5 * (h->grid.width + 3) + eps + 1e-3);
-    fp.gmid_y = 0.5f * (float)(h->grid.height - 1); fp.ghalf_y = (float)(0.5 * (h->grid.height + 3) + eps + 1e-3);
+    fp.grid_w = h->grid.width; fp.grid_h = h->grid.height;
+    fp.ghalf_x = (float)(0.5 * (h->grid.width + 3) + eps + 1e-3);
+    fp.ghalf_y = (float)(0.5 * (h->grid.height + 3) + eps + 1e-3);
     fp.rho_lo = (float)h->ratio_lo; fp.rho_hi = (float)h->ratio_hi;
     fp.max_shift = (float)max_shift;
     fp.coord_hi = (float)(Cm - 1.0);
@@ -500,6 +514,7 @@ int run_score(mcl_engine* h)
     size_t smem = (size_t)h->num_beams * sizeof(Beam);          // == sizeof(FastBeam) per beam
     bool tile = false, batch = false;
     size_t batch_tile_bytes = 0;
+    long long batch_max_dim = 0;
     if (h->params.map_tile != 1 && local > 0 && h->num_beams > 0) {
         int* box = h->bbox;
         const int init_box[4] = {0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000};
@@ -555,15 +570,16 @@ int run_score(mcl_engine* h)
             const size_t base2 = std::max(smem, deferred_smem_bytes(h->num_beams, kBatchDefThreads / 32));
             const long long budget = (long long)h->max_smem_optin - (long long)base2 - 1024;
             if (budget > 4096) {
-                h->host_bbox[0] = 0; h->host_bbox[1] = 0;
-                CK(cudaMemcpyAsync(h->bbox, h->host_bbox, 8, cudaMemcpyHostToDevice, h->stream));
+                h->host_bbox[0] = 0; h->host_bbox[1] = 0; h->host_bbox[2] = 0;
+                CK(cudaMemcpyAsync(h->bbox, h->host_bbox, 12, cudaMemcpyHostToDevice, h->stream));
                 batch_window_kernel<<<(int)nb, 256, 0, h->stream>>>(p.x, p.y, q.x, q.y, h->lo, h->hi, h->grid,
                                                                    (double)h->max_range * h->grid.cells_per_meter + 3.0,
                                                                    (int)budget, h->windows, h->bbox);
                 CKL(h);
-                CK(cudaMemcpyAsync(h->host_bbox, h->bbox, 8, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpyAsync(h->host_bbox, h->bbox, 12, cudaMemcpyDeviceToHost, h->stream));
                 CK(cudaStreamSynchronize(h->stream));
                 const int max_bytes = h->host_bbox[0], misfits = h->host_bbox[1];
+                batch_max_dim = h->host_bbox[2];
                 if (max_bytes > 0 && (long long)misfits * 50 <= nb) {     // at most 2 % of the batches without a tile
                     batch = true;
                     tile = true;
@@ -579,8 +595,10 @@ int run_score(mcl_engine* h)
             return fail(h, MCL_ERR_INVALID, "map_tile=2 forced but the cloud's window does not fit in shared memory");
     }
     if (h->params.sensor_path != 1 && local > 0)
-        a.fast = tile ? fast_plan(h, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch)
-                      : fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch);
+        a.fast = batch ? fast_plan(h, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch, batch_max_dim)
+               : tile  ? fast_plan(h, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.tile_pitch, std::max(a.tile_w, a.tile_h))
+                       : fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch,
+                                   std::max(h->grid.width, h->grid.height));
     const bool fast = a.fast.enabled != 0;
     int rc;
     if (fast) {
@@ -1548,7 +1566,7 @@ int mcl_debug_fast_margin(mcl_engine* h, double* max_dev_endpoint, double* max_d
     a.lo = h->lo; a.hi = h->hi;
     a.beams = h->beams; a.num_beams = h->num_beams;
     a.grid = h->grid;
-    a.fast = fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch);
+    a.fast = fast_plan(h, 0, 0, h->grid.width, h->grid.height, h->grid.pitch, std::max(h->grid.width, h->grid.height));
     *eps_out = a.fast.enabled ? h->stats_eps : 0.0;
     *max_dev_endpoint = *max_dev_extended = 0.0;
     if (!a.fast.enabled || h->num_beams == 0) return MCL_OK;

@@ -92,27 +92,33 @@ __device__ __forceinline__ Window make_window(const ScoreArgs& a, const int8_t* 
 }
 
 // The window-dependent fields of the fast plan (the eps-dependent ones are set by the host: mcl_engine.cu fast_plan).
+// Everything here is in WINDOW-RELATIVE cells: cell (x0, y0) of the grid is (0, 0).
 __host__ __device__ inline void plan_set_window(FastPlan& fp, long long x0, long long y0, long long w, long long hh,
                                                 long long pitch)
 {
-    const long long lcx = (x0 + 1 > 0 ? x0 + 1 : 0), hcx = x0 + w - 1;      // certain-interior cells [lc, hc)
-    const long long lcy = (y0 + 1 > 0 ? y0 + 1 : 0), hcy = y0 + hh - 1;
+    fp.shift_x = (float)x0; fp.shift_y = (float)y0;
+    // certain-interior cells [lc, hc): one cell inside the window, and inside the grid (global cell >= 0)
+    const long long lcx = (-x0 > 1 ? -x0 : 1), hcx = w - 1;
+    const long long lcy = (-y0 > 1 ? -y0 : 1), hcy = hh - 1;
     const bool empty = hcx <= lcx || hcy <= lcy;
-    // The cell is read off the fixed-point bits, which carry the band offset kb/1024 (fp.magic): shrink the box by that
-    // much (+ half a fixed-point step) so that the cell taken from the bits is inside [lc, hc) whenever the test passes,
-    // also for endpoints in the uncertain band just below an integer.
-    const float slack = (fp.magic - 12288.0f) + 0.5f / 1024.0f;
-    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = empty ? -1.0f : 0.5f * (float)(hcx - lcx) - slack;
-    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = empty ? -1.0f : 0.5f * (float)(hcy - lcy) - slack;
+    // The cell is read off the fixed-point bits, which carry the band offset (fp.magic): shrink the box by that much
+    // (+ half a fixed-point step, fp.band) so that the cell taken from the bits is inside [lc, hc) whenever the test
+    // passes, also for endpoints in the uncertain band just below an integer.
+    fp.mid_x = 0.5f * (float)(lcx + hcx); fp.half_x = empty ? -1.0f : 0.5f * (float)(hcx - lcx) - fp.band;
+    fp.mid_y = 0.5f * (float)(lcy + hcy); fp.half_y = empty ? -1.0f : 0.5f * (float)(hcy - lcy) - fp.band;
+    fp.gmid_x = 0.5f * (float)(fp.grid_w - 1) - (float)x0;
+    fp.gmid_y = 0.5f * (float)(fp.grid_h - 1) - (float)y0;
+    fp.x2_lo_x = fp.x2_min - (float)x0;
+    fp.x2_lo_y = fp.x2_min - (float)y0;
     fp.pitch_f = (float)pitch;
-    const unsigned mb = (unsigned)kFastMagicBits >> kFastFracBits;
-    fp.idx_bias = (int)((mb + (unsigned)(int)y0) * (unsigned)pitch + mb + (unsigned)(int)x0);
+    fp.idx_bias = (int)((unsigned)fp.mbk * (unsigned)pitch + (unsigned)fp.mbk);
     fp.safe_idx = (int)pitch + 1;          // an empty window still has (pitch >= 4) bytes of shared memory behind it
 }
 
 // Bounding box of a batch's poses and parents -> its map window, with the same rule as the single-tile path
 // (bbox +- (max range + 3 cells), clipped to the grid plus a 2-cell zero margin, 4-byte aligned, odd word pitch).
-// summary[0] = largest window in bytes among batches that fit the budget, summary[1] = batches that do not fit
+// summary[0] = largest window in bytes among batches that fit the budget, summary[2] = their largest width/height,
+// summary[1] = batches that do not fit
 // (they get an empty window: pass 1 defers everything, the exact pass reads the global mirror).
 __device__ __forceinline__ int float_order_i(float f)
 {
@@ -174,7 +180,8 @@ __global__ void __launch_bounds__(256) batch_window_kernel(const float* x, const
             }
         }
         out[blockIdx.x] = bw;
-        if (fits) atomicMax(summary + 0, bw.bytes); else atomicAdd(summary + 1, 1);
+        if (fits) { atomicMax(summary + 0, bw.bytes); atomicMax(summary + 2, max(bw.w, bw.h)); }
+        else atomicAdd(summary + 1, 1);
     }
 }
 

@@ -42,7 +42,8 @@ def test_certain_evaluations_equal_the_oracle(case):
     grid, cloud, r, th, t = make_case(case)
     ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
         int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
-    plan = cm.Plan(grid, r, th, ratios, MIN_RANGE, 0, 0, grid.width, grid.height)
+    window = (0, 0, grid.width, grid.height) if case % 2 else cm.cloud_window(grid, cloud, r, MIN_RANGE)
+    plan = cm.Plan(grid, r, th, ratios, MIN_RANGE, *window)
     assert plan.enabled and plan.eps < 0.02
     fast_cells = cm.derive_fast_map(grid.cells)
     pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
@@ -88,7 +89,7 @@ def test_the_check_is_sensitive():
     ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
         int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
     plan = cm.Plan(grid, r, th, ratios, MIN_RANGE, 0, 0, grid.width, grid.height)
-    plan.fmask, plan.magic = 1023, np.float32(12288.0)
+    plan.fmask, plan.magic = (1 << plan.fb) - 1, plan.magic_base
     plan.t_dir = plan.t_dir_neg = np.float32(0.0)
     fast_cells = cm.derive_fast_map(grid.cells)
     pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)

@@ -20,7 +20,8 @@ for case in range(cases):
     grid, cloud, r, th, t = T.make_case(case)
     ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
         int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
-    plan = cm.Plan(grid, r, th, ratios, 0.15, 0, 0, grid.width, grid.height)
+    window = (0, 0, grid.width, grid.height) if case % 2 else cm.cloud_window(grid, cloud, r, 0.15)
+    plan = cm.Plan(grid, r, th, ratios, 0.15, *window)
     if not plan.enabled:
         print(case, "float pass not applicable")
         continue
@@ -33,6 +34,6 @@ for case in range(cases):
         for i in range(len(cloud)):
             v2, c = cm.fast_pass(grid, plan, cloud[i], r, th, ratios, 0.15, fc, rng)
             wr += int((c & (v2 != want[i])).sum()); ev += len(v2); ce += int(c.sum())
-    print(case, f"{grid.width}x{grid.height} eps {plan.eps:.2e} band {2 * plan.kb}/1024 certain {ce / ev:.3f} wrong {wr} evals {ev}", flush=True)
+    print(case, f"{grid.width}x{grid.height} eps {plan.eps:.2e} band {2 * plan.kb}/{1 << plan.fb} certain {ce / ev:.3f} wrong {wr} evals {ev}", flush=True)
     tot_e += ev; tot_c += ce; tot_w += wr
 print(f"TOTAL evals {tot_e} certain {tot_c / max(tot_e, 1):.3f} wrong {tot_w}")
