@@ -3,6 +3,7 @@
 // per update the host sends ~6 KB (prepared beams + scalars) and reads back one pose.
 #include "../../include/mcl_cuda.h"
 #include "mcl_kernels.cuh"
+#include "mcl_table.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -90,6 +91,17 @@ struct mcl_engine {
     size_t masks_bytes = 0;
     double* ess_acc = nullptr;
     int* bbox = nullptr;
+    // table sensor path (mcl_table.cuh): device-side window plan, its pinned copy (the host's hint for the next update)
+    TabPlan* tab_plan = nullptr;
+    int* tab_box = nullptr;             // bounding box of the cloud (ordered-int atomics); table_plan_kernel re-arms it
+    int* tab_build = nullptr;           // [0] table entries needed, [1] CTAs whose table overflowed
+    struct TabHint { TabPlan plan; int build[2]; };
+    TabHint* tab_hint = nullptr;        // pinned
+    cudaEvent_t ev_tab_hint = nullptr;
+    bool tab_hint_pending = false;
+    bool tab_ok = false;                // the last plan the host has seen allows the table pass
+    int tab_blocked = 0;                // updates to keep off the table pass after an overflow
+    bool scan_finite = true;
 
     // estimate
     double4* est_partials = nullptr;
@@ -120,6 +132,7 @@ struct mcl_engine {
     void* staging = nullptr;           // device scratch for AoS / double vectors
     size_t staging_bytes = 0;
     int* host_bbox = nullptr;          // pinned 4 ints
+    int* host_bbox_init = nullptr;     // pinned: the empty box
     unsigned long long* host_counters = nullptr;   // pinned: overruns, gathers, fallbacks, (double) total, ess
 
     // stats
@@ -309,7 +322,7 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
     int k = 0;
     float mx = 0.0f, mth = 0.0f;
     double rlo = 1.0, rhi = 1.0;
-    bool finite = true;
+    bool finite = true, all_finite = true;
     for (int i = 0; i < nb; ++i) {
         if (ranges[i] > h->params.min_range) {                 // moving_laser_scan.cpp:24
             Beam b;
@@ -318,6 +331,7 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
             b.ratio = interp ? (double)(times[i] - t_begin) / denom : 1.0;
             h->beams_host[k++] = b;
             if (std::isfinite(ranges[i])) mx = std::max(mx, ranges[i]);
+            else all_finite = false;
             finite = finite && std::isfinite(thetas[i]);
             mth = std::max(mth, std::fabs(thetas[i]));
             rlo = (k == 1) ? b.ratio : std::min(rlo, b.ratio);
@@ -327,6 +341,7 @@ int prepare_scan(mcl_engine* h, const float* ranges, const float* thetas, const 
     h->num_beams = k;
     h->max_range = mx;
     h->max_abs_theta = finite ? mth : INFINITY;
+    h->scan_finite = finite && all_finite;
     h->ratio_lo = rlo; h->ratio_hi = rhi;
     h->scan_interp = interp;
     if (k > 0) CK(cudaMemcpyAsync(h->beams, h->beams_host, sizeof(Beam) * k, cudaMemcpyHostToDevice, h->stream));
@@ -476,6 +491,87 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     return fp;
 }
 
+// ---- table sensor path (mcl_table.cuh) ------------------------------------------------------------------------------
+// Launch order on the engine's stream: bbox_kernel -> table_plan_kernel (one thread: window + budget, in device memory)
+// -> score_table_kernel.  No host round trip: the host only needs to know whether the table pass is APPLICABLE, and
+// takes that from the plan of the previous update (copied to pinned memory behind the kernel); the kernel itself
+// verifies the plan and sends every evaluation down the exact path when it does not hold, so a stale hint costs time,
+// never correctness.  The first scoring pass after the cloud was (re)initialised plans synchronously.
+constexpr long long kTabMinParticles = 1024;
+
+// returns 1 when the table kernel has been launched, 0 when the caller should use the other kernel families, < 0 on error
+int run_score_table(mcl_engine* h, ScoreArgs& sa)
+{
+    const long long local = h->hi - h->lo;
+    const int lanes = h->params.lanes_per_particle;
+    const bool cand = h->params.sensor_path != 1 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
+                      local >= kTabMinParticles && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
+                      std::isfinite(h->max_range) && !std::getenv("MCL_NO_TABLE");
+    if (!cand) return 0;
+    if (h->tab_hint_pending && cudaEventQuery(h->ev_tab_hint) == cudaSuccess) {
+        h->tab_hint_pending = false;
+        h->tab_ok = h->tab_hint->plan.ok != 0;
+        if (h->tab_hint->build[1] != 0) { h->tab_ok = false; h->tab_blocked = 64; }
+        if (h->tab_ok) h->stats_eps = h->tab_hint->plan.eps;
+    }
+    if (h->tab_blocked > 0) { --h->tab_blocked; return 0; }
+    const size_t smem_total = (size_t)h->max_smem_optin - 1024;      // static shared memory of the kernel stays below 1 KB
+    TabPlanIn in{};
+    in.grid = h->grid;
+    in.max_range = h->max_range; in.min_range = h->params.min_range; in.max_abs_theta = h->max_abs_theta;
+    in.ratio_lo = h->ratio_lo; in.ratio_hi = h->ratio_hi;
+    in.num_beams = h->num_beams;
+    in.scan_finite = h->scan_finite ? 1 : 0;
+    in.allow = 1;
+    in.smem_total = (int)smem_total;
+    in.smem_fixed = (int)table_fixed_smem(h->num_beams);
+    bbox_kernel<<<grid_for(h, local, 256), 256, 0, h->stream>>>(sa.x, sa.y, sa.px, sa.py, h->lo, h->hi, h->tab_box);
+    CKL(h);
+    table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan);
+    CKL(h);
+    if (!h->tab_ok) {
+        // no usable hint (first pass after an init / import, or the last plan did not allow the table): plan synchronously
+        CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->tab_hint_pending = false;
+        h->tab_ok = h->tab_hint->plan.ok != 0;
+        if (!h->tab_ok) return 0;
+        h->stats_eps = h->tab_hint->plan.eps;
+    }
+    TabArgs a{};
+    a.x = sa.x; a.y = sa.y; a.th = sa.th; a.px = sa.px; a.py = sa.py; a.pth = sa.pth;
+    a.score2 = sa.score2;
+    a.lo = sa.lo; a.hi = sa.hi;
+    a.beams = sa.beams; a.num_beams = sa.num_beams;
+    a.grid = sa.grid;
+    a.fast_cells = sa.fast_cells;
+    a.plan = h->tab_plan;
+    a.gather_counter = sa.gather_counter;
+    a.deferred_counter = sa.deferred_counter;
+    a.build_info = h->tab_build;
+    a.num_peers = sa.num_peers;
+    for (int r = 0; r < kMaxPeers; ++r) a.peer_score[r] = sa.peer_score[r];
+    CK(cudaMemsetAsync(h->tab_build, 0, 2 * sizeof(int), h->stream));
+    const long long nunits = (local + 31) / 32;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(nunits, h->sm_count));
+    auto launch = [&](auto kernel) -> int {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
+        kernel<<<blocks, kTabThreads, smem_total, h->stream>>>(a);
+        CKL(h);
+        return MCL_OK;
+    };
+    int rc;
+    if (h->scan_interp) rc = h->count_gathers ? launch(score_table_kernel<true, true>) : launch(score_table_kernel<true, false>);
+    else rc = h->count_gathers ? launch(score_table_kernel<false, true>) : launch(score_table_kernel<false, false>);
+    if (rc) return rc;
+    // the plan and the build summary follow the kernel to pinned memory: the hint for the next update
+    CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->tab_hint->build, h->tab_build, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_tab_hint, h->stream));
+    h->tab_hint_pending = true;
+    return 1;
+}
+
 int run_score(mcl_engine* h)
 {
     if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
@@ -502,6 +598,30 @@ int run_score(mcl_engine* h)
     a.deferred_counter = h->deferred_counter;
     if (h->count_gathers) CK(cudaMemsetAsync(h->gather_counter, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->deferred_counter, 0, sizeof(unsigned long long), h->stream));
+
+    if (local > 0) {
+        const int tr = run_score_table(h, a);
+        if (tr < 0) return tr;
+        if (tr == 1) {
+            int rc = join_pushes(h);
+            if (rc) return rc;
+            if (a.num_peers > 0) {
+                rc = rank_barrier(h);
+                if (rc) return rc;
+                ++h->collectives;
+            } else {
+                rc = exchange_slices(h, h->score2, sizeof(int32_t));
+                if (rc) return rc;
+            }
+            h->stats.lanes_per_particle = 1;
+            h->stats.map_tile_used = 4;
+            h->stats.sensor_path = 3;
+            h->stats.fast_eps = h->stats_eps;
+            h->stats.evals = local * (long long)h->num_beams;
+            h->have_scores = true;
+            return MCL_OK;
+        }
+    }
 
     // lanes per particle: enough particle groups to fill the machine (148 SMs x 8 CTAs x (256/G) slots)
     int G = h->params.lanes_per_particle;
@@ -829,6 +949,10 @@ void free_all(mcl_engine* h)
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
     if (h->host_bbox) cudaFreeHost(h->host_bbox);
+    if (h->host_bbox_init) cudaFreeHost(h->host_bbox_init);
+    if (h->tab_hint) cudaFreeHost(h->tab_hint);
+    if (h->ev_tab_hint) cudaEventDestroy(h->ev_tab_hint);
+    F(h->tab_plan); F(h->tab_build); F(h->tab_box);
     if (h->host_counters) cudaFreeHost(h->host_counters);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -930,6 +1054,17 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMalloc((void**)&h->est_out, 16));
     CKB(cudaMallocHost((void**)&h->est_host, 16));
     CKB(cudaMallocHost((void**)&h->host_bbox, 16));
+    CKB(cudaMallocHost((void**)&h->host_bbox_init, 16));
+    h->host_bbox_init[0] = h->host_bbox_init[1] = 0x7fffffff;
+    h->host_bbox_init[2] = h->host_bbox_init[3] = (int)0x80000000;
+    CKB(cudaMalloc((void**)&h->tab_box, 16));
+    CKB(cudaMemcpy(h->tab_box, h->host_bbox_init, 16, cudaMemcpyHostToDevice));
+    CKB(cudaMalloc((void**)&h->tab_plan, sizeof(TabPlan)));
+    CKB(cudaMemset(h->tab_plan, 0, sizeof(TabPlan)));
+    CKB(cudaMalloc((void**)&h->tab_build, 2 * sizeof(int)));
+    CKB(cudaMallocHost((void**)&h->tab_hint, sizeof(mcl_engine::TabHint)));
+    std::memset(h->tab_hint, 0, sizeof(mcl_engine::TabHint));
+    CKB(cudaEventCreateWithFlags(&h->ev_tab_hint, cudaEventDisableTiming));
     CKB(cudaMallocHost((void**)&h->host_counters, 64));
 #undef CKB
     h->stats.num_particles = h->n;
@@ -1215,6 +1350,7 @@ int mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime
     fill_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->weight[h->wcur], h->n, 1.0 / (double)h->n);
     CKL(h);
     h->pose_utime = h->parent_utime = utime;     // particle_filter.cpp:29-30
+    h->tab_ok = false;
     h->have_particles = true;
     h->have_scores = false;
     h->last_estimate.x = x; h->last_estimate.y = y; h->last_estimate.theta = theta; h->last_estimate.utime = utime;
@@ -1242,6 +1378,7 @@ int mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed)
     fill_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->weight[h->wcur], h->n, 1.0 / (double)h->n);
     CKL(h);
     h->pose_utime = h->parent_utime = utime;
+    h->tab_ok = false;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;
@@ -1267,6 +1404,7 @@ int mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n)
     CK(cudaStreamSynchronize(h->stream));
     h->pose_utime = aos[0].pose.utime;
     h->parent_utime = aos[0].parent_pose.utime;
+    h->tab_ok = false;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;

@@ -16,8 +16,7 @@ TRIG_ERR = 2.0e-6                   # kFastTrigErr
 def fma32(a, b, c):
     """float32 fused multiply-add: the product of two floats is exact in double; one rounding to double, one to float
     (double rounding can differ from a true FMA in ~2^-29 of the cases, far below what the budget resolves)."""
-    return (a.astype(np.float64) * np.float64(b) + np.float64(c)).astype(F) if np.ndim(b) == 0 else \
-        (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F)
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(F)
 
 
 class Plan:
@@ -176,3 +175,204 @@ def fast_pass(grid, plan, particle, ranges, thetas, ratios, min_range, fast_cell
     certain = val_ok | outside | (in_win & (odds == -1))
     v = np.where(odds > 0, 2 * odds, np.where(o1 > 0, o1, np.maximum(o2, 0)))
     return np.where(val_ok, v, 0), certain
+
+
+# ======================================================================================================================
+# Model of the TABLE pass (botlab_b200/csrc/mcl_table.cuh: table_plan_kernel, make_tab_base, tab_eval, the K/T build).
+# Same role as the model above: the design is checked on the CPU against the oracle's per-ray scores before (and
+# independently of) the CUDA code.  Keep in step with mcl_table.cuh.
+# ======================================================================================================================
+TAB_FIXED = 129
+TAB_B2 = F(0.59033447)
+TAB_S = F(0.84697730)
+TAB_C8 = F(1.27323954)
+# sector s steps (ux, uy): 0 (+1,0) 1 (+1,+1) 2 (0,+1) 3 (-1,+1) 4 (-1,0) 5 (-1,-1) 6 (0,-1) 7 (+1,-1)
+TAB_STEPS = [(1, 0), (1, 1), (0, 1), (-1, 1), (-1, 0), (-1, -1), (0, -1), (1, -1)]
+
+
+class TabPlan:
+    """table_plan_kernel for a cloud: window = bounding box of poses and parents +- (longest ray + 6 cells), clipped to
+    the grid plus a 2-cell margin; budget with the three grid roundings carried by k."""
+
+    def __init__(self, grid, cloud, ranges, thetas, ratios, min_range, smem_total=231424, smem_fixed=None):
+        cpm = float(F(grid.cells_per_meter))
+        valid = ranges > F(min_range)
+        nb = int(valid.sum())
+        self.ok = False
+        if nb < 1 or nb > 2047 or not np.isfinite(ranges[valid]).all() or not np.isfinite(thetas[valid]).all():
+            return
+        max_range = float(ranges[valid].max())
+        rc_max = max_range * cpm
+        rho_lo, rho_hi = float(ratios[valid].min()), float(ratios[valid].max())
+        rho_max = max(abs(rho_lo), abs(rho_hi))
+        max_abs_theta = float(np.abs(thetas[valid]).max())
+        if not (min_range * cpm >= 2.5 and max_abs_theta <= 6.3 and rho_lo >= -1.0 and rho_hi <= 2.0):
+            return
+        xs = np.concatenate([cloud["pose"]["x"], cloud["parent_pose"]["x"]])
+        ys = np.concatenate([cloud["pose"]["y"], cloud["parent_pose"]["y"]])
+        if not (np.isfinite(xs).all() and np.isfinite(ys).all()):
+            return
+        ox, oy = float(F(grid.origin_x)), float(F(grid.origin_y))
+        reach = rc_max + 6.0
+        cx0 = np.floor((float(xs.min()) - ox) * cpm - reach); cx1 = np.ceil((float(xs.max()) - ox) * cpm + reach)
+        cy0 = np.floor((float(ys.min()) - oy) * cpm - reach); cy1 = np.ceil((float(ys.max()) - oy) * cpm + reach)
+        x0, y0 = int(max(cx0, -2.0)), int(max(cy0, -2.0))
+        x1, y1 = int(min(cx1, grid.width + 1)), int(min(cy1, grid.height + 1))
+        if x1 < x0 + 2 or y1 < y0 + 2:
+            return
+        tw, th_ = x1 - x0 + 1, y1 - y0 + 1
+        pitch_k = (tw + 1) & ~1
+        if ((pitch_k >> 1) & 1) == 0:
+            pitch_k += 2
+        k_bytes = (pitch_k * 2 * th_ + 15) & ~15
+        if smem_fixed is None:
+            smem_fixed = (nb * 32 + 32 * 96 * 2 + 1024 * 4 + 15) & ~15
+        room = smem_total - smem_fixed - k_bytes - 64
+        we = max(tw, th_) + rc_max + 8.0
+        cm_ = max(x0 + tw, y0 + th_) + 1.0
+        if room < 8 * (TAB_FIXED + 256) or we >= 4096.0 or cm_ > 16000.0:
+            return
+        self.fb = fb = 12 if we < 1024 else (11 if we < 2048 else 10)
+        xm = cm_ / cpm + max(abs(ox), abs(oy))
+        shift = 64.0
+        ce = cm_ + rc_max
+        e_ref = cpm * U * xm + 2 * U * ce + 2 * U * rc_max + rc_max * (20 * U + 1.2e-7) + 1e-9
+        e_apx = (1 + 2 * rho_max) * U * shift + 2 * U * rc_max + rc_max * ((3.14159265358979 * (3 * rho_max + 1) + 9.5) * U + TRIG_ERR)
+        self.eps = eps = 1.25 * (e_ref + e_apx) + 1e-6
+        one = 1 << fb
+        self.k = k = int(np.ceil(one * eps + 1.5))
+        if k > one // 16:
+            return
+        self.ok = True
+        self.x0, self.y0, self.w, self.h = x0, y0, tw, th_
+        self.cap_entries = room // 8
+        self.mul = 1 << (32 - fb)
+        self.frac_thr = (2 * k) << (32 - fb)
+        magic_base = F(1.5 * 2.0 ** (23 - fb))
+        self.hi_bias = int(magic_base.view(np.uint32)) >> fb
+        self.magic = float(magic_base) + k / one
+        self.magic_f = F(self.magic)
+        assert float(self.magic_f) == self.magic
+        self.t3 = F(3.0 * (1.0 + 2.0 * eps) + 4.0 * U * rc_max + 1e-4)
+        self.rho_lo, self.rho_hi, self.rho_abs = F(rho_lo), F(rho_hi), F(rho_max * (1 + 1e-6))
+        self.max_shift, self.coord_hi = F(shift), F(cm_ - 1.0)
+        self.reach = F(rc_max * (1 + 1e-6) + 4.0)
+        self.grid_min_dim = F(min(grid.width, grid.height))
+        self.ang_room = F(9.5) - F(max_abs_theta)
+        self.wlo_x, self.whi_x = F(x0 + 1.5 + float(self.reach)), F(x0 + tw - 1.5 - float(self.reach))
+        self.wlo_y, self.whi_y = F(y0 + 1.5 + float(self.reach)), F(y0 + th_ - 1.5 - float(self.reach))
+        kappa = k / one + 1.0 / one
+        lcx, hcx, lcy, hcy = max(-x0, 1), tw - 1, max(-y0, 1), th_ - 1
+        empty = hcx <= lcx or hcy <= lcy
+        self.cmid_x, self.chalf_x = F(0.5 * (lcx + hcx) + self.magic), F(-1.0) if empty else F(0.5 * (hcx - lcx) - kappa)
+        self.cmid_y, self.chalf_y = F(0.5 * (lcy + hcy) + self.magic), F(-1.0) if empty else F(0.5 * (hcy - lcy) - kappa)
+        self.gmid_x, self.gmid_y = F(0.5 * (grid.width - 1) - x0 + self.magic), F(0.5 * (grid.height - 1) - y0 + self.magic)
+        self.ghalf_x, self.ghalf_y = F(0.5 * (grid.width + 3) + eps + kappa + 1e-3), F(0.5 * (grid.height + 3) + eps + kappa + 1e-3)
+        self.x2_lo_x, self.x2_lo_y = F(3.0 * eps + 2.0 * kappa + 1e-3 - x0), F(3.0 * eps + 2.0 * kappa + 1e-3 - y0)
+
+
+def build_score_table(grid, plan):
+    """The K tile (class per window cell) and the table T (8 sector scores per class) of score_table_kernel."""
+    cells = np.pad(grid.cells.astype(np.int64), 4)          # zero outside the grid, 4 cells of it
+
+    def raw(gx, gy):                                         # arrays of global cells, any value in [-4, W+3]
+        return cells[np.clip(gy + 4, 0, cells.shape[0] - 1), np.clip(gx + 4, 0, cells.shape[1] - 1)]
+
+    gy, gx = np.meshgrid(np.arange(plan.y0, plan.y0 + plan.h), np.arange(plan.x0, plan.x0 + plan.w), indexing="ij")
+    c = raw(gx, gy)
+    near5 = np.zeros(c.shape, bool)
+    for dy in range(-2, 3):
+        for dx in range(-2, 3):
+            near5 |= raw(gx + dx, gy + dy) > 0
+    nb = np.stack([raw(gx + ux, gy + uy) for ux, uy in TAB_STEPS])          # [8, h, w]
+    any8 = (nb > 0).any(axis=0)
+    K = np.zeros(c.shape, np.int64)
+    K[(c <= 0) & near5 & ~any8] = 1
+    K[c > 0] = 1 + c[c > 0]
+    nt = (c <= 0) & any8
+    idx = np.flatnonzero(nt.ravel())
+    T = np.zeros((TAB_FIXED + len(idx), 8), np.int64)
+    for i in range(2, TAB_FIXED):
+        T[i, :] = 2 * (i - 1)
+    K.ravel()[idx] = TAB_FIXED + np.arange(len(idx))
+    nbf = nb.reshape(8, -1)[:, idx]
+    for s in range(8):
+        o1, o2 = nbf[(s + 4) & 7], nbf[s]
+        T[TAB_FIXED:, s] = np.where(o1 > 0, o1, np.maximum(o2, 0))
+    return K, T, len(idx)
+
+
+def table_pass(grid, plan, K, T, particle, ranges, thetas, ratios, min_range, rng, interp=True, force_edge=None):
+    """One particle, all valid beams: (half_unit_scores, certain, edge).  rng perturbs the sine/cosine as in fast_pass."""
+    valid = ranges > F(min_range)
+    r, th, rho = ranges[valid], thetas[valid], ratios[valid].astype(F)
+    n = len(r)
+    gx, gy, cpm_d = np.float64(F(grid.origin_x)), np.float64(F(grid.origin_y)), np.float64(F(grid.cells_per_meter))
+    xa, ya, tha = (F(particle["pose"][k]) for k in ("x", "y", "theta"))
+    xb, yb, thb = (F(particle["parent_pose"][k]) for k in ("x", "y", "theta"))
+    if interp:
+        gsx, gsy = (np.float64(xb) - gx) * cpm_d, (np.float64(yb) - gy) * cpm_d
+        dsx, dsy = F(np.float64(F(xa - xb)) * cpm_d), F(np.float64(F(ya - yb)) * cpm_d)
+        d = np.float64(tha) - np.float64(thb)
+        if abs(d) > np.pi:
+            d += -2 * np.pi if d > 0 else 2 * np.pi
+        th0, dth = thb, F(d)
+    else:
+        gsx, gsy = (np.float64(xa) - gx) * cpm_d, (np.float64(ya) - gy) * cpm_d
+        dsx = dsy = dth = F(0)
+        th0 = tha
+    sxbm, sybm = F((gsx - plan.x0) + plan.magic), F((gsy - plan.y0) + plan.magic)
+    gxb, gyb = F(gsx), F(gsy)
+    one = np.ones(1, F)
+    xs = [fma32(dsx * one, plan.rho_lo, gxb * one)[0], fma32(dsx * one, plan.rho_hi, gxb * one)[0]]
+    ys = [fma32(dsy * one, plan.rho_lo, gyb * one)[0], fma32(dsy * one, plan.rho_hi, gyb * one)[0]]
+    xlo, xhi, ylo, yhi = min(xs), max(xs), min(ys), max(ys)
+    lo, hi = min(xlo, ylo), max(xhi, yhi)
+    ok = (lo >= 1.0 and hi <= plan.coord_hi and abs(dsx) <= plan.max_shift and abs(dsy) <= plan.max_shift
+          and abs(th0) <= F(3.15) and abs(dth) <= F(3.15)
+          and fma32(plan.rho_abs * one, abs(dth), abs(th0) * one)[0] <= plan.ang_room)
+    if not ok:
+        return np.zeros(n, np.int64), np.zeros(n, bool), -1
+    in_grid = lo >= plan.reach and hi <= plan.grid_min_dim - plan.reach
+    in_winp = xlo >= plan.wlo_x and xhi <= plan.whi_x and ylo >= plan.wlo_y and yhi <= plan.whi_y
+    edge = (0 if (in_grid and in_winp) else 1) if lo >= F(2.0) * plan.reach else 2
+    if force_edge is not None:
+        edge = max(edge, force_edge)
+    onev = np.ones(n, F)
+    sxm = fma32(dsx * onev, rho, sxbm * onev) if interp else sxbm * onev
+    sym = fma32(dsy * onev, rho, sybm * onev) if interp else sybm * onev
+    thr = fma32(dth * onev, rho, th0 * onev) if interp else th0 * onev
+    a = (thr - th).astype(F)
+    err = rng.uniform(-1.3e-6, 1.3e-6, (2, n))
+    s = (np.sin(a.astype(np.float64)) + err[0]).astype(F)
+    c = (np.cos(a.astype(np.float64)) + err[1]).astype(F)
+    rc = (r * F(grid.cells_per_meter)).astype(F)
+    bxf, byf = fma32(rc, c, sxm), fma32(rc, s, sym)
+    wx = bxf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul)
+    wy = byf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul)
+    fx, hx = (wx & np.uint64(0xffffffff)).astype(np.int64), (wx >> np.uint64(32)).astype(np.int64)
+    fy, hy = (wy & np.uint64(0xffffffff)).astype(np.int64), (wy >> np.uint64(32)).astype(np.int64)
+    cell_ok = np.minimum(fx, fy) >= plan.frac_thr
+    cx, cy = hx - plan.hi_bias, hy - plan.hi_bias               # window cells
+    in_win = np.ones(n, bool); outside = np.zeros(n, bool); x2_pos = np.ones(n, bool)
+    if edge >= 1:
+        in_win = (np.abs((bxf - plan.cmid_x).astype(F)) < plan.chalf_x) & (np.abs((byf - plan.cmid_y).astype(F)) < plan.chalf_y)
+        outside = (np.abs((bxf - plan.gmid_x).astype(F)) >= plan.ghalf_x) | (np.abs((byf - plan.gmid_y).astype(F)) >= plan.ghalf_y)
+        cx, cy = np.where(in_win, cx, 1), np.where(in_win, cy, 1)
+    if edge >= 2:
+        ex, ey = (bxf - plan.magic_f).astype(F), (byf - plan.magic_f).astype(F)
+        x2_pos = (fma32(rc, c, ex) >= plan.x2_lo_x) & (fma32(rc, s, ey) >= plan.x2_lo_y)
+    assert (cx >= 0).all() and (cx < plan.w).all() and (cy >= 0).all() and (cy < plan.h).all(), "table pass read outside its window"
+    Kv = K[cy, cx]
+    r8 = fma32(a, TAB_C8, F(25165824.0) * onev)
+    u8 = fma32(a, TAB_C8, -(r8 - F(25165824.0)).astype(F))
+    wq = fma32(u8, TAB_S, (r8 - F(12582912.0)).astype(F))
+    sector = wq.view(np.uint32).astype(np.int64) & 7
+    v = T[Kv, sector]
+    xq = np.float64(plan.t3) / (2.2360679 * rc.astype(np.float64) * (1.0 - 1e-6))
+    with np.errstate(invalid="ignore"):
+        d8 = np.where((xq >= 0.3) | ~(xq >= 0.0), 4.0, (np.arcsin(np.minimum(xq, 1.0)) + 2e-5) * 1.2732395447351628 * (1 + 1e-6))
+    d8 = d8.astype(F) + F(1e-6)
+    dir_ok = x2_pos & (np.abs((np.abs(u8) - TAB_B2).astype(F)) > d8)
+    val_ok = in_win & ((Kv == 0) | (cell_ok & ((Kv < TAB_FIXED) | dir_ok)))
+    return np.where(val_ok, v, 0), val_ok | outside, edge

@@ -100,3 +100,86 @@ def test_the_check_is_sensitive():
         want2 = np.rint(2.0 * port.ray_scores(pg, cloud[i], r, th, t)).astype(np.int64)
         wrong += int((certain & (v2 != want2)).sum())
     assert wrong > 0
+
+
+# ---- the table pass (mcl_table.cuh) ---------------------------------------------------------------------------------
+def make_interior_case(case):
+    """A tracking cloud well inside a large map: the table pass's EDGE = 0 variant (no window / grid tests per ray)."""
+    rng = np.random.default_rng(8000 + case)
+    grid = synth.make_map(900, seed=190 + case)
+    while True:
+        truth = synth.find_free_pose(grid, rng)
+        cx, cy = (truth[0] - grid.origin_x) / 0.05, (truth[1] - grid.origin_y) / 0.05
+        if 260 < cx < 640 and 260 < cy < 640:
+            break
+    r, th, t = synth.make_scan(grid, truth, num_beams=360, seed=case, max_range=4.0)
+    cloud = synth.make_particles(150, truth, seed=case, sigma_xy=0.10, sigma_theta=0.05, parent_utime=int(t[0]),
+                                 pose_utime=int(t[-1]))
+    return grid, cloud, r, th, t
+
+
+def _table_case(case, force_edge=None, interp=True, perturb=None):
+    grid, cloud, r, th, t = make_case(case) if case < 100 else make_interior_case(case)
+    t_b, t_a = int(cloud["parent_pose"]["utime"][0]), int(cloud["pose"]["utime"][0])
+    if interp:
+        ratios = (t - t_b).astype(np.float64) / float(t_a - t_b)
+    else:
+        ratios = np.ones(len(t))
+        cloud["parent_pose"]["utime"] = t_a
+    plan = cm.TabPlan(grid, cloud, r, th, ratios, MIN_RANGE)
+    if not plan.ok:
+        return None
+    if perturb:
+        perturb(plan)
+    K, T, entries = cm.build_score_table(grid, plan)
+    pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
+    rng = np.random.default_rng(case)
+    evals = certain_total = wrong = 0
+    edges = set()
+    for i in range(len(cloud)):
+        v2, certain, edge = cm.table_pass(grid, plan, K, T, cloud[i], r, th, ratios, MIN_RANGE, rng, interp=interp,
+                                          force_edge=force_edge)
+        want2 = np.rint(2.0 * port.ray_scores(pg, cloud[i], r, th, t)).astype(np.int64)
+        assert len(want2) == len(v2)
+        wrong += int((certain & (v2 != want2)).sum())
+        evals += len(v2)
+        certain_total += int(certain.sum())
+        edges.add(edge)
+    return wrong, certain_total, evals, edges, plan
+
+
+@pytest.mark.parametrize("case", range(8))
+@pytest.mark.parametrize("force_edge", [None, 2])
+def test_table_pass_certain_evaluations_equal_the_oracle(case, force_edge):
+    res = _table_case(case, force_edge)
+    if res is None:
+        pytest.skip("window does not fit the table pass's budget")
+    wrong, certain_total, evals, edges, plan = res
+    assert wrong == 0
+    assert plan.eps < 0.02
+    if force_edge is None and case % 3 != 2:
+        assert certain_total >= 0.5 * evals, (certain_total, evals, edges)
+
+
+@pytest.mark.parametrize("case", [100, 101, 102])
+@pytest.mark.parametrize("interp", [True, False])
+def test_table_pass_interior_cloud(case, interp):
+    res = _table_case(case, interp=interp)
+    assert res is not None
+    wrong, certain_total, evals, edges, plan = res
+    assert wrong == 0 and edges == {0}
+    assert certain_total >= 0.9 * evals, (certain_total, evals)
+
+
+def test_table_pass_equal_utime_variant():
+    res = _table_case(0, interp=False)
+    assert res is not None and res[0] == 0 and res[1] >= 0.5 * res[2]
+
+
+def test_table_check_is_sensitive():
+    """Negative control: without the cell band and the direction band the same comparison finds wrong scores."""
+    def blind(plan):
+        plan.frac_thr = 0
+        plan.t3 = np.float32(0.0)
+    res = _table_case(3, perturb=blind)
+    assert res is not None and res[0] > 0
