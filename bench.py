@@ -349,8 +349,9 @@ def run_engine(args):
             "gpu_launches": launches,
             "clocks": clock_info,
             "roofline": {"bound": "hbm",
-                         "kernel": ("score_fast_kernel + score_deferred_kernel (sensor stage)" if st["sensor_path"] == 2
-                                    else "score_kernel (sensor stage)"),
+                         "kernel": {3: "score_table_kernel (sensor stage)",
+                                    2: "score_fast_kernel + score_deferred_kernel (sensor stage)"}.get(
+                                        st["sensor_path"], "score_kernel (sensor stage)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(args.config, world, n),
                          "peak_kind": peak_kind,

@@ -504,7 +504,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
 {
     const long long local = h->hi - h->lo;
     const int lanes = h->params.lanes_per_particle;
-    const bool cand = h->params.sensor_path != 1 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
+    const bool cand = h->params.sensor_path == 0 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
                       local >= kTabMinParticles && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
                       std::isfinite(h->max_range) && !std::getenv("MCL_NO_TABLE");
     if (!cand) return 0;

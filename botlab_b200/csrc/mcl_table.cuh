@@ -15,14 +15,16 @@
 //                            doubled endpoint).  Entries 0..128 are the uniform classes (same byte in all 8 slots),
 //                            so one dependent LDS gives the score of every class.
 //
-// One evaluation is then: the float model of the endpoint in fixed point (an FFMA whose addend carries the magic number,
-// so the sum lands on the 2^-FB grid), cell + fraction split by one IMAD.WIDE per axis, K, the sector from the angle by
-// magic-number rounding (boundaries at +-atan(1/2) around each axis), T -- about half the issue slots of
-// score_beam_fast, with the compare/select work (the ALU pipe, the co-limiter there) cut to a third.
+// One evaluation is then: the float model of the endpoint in WINDOW-NORMALISED coordinates ((cell + kappa - 0.5) /
+// (w - 1.5), so one saturating FFMA both evaluates it and clamps it onto the window -- rays that leave a clipped window
+// land on its border cells, which are class 0 -- and NaNs become 0), +1.0 to make the mantissa linear, one IMAD.WIDE
+// per axis by (2w - 3) 2^8 that yields the cell in the high word and the 32-bit fraction in the low word, K, the sector
+// from the angle by magic-number rounding (boundaries at +-atan(1/2) around each axis), T -- about half the issue
+// slots of score_beam_fast, with the compare/select work (the ALU pipe, the co-limiter there) cut to a third.
 //
 // Certification (the score is only taken when it provably equals the reference's):
-//   * cell:   the fixed-point coordinate is further than kappa = k 2^-FB from an integer, kappa >= eps + the three grid
-//             roundings (TabPlan / table_plan_kernel has the budget);
+//   * cell:   the coordinate is further than kappa from an integer, kappa >= eps + the float roundings of the
+//             normalised coordinates (TabPlan / table_plan_kernel has the budget);
 //   * sector: the angle is further than d8 (per beam: asin(T3 / (sqrt5 rc)) + slack) from the octant boundaries, i.e.
 //             |2|px| - |py|| and |2|py| - |px|| exceed T3 = 3(1 + 2 eps) -- only needed for K >= 129;
 //   * K == 0 needs neither (mcl_kernels.cuh: derive_fast_map_kernel has the argument).
@@ -30,6 +32,12 @@
 // beam of the current 32-beam word, the warp compacts the set bits of its 32 lanes into a shared-memory queue and drains
 // it 32 entries at a time (poses travel by shuffle, results by shared-memory integer atomics), so there is no mask
 // array in HBM and no second launch.
+//
+// The window is the bounding box of the cloud +- the longest ray, clipped to the grid plus four cells: cells outside the
+// grid read 0 (occupancy_grid.cpp:65-70), so an endpoint beyond the grid's high edges is just another table lookup, and
+// four or more cells out everything is class 0.  Below zero the reference truncates toward zero instead of flooring (sensor_model.cpp:34-38 casts to int), so window cells
+// with a negative global coordinate are never certified (class 1 + a cell test) unless they are four or more cells out
+// (class 0: the truncated cell and its neighbours are all outside the grid).
 //
 // The window is planned ON THE DEVICE (table_plan_kernel, from bbox_kernel's box), so an update needs no host round
 // trip; when the window or the table does not fit, every evaluation takes the exact path (same results, slower) and
@@ -41,14 +49,16 @@ namespace mcl {
 
 constexpr int kTabThreads = 1024;            // one CTA per SM: one K/T copy per SM
 constexpr int kTabWarps = kTabThreads / 32;
-constexpr int kTabQueue = 96;                // per-warp queue of deferred (lane, beam) entries
+constexpr int kTabQueue = 192;               // per-warp queue of deferred (lane, beam) entries
 constexpr int kTabFixed = 129;               // T entries 0..128: the uniform classes
 constexpr int kTabMaxBeams = 2047;           // queue entries are (lane << 11) | beam
 constexpr float kTabB2 = 0.59033447f;        // 4/pi * atan(1/2): the octant boundaries in u8 units (see tab_sector)
 constexpr float kTabS = 0.84697730f;         // 0.5 / kTabB2: u8 * S rounds to 0 inside +-B2, to +-1 beyond
 constexpr float kTabC8 = 1.27323954f;        // 8 / (2 pi)
 
-struct __align__(16) TabBeam { float ratio, theta, rc, d8; };
+// per beam: interpolation ratio, beam angle, range in window-normalised units per axis (range * cells/m / (w - 1.5),
+// ... / (h - 1.5)); the sector band d8 lives in a second array (one more broadcast LDS)
+struct __align__(16) TabBeam { float ratio, theta, rcx, rcy; };
 
 // Written by table_plan_kernel, read by score_table_kernel (device memory; a copy travels to pinned host memory as the
 // host's hint for the next update).
@@ -58,21 +68,18 @@ struct TabPlan {
     int pitch_k;                 // K entries per row (2 bytes each); pitch_k / 2 is odd (rows spread over the banks)
     int cap_entries;             // T capacity, the fixed ones included
     unsigned off_k, off_t;       // byte offsets of K and T in dynamic shared memory
-    int frac_bits;               // FB
-    unsigned mul;                // 1 << (32 - FB): bits * mul = (cell + bias) : (fraction << (32 - FB))
-    unsigned frac_thr;           // (2k) << (32 - FB): fractions below it are within kappa of an integer
-    unsigned hi_bias;            // bits(1.5 * 2^(23-FB)) >> FB
-    double magic;                // 1.5 * 2^(23-FB) + k 2^-FB
-    float magic_f;
-    float eps, t3;
+    // normalised coordinate of a window-relative coordinate c:  n = (c + off) * inv_s,  off = kappa - 0.5,
+    // s = w - 1.5 (x) / h - 1.5 (y).  bits(1 + n) * mul = ((floor(c + kappa) + bias) << 32) | fraction(c + kappa) 2^32
+    double off, inv_sx, inv_sy;
+    unsigned mul_x, mul_y;       // (2w - 3) << 8, (2h - 3) << 8
+    unsigned bias_x, bias_y;     // 127 w - 191, 127 h - 191
+    unsigned frac_thr;           // ceil(2 kappa 2^32): fractions below it are within kappa of an integer
+    float eps, kappa, t3;
     // particle validity (as FastPlan)
-    float rho_lo, rho_hi, rho_abs, max_shift, coord_hi, reach, grid_min_dim, ang_room;
-    float wlo_x, whi_x, wlo_y, whi_y;     // GLOBAL robot coordinates whose rays stay interior to the window
-    // EDGE >= 1 tests on the biased fixed-point floats (constants carry the magic number)
-    float cmid_x, chalf_x, cmid_y, chalf_y;   // certain-interior box
-    float gmid_x, ghalf_x, gmid_y, ghalf_y;   // |e - gmid| >= ghalf: certainly two or more cells outside the grid
-    float x2_lo_x, x2_lo_y;                   // doubled endpoint certainly non-negative (window-relative, unbiased)
-    int safe_off;                // byte offset (from K) of window cell (1,1)
+    float rho_lo, rho_hi, rho_abs, max_shift, coord_hi, reach, ang_room;
+    float ulo_x, uhi_x, ulo_y, uhi_y;     // GLOBAL robot coordinates whose rays stay inside the cloud's bounding box +- reach
+    unsigned hmin_x, hmin_y;              // EDGE 2: (cell + bias) values at or above these have a global cell >= 0
+    float x2_lo_x, x2_lo_y;               // EDGE >= 1: normalised doubled endpoints at or above these are certainly >= 0
     int need_bytes;              // shared memory the window needs (K + fixed T + a minimum of entries)
     int reason;                  // why ok == 0 (diagnostic): 1 scan, 2 bbox, 3 window size, 4 eps, 5 disabled
 };
@@ -104,91 +111,79 @@ __global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
             !((double)in.min_range * cpm >= 2.5) || !(in.max_abs_theta <= 6.3f) || !(in.ratio_lo >= -1.0) ||
             !(in.ratio_hi <= 2.0)) { pl.reason = 1; break; }
         if (!(isfinite(mnx) && isfinite(mny) && isfinite(mxx) && isfinite(mxy)) || mnx > mxx || mny > mxy) { pl.reason = 2; break; }
-        // window = bounding box of poses and parents +- (longest ray + 3 cells), clipped to the grid plus a 2-cell
-        // zero margin (cells outside the grid read 0: occupancy_grid.cpp:65-70)
-        // (+6: every particle of the cloud then passes make_tab_base's interior test, whose reach carries 4 cells of
-        // margin plus 1.5 for the window's border)
+        // window = bounding box of poses and parents +- (longest ray + 6 cells), not clipped to the grid (cells outside
+        // read 0).  +6: every particle of the cloud then passes make_tab_base's interior test, whose reach carries
+        // 4 cells of margin plus 1.5 for the window's border.
         const double reach = Rc + 6.0;
         const double cx0 = floor(((double)mnx - (double)in.grid.origin_x) * cpm - reach);
         const double cy0 = floor(((double)mny - (double)in.grid.origin_y) * cpm - reach);
         const double cx1 = ceil(((double)mxx - (double)in.grid.origin_x) * cpm + reach);
         const double cy1 = ceil(((double)mxy - (double)in.grid.origin_y) * cpm + reach);
-        const long long x0 = (long long)fmax(cx0, -2.0), y0 = (long long)fmax(cy0, -2.0);
-        const long long x1 = (long long)fmin(cx1, (double)in.grid.width + 1), y1 = (long long)fmin(cy1, (double)in.grid.height + 1);
-        if (x1 < x0 + 2 || y1 < y0 + 2) { pl.reason = 3; break; }
+        if (!(fabs(cx0) < 1.0e6 && fabs(cy0) < 1.0e6 && cx1 - cx0 < 8192.0 && cy1 - cy0 < 8192.0)) { pl.reason = 3; break; }
+        const long long ux0 = (long long)cx0, uy0 = (long long)cy0, ux1 = (long long)cx1, uy1 = (long long)cy1;
+        // clipped to the grid plus four cells: everything beyond is class 0, and so are the clipped window's border cells,
+        // onto which the saturating coordinate arithmetic maps rays that leave it
+        const long long x0 = ux0 > -4 ? ux0 : -4, y0 = uy0 > -4 ? uy0 : -4;
+        const long long x1 = ux1 < in.grid.width + 3 ? ux1 : in.grid.width + 3, y1 = uy1 < in.grid.height + 3 ? uy1 : in.grid.height + 3;
         const long long tw = x1 - x0 + 1, th = y1 - y0 + 1;
+        if (tw < 8 || th < 8) { pl.reason = 3; break; }       // (a cloud whose rays cannot reach the grid)
         long long pitch_k = (tw + 1) & ~1ll;
         if (((pitch_k >> 1) & 1) == 0) pitch_k += 2;
         const long long k_bytes = (pitch_k * 2 * th + 15) & ~15ll;
         const long long room = (long long)in.smem_total - in.smem_fixed - k_bytes - 64;
         pl.need_bytes = (int)fmin(2.0e9, (double)(in.smem_fixed + k_bytes + 64 + 8 * (kTabFixed + 256)));
-        const double We = (double)(tw > th ? tw : th) + Rc + 8.0;       // magnitude of every coordinate the bits carry
-        if (room < 8 * (kTabFixed + 256) || We >= 4096.0 || (double)(x0 + tw > y0 + th ? x0 + tw : y0 + th) + 1.0 > 16000.0) {
-            pl.reason = 3; break;
-        }
-        const int fb = We < 1024.0 ? 12 : (We < 2048.0 ? 11 : 10);
+        if (room < 8 * (kTabFixed + 256)) { pl.reason = 3; break; }
         // error budget (cells).  Reference vs the real-valued model: as fast_plan (mcl_engine.cu).  Float model vs the
         // same: roundings of dS, rho and rc, the angle roundings and the measured SFU error; its coordinate roundings
-        // are the three grid roundings (sxbm, the ratio FFMA, the endpoint FFMA), half a step each, carried by k.
+        // (the normalised robot coordinate, the ratio FFMA, the endpoint FFMA, the +1.0) are below 2^-24 of the
+        // window's extent each.
         const double u = 5.9604644775390625e-08;
-        const double Cm = (double)(x0 + tw > y0 + th ? x0 + tw : y0 + th) + 1.0;
+        const double Cm = (double)(ux1 > uy1 ? ux1 : uy1) + 2.0;
+        if (Cm > 16000.0) { pl.reason = 3; break; }
         const double Xm = Cm / cpm + fmax(fabs((double)in.grid.origin_x), fabs((double)in.grid.origin_y));
         const double max_shift = 64.0;
         const double Ce = Cm + Rc;
         const double e_ref = cpm * u * Xm + 2.0 * u * Ce + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
-        const double e_apx = (1.0 + 2.0 * rho_max) * u * max_shift + 2.0 * u * Rc +
+        const double e_apx = 6.0 * u * (double)(tw > th ? tw : th) + (1.0 + 2.0 * rho_max) * u * max_shift + 3.0 * u * Rc +
                              Rc * ((3.14159265358979 * (3.0 * rho_max + 1.0) + 9.5) * u + (double)kFastTrigErr);
         const double eps = 1.25 * (e_ref + e_apx) + 1e-6;
-        const int one = 1 << fb;
-        const int k = (int)ceil((double)one * eps + 1.5);
-        if (k > one / 16) { pl.reason = 4; break; }
+        const double kappa = eps + 1e-5;
+        if (kappa > 1.0 / 16.0) { pl.reason = 4; break; }
         pl.ok = 1;
         pl.x0 = (int)x0; pl.y0 = (int)y0; pl.w = (int)tw; pl.h = (int)th; pl.pitch_k = (int)pitch_k;
         pl.cap_entries = (int)(room / 8);
         pl.off_k = (unsigned)in.smem_fixed;
         pl.off_t = (unsigned)(in.smem_fixed + k_bytes);
-        pl.frac_bits = fb;
-        pl.mul = 1u << (32 - fb);
-        pl.frac_thr = (unsigned)(2 * k) << (32 - fb);
-        const float magic_base = (float)(1.5 * (double)(1 << (23 - fb)));
-        pl.hi_bias = __float_as_uint(magic_base) >> fb;
-        pl.magic = (double)magic_base + (double)k / (double)one;
-        pl.magic_f = (float)pl.magic;                       // exact: a multiple of 2^-FB inside the binade
-        pl.eps = (float)eps;
+        pl.off = kappa - 0.5;
+        pl.inv_sx = 1.0 / ((double)tw - 1.5); pl.inv_sy = 1.0 / ((double)th - 1.5);
+        pl.mul_x = (unsigned)(2 * tw - 3) << 8; pl.mul_y = (unsigned)(2 * th - 3) << 8;
+        pl.bias_x = (unsigned)(127 * tw - 191); pl.bias_y = (unsigned)(127 * th - 191);
+        pl.frac_thr = (unsigned)ceil(2.0 * kappa * 4294967296.0);
+        pl.eps = (float)eps; pl.kappa = (float)kappa;
         pl.t3 = (float)(3.0 * (1.0 + 2.0 * eps) + 4.0 * u * Rc + 1e-4);
         pl.rho_lo = (float)in.ratio_lo; pl.rho_hi = (float)in.ratio_hi; pl.rho_abs = (float)(rho_max * (1.0 + 1e-6));
         pl.max_shift = (float)max_shift;
         pl.coord_hi = (float)(Cm - 1.0);
         pl.reach = (float)(Rc * (1.0 + 1e-6) + 4.0);
-        pl.grid_min_dim = (float)(in.grid.width < in.grid.height ? in.grid.width : in.grid.height);
         pl.ang_room = 9.5f - in.max_abs_theta;             // kFastTrigErr is measured for |angle| <= 9.5
-        pl.wlo_x = (float)((double)x0 + 1.5 + (double)pl.reach); pl.whi_x = (float)((double)(x0 + tw) - 1.5 - (double)pl.reach);
-        pl.wlo_y = (float)((double)y0 + 1.5 + (double)pl.reach); pl.whi_y = (float)((double)(y0 + th) - 1.5 - (double)pl.reach);
-        // certain-interior cells [lc, hc): one cell inside the window and inside the grid (global cell >= 0: there the
-        // reference's truncation is a floor); the cell comes from bits that carry the +k offset: shrink by kappa
-        const double kappa = (double)k / (double)one + 1.0 / (double)one;
-        const long long lcx = (-x0 > 1 ? -x0 : 1), hcx = tw - 1, lcy = (-y0 > 1 ? -y0 : 1), hcy = th - 1;
-        const bool empty = hcx <= lcx || hcy <= lcy;
-        pl.cmid_x = (float)(0.5 * (double)(lcx + hcx) + pl.magic); pl.chalf_x = empty ? -1.0f : (float)(0.5 * (double)(hcx - lcx) - kappa);
-        pl.cmid_y = (float)(0.5 * (double)(lcy + hcy) + pl.magic); pl.chalf_y = empty ? -1.0f : (float)(0.5 * (double)(hcy - lcy) - kappa);
-        pl.gmid_x = (float)(0.5 * (double)(in.grid.width - 1) - (double)x0 + pl.magic);
-        pl.gmid_y = (float)(0.5 * (double)(in.grid.height - 1) - (double)y0 + pl.magic);
-        pl.ghalf_x = (float)(0.5 * (double)(in.grid.width + 3) + eps + kappa + 1e-3);
-        pl.ghalf_y = (float)(0.5 * (double)(in.grid.height + 3) + eps + kappa + 1e-3);
-        pl.x2_lo_x = (float)(3.0 * eps + 2.0 * kappa + 1e-3 - (double)x0);
-        pl.x2_lo_y = (float)(3.0 * eps + 2.0 * kappa + 1e-3 - (double)y0);
-        pl.safe_off = (int)(2 * (pitch_k + 1));
+        pl.ulo_x = (float)((double)ux0 + 1.5 + (double)pl.reach); pl.uhi_x = (float)((double)(ux1 + 1) - 1.5 - (double)pl.reach);
+        pl.ulo_y = (float)((double)uy0 + 1.5 + (double)pl.reach); pl.uhi_y = (float)((double)(uy1 + 1) - 1.5 - (double)pl.reach);
+        pl.hmin_x = (unsigned)((long long)pl.bias_x - x0);
+        pl.hmin_y = (unsigned)((long long)pl.bias_y - y0);
+        const double x2_min = 3.0 * eps + 2.0 * kappa + 1e-3;         // global coordinate the doubled endpoint must exceed
+        pl.x2_lo_x = (float)((x2_min - (double)x0 + pl.off) * pl.inv_sx * (1.0 + 1e-6) + 1e-7);
+        pl.x2_lo_y = (float)((x2_min - (double)y0 + pl.off) * pl.inv_sy * (1.0 + 1e-6) + 1e-7);
     } while (false);
     *out = pl;
 }
 
-// Per-particle constants of the table pass: robot coordinate at rho = 0 in window-relative cells WITH the magic number
-// added (one rounding to the 2^-FB grid), its change over rho = 0..1, heading likewise.
+// Per-particle constants of the table pass: robot coordinate at rho = 0 in window-normalised units, its change over
+// rho = 0..1, heading likewise.
 struct TabBase {
-    float sxbm, sybm, thb, dsx, dsy, dth;
+    float sxn, syn, thb, dsxn, dsyn, dth;
     bool ok;
-    int edge;       // 0: no endpoint leaves the window's interior or comes within 2 cells of the grid's edge;
-                    // 1: they may; 2: the doubled endpoint may also have a negative coordinate
+    int edge;       // 0: neither endpoints nor doubled endpoints can have a negative global coordinate;
+                    // 1: doubled endpoints may; 2: endpoints may too
 };
 
 template <bool INTERP>
@@ -196,74 +191,82 @@ __device__ __forceinline__ TabBase make_tab_base(float xa, float ya, float tha, 
                                                  double gy, double cpm_d, const TabPlan& pl)
 {
     TabBase f;
-    double gsx, gsy;
+    double gsx, gsy, ddx = 0.0, ddy = 0.0;      // robot cell coordinate (global, double) and its change over the sweep
     if (INTERP) {
         gsx = __dmul_rn(__dsub_rn((double)xb, gx), cpm_d);
         gsy = __dmul_rn(__dsub_rn((double)yb, gy), cpm_d);
         f.thb = thb;
-        f.dsx = (float)__dmul_rn((double)__fsub_rn(xa, xb), cpm_d);     // the reference's float difference (interpolation.hpp:39)
-        f.dsy = (float)__dmul_rn((double)__fsub_rn(ya, yb), cpm_d);
+        ddx = __dmul_rn((double)__fsub_rn(xa, xb), cpm_d);              // the reference's float difference (interpolation.hpp:39)
+        ddy = __dmul_rn((double)__fsub_rn(ya, yb), cpm_d);
         f.dth = (float)fold_pi(__dsub_rn((double)tha, (double)thb));    // angle_diff (:41)
     } else {
         gsx = __dmul_rn(__dsub_rn((double)xa, gx), cpm_d);
         gsy = __dmul_rn(__dsub_rn((double)ya, gy), cpm_d);
         f.thb = tha;
-        f.dsx = 0.0f; f.dsy = 0.0f; f.dth = 0.0f;
+        f.dth = 0.0f;
     }
-    f.sxbm = (float)__dadd_rn(__dsub_rn(gsx, (double)pl.x0), pl.magic);
-    f.sybm = (float)__dadd_rn(__dsub_rn(gsy, (double)pl.y0), pl.magic);
-    const float gxb = (float)gsx, gyb = (float)gsy;
-    const float xs0 = __fmaf_rn(f.dsx, pl.rho_lo, gxb), xs1 = __fmaf_rn(f.dsx, pl.rho_hi, gxb);
-    const float ys0 = __fmaf_rn(f.dsy, pl.rho_lo, gyb), ys1 = __fmaf_rn(f.dsy, pl.rho_hi, gyb);
+    f.sxn = (float)__dmul_rn(__dadd_rn(__dsub_rn(gsx, (double)pl.x0), pl.off), pl.inv_sx);
+    f.syn = (float)__dmul_rn(__dadd_rn(__dsub_rn(gsy, (double)pl.y0), pl.off), pl.inv_sy);
+    f.dsxn = (float)__dmul_rn(ddx, pl.inv_sx);
+    f.dsyn = (float)__dmul_rn(ddy, pl.inv_sy);
+    const float gxb = (float)gsx, gyb = (float)gsy, dsx = (float)ddx, dsy = (float)ddy;
+    const float xs0 = __fmaf_rn(dsx, pl.rho_lo, gxb), xs1 = __fmaf_rn(dsx, pl.rho_hi, gxb);
+    const float ys0 = __fmaf_rn(dsy, pl.rho_lo, gyb), ys1 = __fmaf_rn(dsy, pl.rho_hi, gyb);
     const float xlo = fminf(xs0, xs1), xhi = fmaxf(xs0, xs1), ylo = fminf(ys0, ys1), yhi = fmaxf(ys0, ys1);
     const float lo = fminf(xlo, ylo), hi = fmaxf(xhi, yhi);
+    // every ray of the particle must end inside the cloud's bounding box +- reach (always true for interpolation ratios
+    // in [0, 1]; extrapolating ratios can leave it): beyond it the window's border need not be class 0
     // (NaN anywhere: the comparisons fail and the particle is left to the exact path)
-    f.ok = lo >= 1.0f && hi <= pl.coord_hi && fabsf(f.dsx) <= pl.max_shift && fabsf(f.dsy) <= pl.max_shift &&
-           fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f && __fmaf_rn(pl.rho_abs, fabsf(f.dth), fabsf(f.thb)) <= pl.ang_room;
-    const bool in_grid = lo >= pl.reach && hi <= pl.grid_min_dim - pl.reach;
-    const bool in_win = xlo >= pl.wlo_x && xhi <= pl.whi_x && ylo >= pl.wlo_y && yhi <= pl.whi_y;
-    const bool x2_pos = lo >= 2.0f * pl.reach;
-    f.edge = x2_pos ? ((in_grid && in_win) ? 0 : 1) : 2;
+    const bool in_uwin = xlo >= pl.ulo_x && xhi <= pl.uhi_x && ylo >= pl.ulo_y && yhi <= pl.uhi_y;
+    f.ok = lo >= 1.0f && hi <= pl.coord_hi && fabsf(dsx) <= pl.max_shift && fabsf(dsy) <= pl.max_shift &&
+           fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f &&
+           __fmaf_rn(pl.rho_abs, fabsf(f.dth), fabsf(f.thb)) <= pl.ang_room && in_uwin;
+    f.edge = lo >= 2.0f * pl.reach ? 0 : (lo >= pl.reach ? 1 : 2);
     return f;
 }
 
 // Hot-loop constants of one CTA (registers).
 struct TabConst {
-    unsigned mul, frac_thr;
+    unsigned mul_x, mul_y, frac_thr;
     unsigned pitch2;        // bytes per K row
     unsigned kbase;         // shared address of K minus the bias of both axes
     unsigned k0;            // shared address of T / 8: the K tile stores class + k0
+    unsigned k129;          // k0 + kTabFixed
 };
 
-// One certified evaluation of the table pass.  Returns true when certain; add = its score in half units (else 0).
-template <bool INTERP, bool COUNT, int EDGE>
-__device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, const TabConst& tc, const TabPlan& pl,
-                                         unsigned ksafe, int& add, int& gathers)
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
 {
-    const float sxm = INTERP ? __fmaf_rn(p.dsx, b.ratio, p.sxbm) : p.sxbm;
-    const float sym = INTERP ? __fmaf_rn(p.dsy, b.ratio, p.sybm) : p.sybm;
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));     // clamps to [0, 1]; NaN -> +0
+    return r;
+}
+
+// One certified evaluation of the table pass.  Returns true when certain; add = its score in half units (else 0).
+// EDGE (warp-uniform, from TabBase::edge): 1 adds the test that the doubled endpoint has no negative coordinate (the
+// sector is not certified otherwise), 2 also the test that the endpoint's global cell is >= 0.
+template <bool INTERP, bool COUNT, int EDGE>
+__device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, float d8, const TabConst& tc,
+                                         const TabPlan& pl, int& add, int& gathers)
+{
+    const float sxn = INTERP ? __fmaf_rn(p.dsxn, b.ratio, p.sxn) : p.sxn;
+    const float syn = INTERP ? __fmaf_rn(p.dsyn, b.ratio, p.syn) : p.syn;
     const float thr = INTERP ? __fmaf_rn(p.dth, b.ratio, p.thb) : p.thb;
     const float a = __fsub_rn(thr, b.theta);
     const float s = __sinf(a), c = __cosf(a);
-    const float bxf = __fmaf_rn(b.rc, c, sxm), byf = __fmaf_rn(b.rc, s, sym);      // on the 2^-FB grid
-    // bits * 2^(32-FB): high word = cell + bias, low word = fraction << (32 - FB)
+    // normalised endpoint, clamped onto the window; 1 + n has a linear mantissa
+    const float nx = fma_sat(b.rcx, c, sxn), ny = fma_sat(b.rcy, s, syn);
+    const float bxf = __fadd_rn(nx, 1.0f), byf = __fadd_rn(ny, 1.0f);
+    // bits * (2w - 3) 2^8: high word = cell + bias, low word = fraction * 2^32 (both of coordinate + kappa)
     unsigned fx, hx, fy, hy, kaddr;
-    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(fx), "=r"(hx) : "r"(__float_as_uint(bxf)), "r"(tc.mul));
-    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(fy), "=r"(hy) : "r"(__float_as_uint(byf)), "r"(tc.mul));
-    const bool cell_ok = min(fx, fy) >= tc.frac_thr;
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(fx), "=r"(hx) : "r"(__float_as_uint(bxf)), "r"(tc.mul_x));
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(fy), "=r"(hy) : "r"(__float_as_uint(byf)), "r"(tc.mul_y));
+    bool cell_ok = min(fx, fy) >= tc.frac_thr;
+    if (EDGE >= 2) cell_ok = cell_ok & (hx >= pl.hmin_x) & (hy >= pl.hmin_y);       // global cell >= 0 on both axes
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(kaddr) : "r"(hy), "r"(tc.pitch2), "r"(tc.kbase));
     asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(kaddr) : "r"(hx), "r"(kaddr));
-    bool in_win = true, outside = false, x2_pos = true;
-    if (EDGE >= 1) {
-        in_win = (fabsf(__fsub_rn(bxf, pl.cmid_x)) < pl.chalf_x) & (fabsf(__fsub_rn(byf, pl.cmid_y)) < pl.chalf_y);
-        outside = (fabsf(__fsub_rn(bxf, pl.gmid_x)) >= pl.ghalf_x) | (fabsf(__fsub_rn(byf, pl.gmid_y)) >= pl.ghalf_y);
-        kaddr = in_win ? kaddr : ksafe;
-    }
-    if (EDGE >= 2) {
-        // the doubled endpoint must not have a negative coordinate (the reference truncates toward zero there)
-        const float ex = __fsub_rn(bxf, pl.magic_f), ey = __fsub_rn(byf, pl.magic_f);
-        x2_pos = (__fmaf_rn(b.rc, c, ex) >= pl.x2_lo_x) & (__fmaf_rn(b.rc, s, ey) >= pl.x2_lo_y);
-    }
+    bool x2_pos = true;
+    if (EDGE >= 1)      // the doubled endpoint must not have a negative coordinate (the reference truncates toward zero there)
+        x2_pos = (__fmaf_rn(b.rcx, c, nx) >= pl.x2_lo_x) & (__fmaf_rn(b.rcy, s, ny) >= pl.x2_lo_y);
     unsigned K;
     asm("ld.shared.u16 %0, [%1];" : "=r"(K) : "r"(kaddr));
     // sector: u8 = 8t - 2 round(4t) in [-1, 1] (t = a / 2pi) is the offset from the nearest axis, +-1 = 45 degrees;
@@ -275,11 +278,10 @@ __device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, con
     unsigned v, taddr;
     asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(taddr) : "r"(K), "r"(__float_as_uint(wq) & 7u));
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(taddr));
-    const bool dir_ok = x2_pos & (fabsf(__fsub_rn(fabsf(u8), kTabB2)) > b.d8);
-    const bool val_ok = in_win & ((K == tc.k0) | (cell_ok & ((K < tc.k0 + (unsigned)kTabFixed) | dir_ok)));
-    add = val_ok ? (int)v : 0;
-    const bool certain = val_ok | outside;
-    if (COUNT) gathers += certain ? ((K - tc.k0 - 2u < 127u) & !outside ? 1 : 3) : 0;
+    const bool dir_ok = x2_pos & (fabsf(__fsub_rn(fabsf(u8), kTabB2)) > d8);
+    const bool certain = (K == tc.k0) | (cell_ok & ((K < tc.k129) | dir_ok));
+    add = certain ? (int)v : 0;
+    if (COUNT) gathers += certain ? (K - tc.k0 - 2u < 127u ? 1 : 3) : 0;
     return certain;
 }
 
@@ -303,10 +305,26 @@ struct TabArgs {
 struct TabCold {
     DevGrid grid;
     const Beam* sbeams;
+    const uint16_t* ktile;      // class tile (null: not built -- read the mirror)
+    int x0, y0, w, h, pitch_k;
+    unsigned k0;
     unsigned long long deferred, gathers;
 };
 
-// Exact evaluation of one queue entry per lane (the literal restatement against the L2-resident mirror).
+// Cell value as the score sees it: the log-odds where positive, else 0 (sensor_model.cpp:41-57 only ever tests
+// "> 0").  Inside the window the class tile has it (classes 2..128 = occupied, log-odds class - 1); outside, the mirror.
+__device__ __forceinline__ int tab_cell_value(const TabCold* c, int gx, int gy)
+{
+    const int tx = (int)((unsigned)gx - (unsigned)c->x0), ty = (int)((unsigned)gy - (unsigned)c->y0);
+    if (c->ktile && (unsigned)tx < (unsigned)c->w && (unsigned)ty < (unsigned)c->h) {
+        const unsigned cls = (unsigned)c->ktile[ty * c->pitch_k + tx] - c->k0;
+        return (cls - 2u < 127u) ? (int)cls - 1 : 0;
+    }
+    return max(grid_read(c->grid, gx, gy), 0);
+}
+
+// Exact evaluation of one queue entry per lane: the literal restatement (exact_endpoint + the integer rules of
+// sensor_model.cpp:41-86 with x86 conversion semantics), cell values from the class tile.
 template <bool INTERP, bool COUNT>
 __device__ __noinline__ void tab_drain_round(unsigned entry, bool active, float xa, float ya, float tha, float xb,
                                              float yb, float thb, TabCold* cold, int* wacc)
@@ -321,12 +339,24 @@ __device__ __noinline__ void tab_drain_round(unsigned entry, bool active, float 
         gc.cpm = cold->grid.cells_per_meter; gc.cpm_d = (double)cold->grid.cells_per_meter;
         gc.trig.hpi_inv = gs_k[0]; gc.trig.hpi = gs_k[1]; gc.trig.s1 = gs_k[2]; gc.trig.s2 = gs_k[3]; gc.trig.s3 = gs_k[4];
         gc.trig.c0 = gs_k[5]; gc.trig.c1 = gs_k[6]; gc.trig.c2 = gs_k[7]; gc.trig.c3 = gs_k[8]; gc.trig.c4 = gs_k[9];
-        Window win;
-        win.base = cold->grid.cells; win.x0 = 0; win.y0 = 0; win.w = cold->grid.width; win.h = cold->grid.height;
-        win.pitch = cold->grid.pitch;
         const RayBase rb = make_ray_base(pxa, pya, ptha, pxb, pyb, pthb);
-        int g = 0;
-        const int v = score_beam<INTERP, false, COUNT>(rb, cold->sbeams[j], gc, win, cold->grid, g);
+        float sx, sy, px, py, e1x, e1y;
+        exact_endpoint<INTERP>(rb, cold->sbeams[j], gc, sx, sy, px, py, e1x, e1y);
+        const int ex = f2i_x86(e1x), ey = f2i_x86(e1y);                                   // sensor_model.cpp:34-35
+        int v, g = 1;
+        const int odds = tab_cell_value(cold, ex, ey);                                    // :41
+        if (odds > 0) {
+            v = 2 * odds;
+        } else {
+            const int xx = f2i_x86(__fadd_rn(__fmul_rn(2.0f, px), sx));                   // :37-38
+            const int xy = f2i_x86(__fadd_rn(__fmul_rn(2.0f, py), sy));
+            int ax, ay, bx, by;
+            bresenham_step(ex, ey, f2i_x86(sx), f2i_x86(sy), ax, ay);                     // :48
+            bresenham_step(ex, ey, xx, xy, bx, by);                                       // :49
+            const int o1 = tab_cell_value(cold, ax, ay), o2 = tab_cell_value(cold, bx, by);
+            v = o1 > 0 ? o1 : o2;
+            g = 3;
+        }
         if (v) atomicAdd(wacc + src, v);
         if (COUNT) atomicAdd(&cold->gathers, (unsigned long long)g);
     }
@@ -334,14 +364,15 @@ __device__ __noinline__ void tab_drain_round(unsigned entry, bool active, float 
     if ((threadIdx.x & 31) == 0) atomicAdd(&cold->deferred, (unsigned long long)cnt);
 }
 
-// Hands the set bits of the warp's 32 mask words (beams 32w .. 32w+31 of each lane's particle) to the exact path.
-// Returns the new queue length (< 32).
+// Hands the set bits of the warp's mask words (m0..m3: beams 32 wbase .. 32 wbase + 127 of each lane's particle) to the
+// exact path.  Returns the new queue length (< 32).
 template <bool INTERP, bool COUNT>
-__device__ __noinline__ int tab_defer_word(unsigned m, int w, int qn, float xa, float ya, float tha, float xb, float yb,
-                                           float thb, TabCold* cold, uint16_t* q, int* wacc)
+__device__ __noinline__ int tab_defer_words(unsigned m0, unsigned m1, unsigned m2, unsigned m3, int wbase, int qn,
+                                            float xa, float ya, float tha, float xb, float yb, float thb, TabCold* cold,
+                                            uint16_t* q, int* wacc)
 {
     const int lane = threadIdx.x & 31;
-    const int c = __popc(m);
+    const int c = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -351,10 +382,16 @@ __device__ __noinline__ int tab_defer_word(unsigned m, int w, int qn, float xa, 
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (qn + total <= kTabQueue) {
         int pos = qn + incl - c;
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            q[pos++] = (uint16_t)((lane << 11) | (w * 32 + k));
+        unsigned m = m0;
+        int beam0 = wbase * 32;
+        for (int part = 0; part < 4; ++part) {
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                q[pos++] = (uint16_t)((lane << 11) | (beam0 + k));
+            }
+            m = part == 0 ? m1 : (part == 1 ? m2 : m3);
+            beam0 += 32;
         }
         qn += total;
         __syncwarp();
@@ -364,13 +401,19 @@ __device__ __noinline__ int tab_defer_word(unsigned m, int w, int qn, float xa, 
         }
         __syncwarp();
     } else {
-        // burst (a lane outside the table pass's domain, or a scan it cannot certify): every lane with bits left
-        // evaluates its own next beam; the queue keeps what it held
-        while (__any_sync(0xffffffffu, m != 0u)) {
-            const bool has = m != 0u;
-            const int k = has ? __ffs(m) - 1 : 0;
-            if (has) m &= m - 1;
-            tab_drain_round<INTERP, COUNT>((unsigned)((lane << 11) | (w * 32 + k)), has, xa, ya, tha, xb, yb, thb, cold, wacc);
+        // burst (lanes outside the table pass's domain): every lane with bits left evaluates its own next beam; the
+        // queue keeps what it held
+        unsigned m = m0;
+        int beam0 = wbase * 32;
+        for (int part = 0; part < 4; ++part) {
+            while (__any_sync(0xffffffffu, m != 0u)) {
+                const bool has = m != 0u;
+                const int k = has ? __ffs(m) - 1 : 0;
+                if (has) m &= m - 1;
+                tab_drain_round<INTERP, COUNT>((unsigned)((lane << 11) | (beam0 + k)), has, xa, ya, tha, xb, yb, thb, cold, wacc);
+            }
+            m = part == 0 ? m1 : (part == 1 ? m2 : m3);
+            beam0 += 32;
         }
     }
     return qn;
@@ -390,14 +433,15 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = a.num_beams;
+    const int nb4 = (nb + 3) & ~3;
     TabBeam* sfast = reinterpret_cast<TabBeam*>(smem);
-    Beam* sbeams = reinterpret_cast<Beam*>(smem + (size_t)nb * sizeof(TabBeam));
-    uint16_t* squeue = reinterpret_cast<uint16_t*>(smem + (size_t)nb * (sizeof(TabBeam) + sizeof(Beam)));
+    Beam* sbeams = reinterpret_cast<Beam*>(smem + (size_t)nb4 * sizeof(TabBeam));
+    float* sd8 = reinterpret_cast<float*>(smem + (size_t)nb4 * (sizeof(TabBeam) + sizeof(Beam)));
+    uint16_t* squeue = reinterpret_cast<uint16_t*>(sd8 + nb4);
     int* swacc = reinterpret_cast<int*>(squeue + kTabWarps * kTabQueue);
 
     if (tid == 0) {
         s_plan = *a.plan;
-        s_cold.grid = a.grid; s_cold.sbeams = sbeams; s_cold.deferred = 0ull; s_cold.gathers = 0ull;
         s_count = 0; s_overflow = 0;
     }
     swacc[tid] = 0;
@@ -409,11 +453,13 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
         const Beam b = a.beams[i];
         sbeams[i] = b;
         TabBeam f;
-        f.ratio = (float)b.ratio; f.theta = b.theta; f.rc = __fmul_rn(b.range, cpm);
+        const float rc = __fmul_rn(b.range, cpm);
+        f.ratio = (float)b.ratio; f.theta = b.theta;
+        f.rcx = (float)((double)rc * pl.inv_sx); f.rcy = (float)((double)rc * pl.inv_sy);
         // |2|px| - |py|| = sqrt5 rc |sin(angle to the octant boundary)| must exceed T3: angular band, in u8 units
-        const double xq = (double)pl.t3 / (2.2360679 * (double)f.rc * (1.0 - 1e-6));
+        const double xq = (double)pl.t3 / (2.2360679 * (double)rc * (1.0 - 1e-6));
         const double d8 = (xq >= 0.3 || !(xq >= 0.0)) ? 4.0 : (asin(xq) + 2e-5) * 1.2732395447351628 * (1.0 + 1e-6);
-        f.d8 = (float)d8 + 1e-6f;
+        sd8[i] = (float)d8 + 1e-6f;
         sfast[i] = f;
     }
 
@@ -433,43 +479,49 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
         for (int i = tid; i < total; i += kTabThreads) {
             const int ty = i / pl.w, tx = i - ty * pl.w;
             const int gxc = pl.x0 + tx, gyc = pl.y0 + ty;
-            int f;
-            if ((unsigned)gxc < (unsigned)W && (unsigned)gyc < (unsigned)H) {
-                f = (int)__ldg(a.fast_cells + (size_t)gyc * gp + gxc);
-            } else {        // the window's zero margin: the cell reads 0; is anything positive within two cells?
-                bool any = false;
-                for (int dy = -2; dy <= 2; ++dy)
-                    for (int dx = -2; dx <= 2; ++dx) any = any || rawc(gxc + dx, gyc + dy) > 0;
-                f = any ? 0 : -1;
-            }
             unsigned K;
-            if (f < 0) K = 0u;
-            else if (f > 0) K = 1u + (unsigned)f;
-            else {
-                // sector s steps (ux, uy): 0 (+1,0) 1 (+1,+1) 2 (0,+1) 3 (-1,+1) 4 (-1,0) 5 (-1,-1) 6 (0,-1) 7 (+1,-1)
-                int n[8];
-                n[0] = rawc(gxc + 1, gyc);     n[1] = rawc(gxc + 1, gyc + 1); n[2] = rawc(gxc, gyc + 1);
-                n[3] = rawc(gxc - 1, gyc + 1); n[4] = rawc(gxc - 1, gyc);     n[5] = rawc(gxc - 1, gyc - 1);
-                n[6] = rawc(gxc, gyc - 1);     n[7] = rawc(gxc + 1, gyc - 1);
-                int mx = 0;
-#pragma unroll
-                for (int sct = 0; sct < 8; ++sct) mx = max(mx, n[sct]);
-                if (mx <= 0) K = 1u;
+            if (gxc <= -4 || gyc <= -4 || gxc >= W + 3 || gyc >= H + 3) {
+                K = 0u;        // the reference's (truncated) endpoint cell and its neighbours are all outside the grid
+            } else if (gxc < 0 || gyc < 0) {
+                K = 1u;        // truncation toward zero differs from the floor here: never certified (tab_eval, EDGE 2)
+            } else {
+                int f;
+                if (gxc < W && gyc < H) {
+                    f = (int)__ldg(a.fast_cells + (size_t)gyc * gp + gxc);
+                } else {        // beyond the high edges: the cell reads 0; is anything positive within two cells?
+                    bool any = false;
+                    for (int dy = -2; dy <= 2; ++dy)
+                        for (int dx = -2; dx <= 2; ++dx) any = any || rawc(gxc + dx, gyc + dy) > 0;
+                    f = any ? 0 : -1;
+                }
+                if (f < 0) K = 0u;
+                else if (f > 0) K = 1u + (unsigned)f;
                 else {
-                    const int e = kTabFixed + atomicAdd(&s_count, 1);
-                    if (e < pl.cap_entries) {
-                        unsigned long long pack = 0ull;
+                    // sector s steps (ux, uy): 0 (+1,0) 1 (+1,+1) 2 (0,+1) 3 (-1,+1) 4 (-1,0) 5 (-1,-1) 6 (0,-1) 7 (+1,-1)
+                    int n[8];
+                    n[0] = rawc(gxc + 1, gyc);     n[1] = rawc(gxc + 1, gyc + 1); n[2] = rawc(gxc, gyc + 1);
+                    n[3] = rawc(gxc - 1, gyc + 1); n[4] = rawc(gxc - 1, gyc);     n[5] = rawc(gxc - 1, gyc - 1);
+                    n[6] = rawc(gxc, gyc - 1);     n[7] = rawc(gxc + 1, gyc - 1);
+                    int mx = 0;
 #pragma unroll
-                        for (int sct = 0; sct < 8; ++sct) {
-                            const int o1 = n[(sct + 4) & 7], o2 = n[sct];      // sensor_model.cpp:48-57
-                            const int v = o1 > 0 ? o1 : max(o2, 0);
-                            pack |= (unsigned long long)v << (8 * sct);
+                    for (int sct = 0; sct < 8; ++sct) mx = max(mx, n[sct]);
+                    if (mx <= 0) K = 1u;
+                    else {
+                        const int e = kTabFixed + atomicAdd(&s_count, 1);
+                        if (e < pl.cap_entries) {
+                            unsigned long long pack = 0ull;
+#pragma unroll
+                            for (int sct = 0; sct < 8; ++sct) {
+                                const int o1 = n[(sct + 4) & 7], o2 = n[sct];      // sensor_model.cpp:48-57
+                                const int v = o1 > 0 ? o1 : max(o2, 0);
+                                pack |= (unsigned long long)v << (8 * sct);
+                            }
+                            ttab[e] = pack;
+                            K = (unsigned)e;
+                        } else {
+                            K = 1u;
+                            s_overflow = 1;
                         }
-                        ttab[e] = pack;
-                        K = (unsigned)e;
-                    } else {
-                        K = 0u;
-                        s_overflow = 1;
                     }
                 }
             }
@@ -478,18 +530,25 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     }
     __syncthreads();
     const bool degrade = !table || s_overflow != 0;
-    if (tid == 0 && table) {
-        atomicMax(a.build_info + 0, kTabFixed + s_count);
-        if (s_overflow) atomicAdd(a.build_info + 1, 1);
+    if (tid == 0) {
+        if (table) {
+            atomicMax(a.build_info + 0, kTabFixed + s_count);
+            if (s_overflow) atomicAdd(a.build_info + 1, 1);
+        }
+        s_cold.grid = a.grid; s_cold.sbeams = sbeams; s_cold.deferred = 0ull; s_cold.gathers = 0ull;
+        s_cold.ktile = degrade ? nullptr : ktile;
+        s_cold.x0 = pl.x0; s_cold.y0 = pl.y0; s_cold.w = pl.w; s_cold.h = pl.h; s_cold.pitch_k = pl.pitch_k;
+        s_cold.k0 = k0;
     }
+    __syncthreads();
 
     TabConst tc;
-    tc.mul = pl.mul; tc.frac_thr = pl.frac_thr;
+    tc.mul_x = pl.mul_x; tc.mul_y = pl.mul_y; tc.frac_thr = pl.frac_thr;
     tc.pitch2 = (unsigned)pl.pitch_k * 2u;
     const unsigned sk = (unsigned)__cvta_generic_to_shared(ktile);
-    tc.kbase = sk - pl.hi_bias * tc.pitch2 - pl.hi_bias * 2u;
+    tc.kbase = sk - pl.bias_y * tc.pitch2 - pl.bias_x * 2u;
     tc.k0 = k0;
-    const unsigned ksafe = sk + (unsigned)pl.safe_off;
+    tc.k129 = k0 + (unsigned)kTabFixed;
     const double gx = (double)a.grid.origin_x, gy = (double)a.grid.origin_y, cpm_d = (double)cpm;
     const int nwords = (nb + 31) / 32;
     uint16_t* q = squeue + warp * kTabQueue;
@@ -508,6 +567,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
         fb.ok = fb.ok && live && !degrade;
         const int edge = __reduce_max_sync(0xffffffffu, fb.ok ? fb.edge : 0);
         int acc = 0, qn = 0;
+        unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;      // uncertain-beam bits of four consecutive 32-beam words
         for (int w = 0; w < nwords; ++w) {
             uint32_t m = 0;
             const int kend = min(32, nb - w * 32);
@@ -515,11 +575,12 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
                 auto run = [&](auto edge_tag) {
                     constexpr int EDGE = decltype(edge_tag)::value;
                     const TabBeam* bw = sfast + w * 32;
+                    const float* dw = sd8 + w * 32;
                     uint32_t bit = 1u;
 MCL_UNROLL(MCL_TAB_UNROLL)
                     for (int k = 0; k < kend; ++k) {
                         int add;
-                        const bool certain = tab_eval<INTERP, COUNT, EDGE>(fb, bw[k], tc, pl, ksafe, add, gathers);
+                        const bool certain = tab_eval<INTERP, COUNT, EDGE>(fb, bw[k], dw[k], tc, pl, add, gathers);
                         acc += add;
                         m |= certain ? 0u : bit;
                         bit += bit;
@@ -531,12 +592,17 @@ MCL_UNROLL(MCL_TAB_UNROLL)
             } else if (live) {
                 m = kend == 32 ? 0xffffffffu : ((1u << kend) - 1u);
             }
-            if (__any_sync(0xffffffffu, m != 0u))
-                qn = tab_defer_word<INTERP, COUNT>(m, w, qn, xa, ya, tha, xb, yb, thb, &s_cold, q, wacc);
+            const int part = w & 3;
+            if (part == 0) m0 = m; else if (part == 1) m1 = m; else if (part == 2) m2 = m; else m3 = m;
+            if (part == 3 || w == nwords - 1) {
+                // hand the uncertain beams of these (up to) four words to the exact path
+                if (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u))
+                    qn = tab_defer_words<INTERP, COUNT>(m0, m1, m2, m3, w & ~3, qn, xa, ya, tha, xb, yb, thb, &s_cold, q, wacc);
+                m0 = m1 = m2 = m3 = 0u;
+            }
         }
-        if (qn > 0) {
+        if (qn > 0)
             tab_drain_round<INTERP, COUNT>(lane < qn ? q[lane] : 0u, lane < qn, xa, ya, tha, xb, yb, thb, &s_cold, wacc);
-        }
         __syncwarp();
         acc += wacc[lane];
         wacc[lane] = 0;
@@ -561,8 +627,8 @@ MCL_UNROLL(MCL_TAB_UNROLL)
 
 __host__ __device__ inline size_t table_fixed_smem(int num_beams)
 {
-    size_t b = (size_t)num_beams * (sizeof(TabBeam) + sizeof(Beam)) + (size_t)kTabWarps * kTabQueue * sizeof(uint16_t) +
-               (size_t)kTabThreads * sizeof(int);
+    size_t b = (size_t)((num_beams + 3) & ~3) * (sizeof(TabBeam) + sizeof(Beam) + sizeof(float)) +
+               (size_t)kTabWarps * kTabQueue * sizeof(uint16_t) + (size_t)kTabThreads * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 

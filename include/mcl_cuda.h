@@ -44,8 +44,11 @@ typedef struct {
                                    pose.utime = odometry utime, real per-ray interpolation (the evident intent). */
     int    lanes_per_particle;  /* sensor kernel mapping: 0 = auto, else 1, 2, 4, 8, 16 or 32 lanes share one particle */
     int    map_tile;            /* 0 = auto, 1 = force L2/global gathers, 2 = force shared-memory map tile */
-    int    sensor_path;         /* 0 = auto: certified float pass, then the literal restatement for every evaluation it
-                                   could not certify (identical results); 1 = literal restatement only */
+    int    sensor_path;         /* 0 = auto: the score-table pass (one kernel: certified table lookups, the literal
+                                   restatement for whatever it cannot certify) where the cloud's map window fits shared
+                                   memory, else the two-pass path; 1 = literal restatement only; 2 = two-pass path only
+                                   (certified float pass, then the literal restatement in a second kernel).  Results are
+                                   identical whichever runs */
     int    weight_mode;         /* 0 (default) = the reference's linear rule w = max(score, weight_floor) / sum
                                    (particle_filter.cpp:116-141): the parity mode.  1 = scores as log-likelihoods:
                                    w = exp(lse_beta (score - max score)) / sum, normalised by a max / log-sum-exp reduction
@@ -77,11 +80,13 @@ typedef struct {
     double  effective_sample_size;
     float   ms_resample, ms_action, ms_score, ms_normalize, ms_estimate, ms_total;  /* last mcl_update, CUDA events */
     int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
-    int     map_tile_used;        /* 1 = L2/global gathers, 2 = one shared-memory tile, 3 = one tile per batch of 1024 particles */
+    int     map_tile_used;        /* 1 = L2/global gathers, 2 = one shared-memory tile, 3 = one tile per batch of 1024 particles,
+                                     4 = one shared-memory class tile + score table (score-table pass) */
     int     kernel_launches;      /* kernels launched by the last mcl_update */
     int     collectives;          /* slice exchanges enqueued by the last mcl_update (0 on one GPU) */
     int     peer_push;            /* 1: pose slices travel by copy-engine peer writes (CUDA IPC), else NCCL all-gather */
-    int     sensor_path;          /* path of the last scoring pass: 2 = certified float pass + exact re-evaluation, 1 = exact only */
+    int     sensor_path;          /* path of the last scoring pass: 3 = score-table pass, 2 = certified float pass + exact
+                                     re-evaluation (two kernels), 1 = exact only */
     int     reserved[2];
     int64_t deferred_evals;       /* evaluations of the last scoring pass the float pass could not certify (re-done exactly) */
     double  fast_eps;             /* error bound (cells) the certification used, 0 when the exact path ran alone */

@@ -192,7 +192,8 @@ TAB_STEPS = [(1, 0), (1, 1), (0, 1), (-1, 1), (-1, 0), (-1, -1), (0, -1), (1, -1
 
 class TabPlan:
     """table_plan_kernel for a cloud: window = bounding box of poses and parents +- (longest ray + 6 cells), clipped to
-    the grid plus a 2-cell margin; budget with the three grid roundings carried by k."""
+    the grid plus four cells; coordinates are window-normalised ((c + kappa - 0.5) / (w - 1.5)) so that one saturating
+    FFMA evaluates and clamps them."""
 
     def __init__(self, grid, cloud, ranges, thetas, ratios, min_range, smem_total=231424, smem_fixed=None):
         cpm = float(F(grid.cells_per_meter))
@@ -216,67 +217,66 @@ class TabPlan:
         reach = rc_max + 6.0
         cx0 = np.floor((float(xs.min()) - ox) * cpm - reach); cx1 = np.ceil((float(xs.max()) - ox) * cpm + reach)
         cy0 = np.floor((float(ys.min()) - oy) * cpm - reach); cy1 = np.ceil((float(ys.max()) - oy) * cpm + reach)
-        x0, y0 = int(max(cx0, -2.0)), int(max(cy0, -2.0))
-        x1, y1 = int(min(cx1, grid.width + 1)), int(min(cy1, grid.height + 1))
-        if x1 < x0 + 2 or y1 < y0 + 2:
+        if not (abs(cx0) < 1e6 and abs(cy0) < 1e6 and cx1 - cx0 < 8192 and cy1 - cy0 < 8192):
             return
+        ux0, uy0, ux1, uy1 = int(cx0), int(cy0), int(cx1), int(cy1)
+        x0, y0 = max(ux0, -4), max(uy0, -4)
+        x1, y1 = min(ux1, grid.width + 3), min(uy1, grid.height + 3)
         tw, th_ = x1 - x0 + 1, y1 - y0 + 1
+        if tw < 8 or th_ < 8:
+            return
         pitch_k = (tw + 1) & ~1
         if ((pitch_k >> 1) & 1) == 0:
             pitch_k += 2
         k_bytes = (pitch_k * 2 * th_ + 15) & ~15
         if smem_fixed is None:
-            smem_fixed = (nb * 32 + 32 * 96 * 2 + 1024 * 4 + 15) & ~15
+            nb4 = (nb + 3) & ~3
+            smem_fixed = (nb4 * 36 + 32 * 192 * 2 + 1024 * 4 + 15) & ~15
         room = smem_total - smem_fixed - k_bytes - 64
-        we = max(tw, th_) + rc_max + 8.0
-        cm_ = max(x0 + tw, y0 + th_) + 1.0
-        if room < 8 * (TAB_FIXED + 256) or we >= 4096.0 or cm_ > 16000.0:
+        if room < 8 * (TAB_FIXED + 256):
             return
-        self.fb = fb = 12 if we < 1024 else (11 if we < 2048 else 10)
+        cm_ = max(ux1, uy1) + 2.0
+        if cm_ > 16000.0:
+            return
         xm = cm_ / cpm + max(abs(ox), abs(oy))
         shift = 64.0
         ce = cm_ + rc_max
         e_ref = cpm * U * xm + 2 * U * ce + 2 * U * rc_max + rc_max * (20 * U + 1.2e-7) + 1e-9
-        e_apx = (1 + 2 * rho_max) * U * shift + 2 * U * rc_max + rc_max * ((3.14159265358979 * (3 * rho_max + 1) + 9.5) * U + TRIG_ERR)
+        e_apx = 6 * U * max(tw, th_) + (1 + 2 * rho_max) * U * shift + 3 * U * rc_max + \
+            rc_max * ((3.14159265358979 * (3 * rho_max + 1) + 9.5) * U + TRIG_ERR)
         self.eps = eps = 1.25 * (e_ref + e_apx) + 1e-6
-        one = 1 << fb
-        self.k = k = int(np.ceil(one * eps + 1.5))
-        if k > one // 16:
+        self.kappa = kappa = eps + 1e-5
+        if kappa > 1.0 / 16.0:
             return
         self.ok = True
         self.x0, self.y0, self.w, self.h = x0, y0, tw, th_
         self.cap_entries = room // 8
-        self.mul = 1 << (32 - fb)
-        self.frac_thr = (2 * k) << (32 - fb)
-        magic_base = F(1.5 * 2.0 ** (23 - fb))
-        self.hi_bias = int(magic_base.view(np.uint32)) >> fb
-        self.magic = float(magic_base) + k / one
-        self.magic_f = F(self.magic)
-        assert float(self.magic_f) == self.magic
+        self.off = kappa - 0.5
+        self.inv_sx, self.inv_sy = 1.0 / (tw - 1.5), 1.0 / (th_ - 1.5)
+        self.mul_x, self.mul_y = (2 * tw - 3) << 8, (2 * th_ - 3) << 8
+        self.bias_x, self.bias_y = 127 * tw - 191, 127 * th_ - 191
+        self.frac_thr = int(np.ceil(2.0 * kappa * 4294967296.0))
         self.t3 = F(3.0 * (1.0 + 2.0 * eps) + 4.0 * U * rc_max + 1e-4)
         self.rho_lo, self.rho_hi, self.rho_abs = F(rho_lo), F(rho_hi), F(rho_max * (1 + 1e-6))
         self.max_shift, self.coord_hi = F(shift), F(cm_ - 1.0)
         self.reach = F(rc_max * (1 + 1e-6) + 4.0)
-        self.grid_min_dim = F(min(grid.width, grid.height))
         self.ang_room = F(9.5) - F(max_abs_theta)
-        self.wlo_x, self.whi_x = F(x0 + 1.5 + float(self.reach)), F(x0 + tw - 1.5 - float(self.reach))
-        self.wlo_y, self.whi_y = F(y0 + 1.5 + float(self.reach)), F(y0 + th_ - 1.5 - float(self.reach))
-        kappa = k / one + 1.0 / one
-        lcx, hcx, lcy, hcy = max(-x0, 1), tw - 1, max(-y0, 1), th_ - 1
-        empty = hcx <= lcx or hcy <= lcy
-        self.cmid_x, self.chalf_x = F(0.5 * (lcx + hcx) + self.magic), F(-1.0) if empty else F(0.5 * (hcx - lcx) - kappa)
-        self.cmid_y, self.chalf_y = F(0.5 * (lcy + hcy) + self.magic), F(-1.0) if empty else F(0.5 * (hcy - lcy) - kappa)
-        self.gmid_x, self.gmid_y = F(0.5 * (grid.width - 1) - x0 + self.magic), F(0.5 * (grid.height - 1) - y0 + self.magic)
-        self.ghalf_x, self.ghalf_y = F(0.5 * (grid.width + 3) + eps + kappa + 1e-3), F(0.5 * (grid.height + 3) + eps + kappa + 1e-3)
-        self.x2_lo_x, self.x2_lo_y = F(3.0 * eps + 2.0 * kappa + 1e-3 - x0), F(3.0 * eps + 2.0 * kappa + 1e-3 - y0)
+        self.ulo_x, self.uhi_x = F(ux0 + 1.5 + float(self.reach)), F(ux1 + 1 - 1.5 - float(self.reach))
+        self.ulo_y, self.uhi_y = F(uy0 + 1.5 + float(self.reach)), F(uy1 + 1 - 1.5 - float(self.reach))
+        self.hmin_x, self.hmin_y = self.bias_x - x0, self.bias_y - y0
+        x2_min = 3.0 * eps + 2.0 * kappa + 1e-3
+        self.x2_lo_x = F((x2_min - x0 + self.off) * self.inv_sx * (1 + 1e-6) + 1e-7)
+        self.x2_lo_y = F((x2_min - y0 + self.off) * self.inv_sy * (1 + 1e-6) + 1e-7)
 
 
 def build_score_table(grid, plan):
     """The K tile (class per window cell) and the table T (8 sector scores per class) of score_table_kernel."""
-    cells = np.pad(grid.cells.astype(np.int64), 4)          # zero outside the grid, 4 cells of it
+    cells = grid.cells.astype(np.int64)
+    H, W = cells.shape
 
-    def raw(gx, gy):                                         # arrays of global cells, any value in [-4, W+3]
-        return cells[np.clip(gy + 4, 0, cells.shape[0] - 1), np.clip(gx + 4, 0, cells.shape[1] - 1)]
+    def raw(gx, gy):                                         # arrays of global cells; 0 outside the grid
+        inside = (gx >= 0) & (gx < W) & (gy >= 0) & (gy < H)
+        return np.where(inside, cells[np.clip(gy, 0, H - 1), np.clip(gx, 0, W - 1)], 0)
 
     gy, gx = np.meshgrid(np.arange(plan.y0, plan.y0 + plan.h), np.arange(plan.x0, plan.x0 + plan.w), indexing="ij")
     c = raw(gx, gy)
@@ -286,10 +286,14 @@ def build_score_table(grid, plan):
             near5 |= raw(gx + dx, gy + dy) > 0
     nb = np.stack([raw(gx + ux, gy + uy) for ux, uy in TAB_STEPS])          # [8, h, w]
     any8 = (nb > 0).any(axis=0)
+    far = (gx <= -4) | (gy <= -4) | (gx >= W + 3) | (gy >= H + 3)     # the truncated cell and its neighbours are outside
+    neg = ~far & ((gx < 0) | (gy < 0))                                # truncation != floor: never certified
+    gen = ~far & ~neg
     K = np.zeros(c.shape, np.int64)
-    K[(c <= 0) & near5 & ~any8] = 1
-    K[c > 0] = 1 + c[c > 0]
-    nt = (c <= 0) & any8
+    K[neg] = 1
+    K[gen & (c <= 0) & near5 & ~any8] = 1
+    K[gen & (c > 0)] = 1 + c[gen & (c > 0)]
+    nt = gen & (c <= 0) & any8
     idx = np.flatnonzero(nt.ravel())
     T = np.zeros((TAB_FIXED + len(idx), 8), np.int64)
     for i in range(2, TAB_FIXED):
@@ -310,58 +314,57 @@ def table_pass(grid, plan, K, T, particle, ranges, thetas, ratios, min_range, rn
     gx, gy, cpm_d = np.float64(F(grid.origin_x)), np.float64(F(grid.origin_y)), np.float64(F(grid.cells_per_meter))
     xa, ya, tha = (F(particle["pose"][k]) for k in ("x", "y", "theta"))
     xb, yb, thb = (F(particle["parent_pose"][k]) for k in ("x", "y", "theta"))
+    ddx = ddy = np.float64(0.0)
     if interp:
         gsx, gsy = (np.float64(xb) - gx) * cpm_d, (np.float64(yb) - gy) * cpm_d
-        dsx, dsy = F(np.float64(F(xa - xb)) * cpm_d), F(np.float64(F(ya - yb)) * cpm_d)
+        ddx, ddy = np.float64(F(xa - xb)) * cpm_d, np.float64(F(ya - yb)) * cpm_d
         d = np.float64(tha) - np.float64(thb)
         if abs(d) > np.pi:
             d += -2 * np.pi if d > 0 else 2 * np.pi
         th0, dth = thb, F(d)
     else:
         gsx, gsy = (np.float64(xa) - gx) * cpm_d, (np.float64(ya) - gy) * cpm_d
-        dsx = dsy = dth = F(0)
+        dth = F(0)
         th0 = tha
-    sxbm, sybm = F((gsx - plan.x0) + plan.magic), F((gsy - plan.y0) + plan.magic)
-    gxb, gyb = F(gsx), F(gsy)
-    one = np.ones(1, F)
-    xs = [fma32(dsx * one, plan.rho_lo, gxb * one)[0], fma32(dsx * one, plan.rho_hi, gxb * one)[0]]
-    ys = [fma32(dsy * one, plan.rho_lo, gyb * one)[0], fma32(dsy * one, plan.rho_hi, gyb * one)[0]]
+    sxn, syn = F(((gsx - plan.x0) + plan.off) * plan.inv_sx), F(((gsy - plan.y0) + plan.off) * plan.inv_sy)
+    dsxn, dsyn = F(ddx * plan.inv_sx), F(ddy * plan.inv_sy)
+    gxb, gyb, dsx, dsy = F(gsx), F(gsy), F(ddx), F(ddy)
+    xs = [fma32(dsx, plan.rho_lo, gxb), fma32(dsx, plan.rho_hi, gxb)]
+    ys = [fma32(dsy, plan.rho_lo, gyb), fma32(dsy, plan.rho_hi, gyb)]
     xlo, xhi, ylo, yhi = min(xs), max(xs), min(ys), max(ys)
     lo, hi = min(xlo, ylo), max(xhi, yhi)
+    in_uwin = xlo >= plan.ulo_x and xhi <= plan.uhi_x and ylo >= plan.ulo_y and yhi <= plan.uhi_y
     ok = (lo >= 1.0 and hi <= plan.coord_hi and abs(dsx) <= plan.max_shift and abs(dsy) <= plan.max_shift
           and abs(th0) <= F(3.15) and abs(dth) <= F(3.15)
-          and fma32(plan.rho_abs * one, abs(dth), abs(th0) * one)[0] <= plan.ang_room)
+          and fma32(plan.rho_abs, abs(dth), abs(th0)) <= plan.ang_room and in_uwin)
     if not ok:
         return np.zeros(n, np.int64), np.zeros(n, bool), -1
-    in_grid = lo >= plan.reach and hi <= plan.grid_min_dim - plan.reach
-    in_winp = xlo >= plan.wlo_x and xhi <= plan.whi_x and ylo >= plan.wlo_y and yhi <= plan.whi_y
-    edge = (0 if (in_grid and in_winp) else 1) if lo >= F(2.0) * plan.reach else 2
+    edge = 0 if lo >= F(2.0) * plan.reach else (1 if lo >= plan.reach else 2)
     if force_edge is not None:
         edge = max(edge, force_edge)
     onev = np.ones(n, F)
-    sxm = fma32(dsx * onev, rho, sxbm * onev) if interp else sxbm * onev
-    sym = fma32(dsy * onev, rho, sybm * onev) if interp else sybm * onev
+    sxm = fma32(dsxn * onev, rho, sxn * onev) if interp else sxn * onev
+    sym = fma32(dsyn * onev, rho, syn * onev) if interp else syn * onev
     thr = fma32(dth * onev, rho, th0 * onev) if interp else th0 * onev
     a = (thr - th).astype(F)
     err = rng.uniform(-1.3e-6, 1.3e-6, (2, n))
     s = (np.sin(a.astype(np.float64)) + err[0]).astype(F)
     c = (np.cos(a.astype(np.float64)) + err[1]).astype(F)
     rc = (r * F(grid.cells_per_meter)).astype(F)
-    bxf, byf = fma32(rc, c, sxm), fma32(rc, s, sym)
-    wx = bxf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul)
-    wy = byf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul)
+    rcx, rcy = (rc.astype(np.float64) * plan.inv_sx).astype(F), (rc.astype(np.float64) * plan.inv_sy).astype(F)
+    nx, ny = np.clip(fma32(rcx, c, sxm), F(0), F(1)), np.clip(fma32(rcy, s, sym), F(0), F(1))      # fma.rn.sat.f32
+    bxf, byf = (nx + F(1)).astype(F), (ny + F(1)).astype(F)
+    wx = bxf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul_x)
+    wy = byf.view(np.uint32).astype(np.uint64) * np.uint64(plan.mul_y)
     fx, hx = (wx & np.uint64(0xffffffff)).astype(np.int64), (wx >> np.uint64(32)).astype(np.int64)
     fy, hy = (wy & np.uint64(0xffffffff)).astype(np.int64), (wy >> np.uint64(32)).astype(np.int64)
     cell_ok = np.minimum(fx, fy) >= plan.frac_thr
-    cx, cy = hx - plan.hi_bias, hy - plan.hi_bias               # window cells
-    in_win = np.ones(n, bool); outside = np.zeros(n, bool); x2_pos = np.ones(n, bool)
-    if edge >= 1:
-        in_win = (np.abs((bxf - plan.cmid_x).astype(F)) < plan.chalf_x) & (np.abs((byf - plan.cmid_y).astype(F)) < plan.chalf_y)
-        outside = (np.abs((bxf - plan.gmid_x).astype(F)) >= plan.ghalf_x) | (np.abs((byf - plan.gmid_y).astype(F)) >= plan.ghalf_y)
-        cx, cy = np.where(in_win, cx, 1), np.where(in_win, cy, 1)
     if edge >= 2:
-        ex, ey = (bxf - plan.magic_f).astype(F), (byf - plan.magic_f).astype(F)
-        x2_pos = (fma32(rc, c, ex) >= plan.x2_lo_x) & (fma32(rc, s, ey) >= plan.x2_lo_y)
+        cell_ok = cell_ok & (hx >= plan.hmin_x) & (hy >= plan.hmin_y)
+    cx, cy = hx - plan.bias_x, hy - plan.bias_y                 # window cells
+    x2_pos = np.ones(n, bool)
+    if edge >= 1:
+        x2_pos = (fma32(rcx, c, nx) >= plan.x2_lo_x) & (fma32(rcy, s, ny) >= plan.x2_lo_y)
     assert (cx >= 0).all() and (cx < plan.w).all() and (cy >= 0).all() and (cy < plan.h).all(), "table pass read outside its window"
     Kv = K[cy, cx]
     r8 = fma32(a, TAB_C8, F(25165824.0) * onev)
@@ -374,5 +377,5 @@ def table_pass(grid, plan, K, T, particle, ranges, thetas, ratios, min_range, rn
         d8 = np.where((xq >= 0.3) | ~(xq >= 0.0), 4.0, (np.arcsin(np.minimum(xq, 1.0)) + 2e-5) * 1.2732395447351628 * (1 + 1e-6))
     d8 = d8.astype(F) + F(1e-6)
     dir_ok = x2_pos & (np.abs((np.abs(u8) - TAB_B2).astype(F)) > d8)
-    val_ok = in_win & ((Kv == 0) | (cell_ok & ((Kv < TAB_FIXED) | dir_ok)))
-    return np.where(val_ok, v, 0), val_ok | outside, edge
+    certain = (Kv == 0) | (cell_ok & ((Kv < TAB_FIXED) | dir_ok))
+    return np.where(certain, v, 0), certain, edge

@@ -118,8 +118,27 @@ def make_interior_case(case):
     return grid, cloud, r, th, t
 
 
+def make_corner_case(case):
+    """A tracking cloud next to the map's low edges: rays end at negative global coordinates, where the reference's
+    truncation toward zero is not a floor (the table pass's EDGE 1 / 2 variants and its never-certified cells)."""
+    rng = np.random.default_rng(9000 + case)
+    grid = synth.make_map(420, seed=290 + case)
+    lo, hi = [(20, 70), (90, 150), (20, 150)][case % 3]
+    while True:
+        truth = synth.find_free_pose(grid, rng)
+        cx, cy = (truth[0] - grid.origin_x) / 0.05, (truth[1] - grid.origin_y) / 0.05
+        if lo < min(cx, cy) < hi:
+            break
+    r, th, t = synth.make_scan(grid, truth, num_beams=360, seed=case, max_range=4.0)
+    r = np.where(np.arange(len(r)) % 7 == 0, np.float32(3.9), r).astype(np.float32)       # some rays leave the grid
+    cloud = synth.make_particles(150, truth, seed=case, sigma_xy=0.15, sigma_theta=0.1, parent_utime=int(t[0]),
+                                 pose_utime=int(t[-1]))
+    return grid, cloud, r, th, t
+
+
 def _table_case(case, force_edge=None, interp=True, perturb=None):
-    grid, cloud, r, th, t = make_case(case) if case < 100 else make_interior_case(case)
+    grid, cloud, r, th, t = (make_case(case) if case < 100 else make_interior_case(case) if case < 200
+                             else make_corner_case(case))
     t_b, t_a = int(cloud["parent_pose"]["utime"][0]), int(cloud["pose"]["utime"][0])
     if interp:
         ratios = (t - t_b).astype(np.float64) / float(t_a - t_b)
@@ -169,6 +188,16 @@ def test_table_pass_interior_cloud(case, interp):
     wrong, certain_total, evals, edges, plan = res
     assert wrong == 0 and edges == {0}
     assert certain_total >= 0.9 * evals, (certain_total, evals)
+
+
+@pytest.mark.parametrize("case", [200, 201, 202, 203, 204, 205])
+def test_table_pass_cloud_at_the_low_edges(case):
+    res = _table_case(case)
+    assert res is not None
+    wrong, certain_total, evals, edges, plan = res
+    assert wrong == 0
+    assert edges & {1, 2}, edges
+    assert certain_total >= 0.5 * evals, (certain_total, evals)
 
 
 def test_table_pass_equal_utime_variant():

@@ -462,9 +462,11 @@ def test_config1_replay_follows_the_reference_filter(legacy, real_map):
 # The default sensor path scores every beam first with a float model whose result it can certify, and re-evaluates the
 # rest with the literal restatement.  These tests pin: (a) identical scores to the exact-only
 # path at scale and on hostile inputs, (b) the measured inputs of the certification's error budget.
-def _scores_both_paths(grid, cloud, r, th, t, **params):
+def _scores_both_paths(grid, cloud, r, th, t, paths=(0, 1), **params):
+    """Scores + stats per sensor_path: 0 = auto (the score-table pass where its window fits, else the two-pass path),
+    2 = the two-pass path (certified float pass + exact re-evaluation), 1 = the literal restatement only."""
     out = []
-    for path in (0, 1):
+    for path in paths:
         e = make_engine(len(cloud), grid, sensor_path=path, **params)
         e.import_particles(cloud)
         e.set_gather_counting(True)
@@ -492,11 +494,16 @@ def test_two_pass_equals_exact_at_scale(side, n, kind, variant):
             cloud["parent_pose"]["utime"] = pu
             cloud["parent_pose"]["x"] += np.float32(0.013)
             cloud["parent_pose"]["theta"] = np.clip(cloud["parent_pose"]["theta"] - np.float32(0.02), -3.14, 3.14)
-    (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t)
+    (s0, st0), (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t, paths=(0, 2, 1))
     assert st2["sensor_path"] == 2 and st1["sensor_path"] == 1
-    assert np.array_equal(s2, s1)
-    assert st2["gathers"] == st1["gathers"] and st2["evals"] == st1["evals"]
-    assert 0 < st2["deferred_evals"] < 0.5 * st2["evals"]
+    # the score-table pass runs wherever the cloud's window (16-bit classes) fits shared memory: any cloud on the
+    # 200 x 200 map (window clipped to the grid), tracking clouds with rays up to about 6 m; the rest falls back to the
+    # two-pass path
+    assert st0["sensor_path"] in (2, 3) and (side != 200 or st0["sensor_path"] == 3), st0
+    assert np.array_equal(s2, s1) and np.array_equal(s0, s1)
+    for st in (st0, st2):
+        assert st["gathers"] == st1["gathers"] and st["evals"] == st1["evals"]
+        assert 0 < st["deferred_evals"] < 0.5 * st["evals"]
 
 
 def test_two_pass_hostile_particles(real_map):
@@ -509,11 +516,18 @@ def test_two_pass_hostile_particles(real_map):
     px[8] = np.nan; px[9] = 40.0; px[10] = -4.999
     h[11] = 4.0; h[12] = -7.0; h[13] = np.nan; h[14] = 3.1415927; h[15] = -3.1415927
     cloud["pose"]["y"][16] = -4.9999; cloud["pose"]["y"][17] = 4.9999; cloud["parent_pose"]["y"][18] = 1e30
-    (s2, st2), (s1, st1) = _scores_both_paths(real_map, cloud, r, th, t)
+    (s0, st0), (s2, st2), (s1, st1) = _scores_both_paths(real_map, cloud, r, th, t, paths=(0, 2, 1))
     assert st2["sensor_path"] == 2
-    assert np.array_equal(s2, s1)
+    assert np.array_equal(s2, s1) and np.array_equal(s0, s1)
     want, gathers, _ = port.likelihood(port_grid(real_map), cloud, r, th, t)
-    assert np.array_equal(s2, want) and st2["gathers"] == gathers
+    assert np.array_equal(s2, want) and st2["gathers"] == gathers and st0["gathers"] == gathers
+    # the same cloud without the non-finite positions (they blow up the window): the score-table pass runs, the
+    # remaining hostile particles go to its exact drain
+    finite = np.isfinite(cloud["pose"]["x"]) & np.isfinite(cloud["parent_pose"]["x"]) & (np.abs(cloud["pose"]["x"]) < 100) & \
+        (np.abs(cloud["parent_pose"]["x"]) < 100) & (np.abs(cloud["parent_pose"]["y"]) < 100)
+    sub = cloud[finite][:2048].copy()
+    (t0, tst0), (t1, tst1) = _scores_both_paths(real_map, sub, r, th, t, paths=(0, 1))
+    assert tst0["sensor_path"] == 3 and np.array_equal(t0, t1) and tst0["gathers"] == tst1["gathers"]
 
 
 def test_two_pass_hostile_scans(real_map):
@@ -528,15 +542,16 @@ def test_two_pass_hostile_scans(real_map):
         "short_ranges": (np.full_like(r, 0.16), th, t),
     }
     for name, (rr, tt, ti) in cases.items():
-        e = make_engine(len(cloud), real_map)
-        e.import_particles(cloud)
-        s = e.score(rr, tt, ti)
-        st = e.stats()
-        want, _, _ = port.likelihood(port_grid(real_map), cloud, rr, tt, ti)
-        assert np.array_equal(s, want), name
-        if name in ("big_theta", "late_times"):
-            assert st["sensor_path"] == 1, name               # the float pass declared itself not applicable
-        e.close()
+        for path in (0, 2):
+            e = make_engine(len(cloud), real_map, sensor_path=path)
+            e.import_particles(cloud)
+            s = e.score(rr, tt, ti)
+            st = e.stats()
+            want, _, _ = port.likelihood(port_grid(real_map), cloud, rr, tt, ti)
+            assert np.array_equal(s, want), (name, path)
+            if name in ("big_theta", "late_times"):
+                assert st["sensor_path"] == 1, name               # the float passes declared themselves not applicable
+            e.close()
 
 
 def test_fast_trig_error_bound():
@@ -707,12 +722,12 @@ def test_config4_full_size_two_pass_equals_exact():
     am.update(*truth, int(t[0]) - 100_000)
     assert am.update(truth[0] + 0.02, truth[1] + 0.01, truth[2] + 0.01, int(t[-1]))
     out = {}
-    for path in (0, 1):
+    for path in (0, 2, 1):
         e = make_engine(n, grid, sensor_path=path)
         e.init_at_pose(*truth, utime=int(t[0]) - 100_000, seed=21)
         est = e.update(am, int(t[-1]), r, th, t, 0.8401877171547095 / n)
         st = e.stats()
-        assert st["sensor_path"] == (2 if path == 0 else 1)
+        assert st["sensor_path"] == {0: 3, 2: 2, 1: 1}[path]
         scores = e.score(r, th, t)                   # same cloud, same scan: the stage alone, all 16 M scores
         am2 = engine.ActionModel()
         am2.c = type(am.c).from_buffer_copy(am.c)
@@ -720,14 +735,15 @@ def test_config4_full_size_two_pass_equals_exact():
         out[path] = (scores, st["weight_sum"], (est.x, est.y, est.theta), (est2.x, est2.y, est2.theta),
                      e.export_particles(stride=1009), st["deferred_evals"], st["evals"])
         e.close()
-    a, b = out[0], out[1]
-    assert np.array_equal(a[0], b[0])
-    assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
-    for k in ("pose", "parent_pose"):
-        for f in ("x", "y", "theta"):
-            assert np.array_equal(a[4][k][f], b[4][k][f])
-    assert np.array_equal(a[4]["weight"], b[4]["weight"])
-    assert 0 < a[5] < 0.2 * a[6] and b[5] == 0
+    b = out[1]
+    for a in (out[0], out[2]):
+        assert np.array_equal(a[0], b[0])
+        assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+        for k in ("pose", "parent_pose"):
+            for f in ("x", "y", "theta"):
+                assert np.array_equal(a[4][k][f], b[4][k][f])
+        assert np.array_equal(a[4]["weight"], b[4]["weight"])
+        assert 0 < a[5] < 0.2 * a[6] and b[5] == 0
 
 
 # ------------------------------------------------------------------ extension: log-sum-exp weights (weight_mode = 1)
@@ -789,11 +805,11 @@ def test_two_pass_randomized_geometry(case):
     else:
         cloud = synth.make_particles(n, truth, seed=case, sigma_xy=float(rng.choice([0.05, 0.3, 1.5])),
                                      sigma_theta=float(rng.choice([0.02, 0.5])), parent_utime=int(t[0]), pose_utime=int(t[-1]))
-    (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t)
+    (s0, st0), (s2, st2), (s1, st1) = _scores_both_paths(grid, cloud, r, th, t, paths=(0, 2, 1))
     want, gathers, evals = port.likelihood(port_grid(grid), cloud, r, th, t)
-    assert np.array_equal(s1, want) and np.array_equal(s2, want)
-    assert st1["gathers"] == gathers and st2["gathers"] == gathers and st2["evals"] == evals
-    assert st1["sensor_path"] == 1
+    assert np.array_equal(s1, want) and np.array_equal(s2, want) and np.array_equal(s0, want)
+    assert st1["gathers"] == gathers and st2["gathers"] == gathers and st2["evals"] == evals and st0["gathers"] == gathers
+    assert st1["sensor_path"] == 1 and st2["sensor_path"] in (1, 2) and st0["sensor_path"] in (1, 2, 3)
 
 
 def test_map_update_reference_golden(real_map):
@@ -813,16 +829,18 @@ def test_map_update_reference_golden(real_map):
     e.close()
 
 
-def test_scoring_follows_device_map_updates():
-    """The fast pass reads a derived copy of the map (empty-neighbourhood look-ahead); it must follow every mutation of
-    the mirror: mcl_map_update, mcl_update_map_rect, mcl_set_map.  Scores after each equal the oracle's on the same map."""
+@pytest.mark.parametrize("path", [0, 2])
+def test_scoring_follows_device_map_updates(path):
+    """The fast passes read a derived copy of the map (empty-neighbourhood look-ahead), the score-table pass builds its
+    class tile and table from it and from the mirror; they must follow every mutation of the mirror: mcl_map_update,
+    mcl_update_map_rect, mcl_set_map.  Scores after each equal the oracle's on the same map."""
     grid = synth.make_map(300, seed=12)
     rng = np.random.default_rng(12)
     pose = synth.find_free_pose(grid, rng)
     r, th, t = synth.make_scan(grid, pose, seed=12)
     cloud = synth.make_particles(20_000, pose, seed=12, sigma_xy=0.4, sigma_theta=0.3, parent_utime=int(t[0]),
                                  pose_utime=int(t[-1]))
-    e = make_engine(len(cloud), grid)
+    e = make_engine(len(cloud), grid, sensor_path=path)
     e.import_particles(cloud)
     cells = grid.cells.copy()
 
@@ -830,7 +848,7 @@ def test_scoring_follows_device_map_updates():
         g = synth.GridSpec(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
         want, _, _ = port.likelihood(port_grid(g), cloud, r, th, t)
         assert np.array_equal(e.score(r, th, t), want), tag
-        assert e.stats()["sensor_path"] == 2
+        assert e.stats()["sensor_path"] == (3 if path == 0 else 2)
 
     check("initial")
     prv = (pose[0] - 0.03, pose[1], pose[2], int(t[0]))
