@@ -295,6 +295,8 @@ struct FastPlan {
     float x2_min;        // extended-point (global) coordinates at or above this are certainly non-negative in the reference
     float ghalf_x, ghalf_y;   // |e - gmid| >= ghalf  =>  the endpoint is certainly two or more cells outside the grid
     float rho_lo, rho_hi;   // range of the scan's interpolation ratios
+    float rho_abs;          // max |ratio|
+    float ang_room;         // 9.5 - max |beam angle|: |heading| + rho_abs |heading change| must stay below it
     float max_shift;     // largest |dS| (cells) a particle may have and still take the fast pass
     float coord_hi;      // largest robot cell coordinate (global) the error budget covers
     float reach;         // longest ray of the scan in cells (+ margin)
@@ -354,7 +356,8 @@ __device__ __forceinline__ FastBase make_fast_base(float xa, float ya, float tha
     const float y0 = __fmaf_rn(f.dsy, fp.rho_lo, gyb), y1 = __fmaf_rn(f.dsy, fp.rho_hi, gyb);
     const float lo = fminf(fminf(x0, x1), fminf(y0, y1)), hi = fmaxf(fmaxf(x0, x1), fmaxf(y0, y1));
     f.ok = lo >= 1.0f && hi <= fp.coord_hi && fabsf(f.dsx) <= fp.max_shift && fabsf(f.dsy) <= fp.max_shift &&
-           fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f;
+           fabsf(f.thb) <= 3.15f && fabsf(f.dth) <= 3.15f &&
+           __fmaf_rn(fp.rho_abs, fabsf(f.dth), fabsf(f.thb)) <= fp.ang_room;      // SFU error bound: |angle| <= 9.5
     // how close to the grid's edges the particle's rays can get (reach already carries the margins)
     const bool inside = lo >= fp.reach && hi <= fp.grid_min_dim - fp.reach;      // no endpoint within 2 cells of an edge
     const bool x2_pos = lo >= 2.0f * fp.reach;                                   // no doubled endpoint below 3 cells

@@ -4,6 +4,7 @@
 #include "../../include/mcl_cuda.h"
 #include "mcl_kernels.cuh"
 #include "mcl_table.cuh"
+#include "mcl_shard.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -47,7 +48,15 @@ struct mcl_engine {
 #endif
     // peer push of pose slices over NVLink by the copy engines (no SMs), overlapped with the sensor kernel
     std::vector<float*> peer_pose_block;         // IPC-mapped pose_block of every rank (own entry = pose_block)
-    std::vector<int32_t*> peer_score2;           // IPC-mapped score_block of every rank (own entry = score_block)
+    // exchange block (mcl_shard.cuh): weights, sequential-sum maps, estimate partials, barrier flags; IPC-mapped by
+    // every rank so that slices are exchanged by peer stores / loads
+    unsigned char* xblock = nullptr;
+    XLayout xl{};
+    XPeers xp{};
+    bool xpeer = false;                          // peers' exchange blocks are mapped (multi-GPU sharded stages)
+    int xepoch[kXFlagSlots] = {0};
+    int* fb_count = nullptr;                     // raw-chunk side-buffer slots handed out by this rank (per stage)
+    long long* xrange = nullptr;                 // [2] groups this rank's children draw from
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_action_done = nullptr, ev_push_done = nullptr;
     bool peer_push = false;
@@ -58,13 +67,10 @@ struct mcl_engine {
     PoseSoA pose[2], parent[2];
     float* pose_block = nullptr;                 // one allocation behind pose[0..1].{x,y,th}: [2][3][N] floats
     int cur = 0;
-    double* weight[2] = {nullptr, nullptr};
+    double* weight[2] = {nullptr, nullptr};      // inside xblock
     int wcur = 0;
-    int32_t* score_block = nullptr;     // [2][N]: two score arrays; multi-GPU runs alternate between them so a fast
-                                        // rank's direct stores for update k+1 cannot overtake a slow rank still
-                                        // reading update k (the per-update barrier then bounds the skew to one)
-    int32_t* score2 = nullptr;          // the array of the current update (= score_block + score_parity * N)
-    int score_parity = 0;
+    int32_t* score_block = nullptr;     // [N] half-unit scores (only the rank's slice is computed)
+    int32_t* score2 = nullptr;
     int32_t* idx = nullptr;
     long long pose_utime = 0, parent_utime = 0;
     bool have_particles = false, have_scores = false;
@@ -104,7 +110,6 @@ struct mcl_engine {
     bool scan_finite = true;
 
     // estimate
-    double4* est_partials = nullptr;
     int est_count = 0;
     float* est_out = nullptr;          // device float4
     float* est_host = nullptr;         // pinned float4
@@ -201,34 +206,58 @@ int ensure_staging(mcl_engine* h, size_t bytes)
     return MCL_OK;
 }
 
-// ---- exact sequential running sum of a double vector on the device (S1..S7) --------------------------------------
-int seq_total(mcl_engine* h, const double* w, bool materialize)
+// ---- cross-rank barrier on the engine's stream: flags in the exchange blocks (mcl_shard.cuh) ------------------------------
+// Everything this rank enqueued before the call (peer stores included) is complete before any rank gets past it.
+int xbarrier(mcl_engine* h, int slot)
+{
+    if (h->world == 1) return MCL_OK;
+    if (!h->xpeer) return fail(h, MCL_ERR_COMM, "exchange blocks are not mapped");
+    const int epoch = ++h->xepoch[slot];
+    xsignal_kernel<<<1, 32, 0, h->stream>>>(h->xp, h->xl.flags, slot, epoch);
+    CKL(h);
+    xwait_kernel<<<1, 32, 0, h->stream>>>(h->xblock, h->xl.flags, h->xl.err, slot, epoch, h->world);
+    CKL(h);
+    ++h->collectives;
+    return MCL_OK;
+}
+
+// ---- exact sequential running sum of the weights (buffer wbuf of the exchange block), sharded over the ranks ----------------
+// Leaves the exact total in h->total and the exact entry sum of every group in h->cin2 on every rank.
+int seq_total(mcl_engine* h, int wbuf)
 {
     const long long n = h->n, n1 = h->n1, n2 = h->n2;
-    const int tiles = (int)((n1 + kSeqTileChunks - 1) / kSeqTileChunks);
-    seq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums, h->tile_sums);
+    const double* w = h->weight[wbuf];
+    const long long tile_lo = h->lo / (kL1 * kSeqTileChunks);
+    const long long tile_hi = (h->hi + kL1 * kSeqTileChunks - 1) / (kL1 * kSeqTileChunks);
+    const long long group_lo = h->lo / kSliceAlign, group_hi = (h->hi + kSliceAlign - 1) / kSliceAlign;
+    const int tiles = (int)(tile_hi - tile_lo);
+    if (tiles > 0) {
+        xseq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_sums);
+        CKL(h);
+    }
+    xseq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tile_lo, tile_hi, h->tile_excl, h->xp, h->xl.tot);
     CKL(h);
-    seq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tiles, h->tile_excl);
-    CKL(h);
-    seq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->sums, h->tile_excl, h->ebias, h->q0, h->q1);
-    CKL(h);
-    seq_group_maps_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->ebias, h->q0, h->q1, n1, n2, h->gebias,
-                                                                          h->g0, h->g1);
-    CKL(h);
+    int rc = xbarrier(h, 0);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->fb_count, 0, sizeof(int), h->stream));
+    if (tiles > 0) {
+        XSeqOut o{h->xl.q0, h->xl.q1, h->xl.eb, h->xl.fbraw};
+        xseq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_excl,
+                                                            (const double*)(h->xblock + h->xl.tot), h->fb_count, h->xp, o);
+        CKL(h);
+        xseq_group_maps_kernel<<<(int)((group_hi - group_lo + 127) / 128), 128, 0, h->stream>>>(
+            h->ebias, h->q0, h->q1, n1, group_lo, group_hi, h->xp, h->xl.g0, h->xl.g1, h->xl.ge);
+        CKL(h);
+    }
+    rc = xbarrier(h, 1);
+    if (rc) return rc;
     {
         const size_t walk_smem = (size_t)n2 * 20;                    // g0, g1 (8 B each) + gebias (4 B) per group
         const int staged = walk_smem + 4096 <= (size_t)h->max_smem_optin ? 1 : 0;
-        if (staged) CK(cudaFuncSetAttribute(seq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
-        seq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(
-            w, n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2, h->cin1, h->opened, h->total,
-            h->fallbacks, staged);
-    }
-    CKL(h);
-    if (materialize) {
-        seq_group_expand_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->q0, h->q1, n1, n2, h->cin2,
-                                                                            h->opened, h->cin1);
-        CKL(h);
-        seq_materialize_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, h->cin1, h->cum);
+        if (staged) CK(cudaFuncSetAttribute(xseq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+        xseq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(
+            n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2, h->cin1, h->opened, h->total,
+            h->fallbacks, staged, h->xp, h->xl.w[wbuf], h->xl.fbraw);
         CKL(h);
     }
     return MCL_OK;
@@ -243,14 +272,12 @@ int exchange_slices(mcl_engine* h, void* buf, size_t elem)
 #ifdef MCL_WITH_NCCL
     char* base = (char*)buf;
     ncclResult_t rc;
-    if (h->n % h->world == 0) {
-        const size_t count = (size_t)(h->n / h->world) * elem;
-        rc = ncclAllGather(base + (size_t)h->lo * elem, base, count, ncclChar, h->comm, h->stream);
-    } else {
+    {
         ncclGroupStart();
         rc = ncclSuccess;
         for (int r = 0; r < h->world && rc == ncclSuccess; ++r) {
-            const long long lo = h->n * r / h->world, hi = h->n * (r + 1) / h->world;
+            const long long lo = h->xp.lo[r], hi = h->xp.lo[r + 1];
+            if (hi <= lo) continue;
             rc = ncclBroadcast(base + (size_t)lo * elem, base + (size_t)lo * elem, (size_t)(hi - lo) * elem, ncclChar, r,
                                h->comm, h->stream);
         }
@@ -447,7 +474,8 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     const bool usable = h->params.sensor_path != 1 && h->num_beams > 0 && std::isfinite(Rc) && cpm > 0.0 &&
                         (double)h->params.min_range * cpm >= 2.5 && h->max_abs_theta <= 6.3f && h->ratio_lo >= -1.0 &&
                         h->ratio_hi <= 2.0 && w >= 3 && hh >= 3 && Cm <= 4090.0 && x0 >= -4 && y0 >= -4 &&
-                        pitch < (1 << 20) && max_dim + 8 < 4096;
+                        pitch < (1 << 20) && max_dim + 8 < 4096 &&
+                        h->num_beams <= 2048;     // score_deferred_kernel's queue entries hold 6 bits of mask-word index
     if (!usable) return fp;
     // v + 1.5*2^(23-FB) must stay in one binade for every coordinate whose bits are used: those inside the window
     const int fb = max_dim + 8 < 1024 ? 12 : (max_dim + 8 < 2048 ? 11 : 10);
@@ -485,6 +513,8 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     fp.coord_hi = (float)(Cm - 1.0);
     fp.reach = (float)(Rc * (1.0 + 1e-6) + 4.0);
     fp.grid_min_dim = (float)std::min(h->grid.width, h->grid.height);
+    fp.rho_abs = (float)(rho_max * (1.0 + 1e-6));
+    fp.ang_room = 9.5f - h->max_abs_theta;      // kFastTrigErr is measured for |angle| <= 9.5
     plan_set_window(fp, x0, y0, w, hh, pitch);
     if (fp.half_x <= 0.0f || fp.half_y <= 0.0f) { fp.enabled = 0; return fp; }
     h->stats_eps = eps;
@@ -582,14 +612,7 @@ int run_score(mcl_engine* h)
     const PoseSoA& p = h->pose[h->cur];
     const PoseSoA& q = h->parent[h->cur];
     a.x = p.x; a.y = p.y; a.th = p.th; a.px = q.x; a.py = q.y; a.pth = q.th;
-    if (h->world > 1 && h->peer_push) {
-        // every rank scores collectively, so the parities stay in lockstep
-        h->score_parity ^= 1;
-        h->score2 = h->score_block + (size_t)h->score_parity * (size_t)h->n;
-        a.num_peers = h->world;
-        for (int r = 0; r < h->world; ++r) a.peer_score[r] = h->peer_score2[r] + (size_t)h->score_parity * (size_t)h->n;
-    }
-    a.score2 = h->score2;
+    a.score2 = h->score2;           // every rank scores, floors and normalises its own slice: scores never travel
     a.fast_cells = h->map_fast;
     a.lo = h->lo; a.hi = h->hi;
     a.beams = h->beams; a.num_beams = h->num_beams;
@@ -605,14 +628,6 @@ int run_score(mcl_engine* h)
         if (tr == 1) {
             int rc = join_pushes(h);
             if (rc) return rc;
-            if (a.num_peers > 0) {
-                rc = rank_barrier(h);
-                if (rc) return rc;
-                ++h->collectives;
-            } else {
-                rc = exchange_slices(h, h->score2, sizeof(int32_t));
-                if (rc) return rc;
-            }
             h->stats.lanes_per_particle = 1;
             h->stats.map_tile_used = 4;
             h->stats.sensor_path = 3;
@@ -741,18 +756,10 @@ int run_score(mcl_engine* h)
         rc = launch_score(h, G, tile, batch, a, 0, smem + batch_tile_bytes, local);
     }
     if (rc) return rc;
+    // (the stream now waits for this rank's pose pushes; the normaliser's first barrier then makes every rank's pushes
+    // complete before anyone starts the next update)
     rc = join_pushes(h);
     if (rc) return rc;
-    if (a.num_peers > 0) {
-        // the sensor kernels already stored every final score into every rank's array; one 4-byte all-reduce makes all
-        // ranks' stores (and pose pushes) complete before anyone reads them
-        rc = rank_barrier(h);
-        if (rc) return rc;
-        ++h->collectives;
-    } else {
-        rc = exchange_slices(h, h->score2, sizeof(int32_t));
-        if (rc) return rc;
-    }
     h->stats.lanes_per_particle = G;
     h->stats.map_tile_used = batch ? 3 : (tile ? 2 : 1);
     h->stats.sensor_path = fast ? 2 : 1;
@@ -766,32 +773,44 @@ int run_normalize(mcl_engine* h)
 {
     if (!h->have_scores) return fail(h, MCL_ERR_STATE, "mcl_score has not run");
     double* w = h->weight[h->wcur];
+    const long long lo = h->lo, hi = h->hi, local = hi - lo;
+    const int g = grid_for(h, local, 256);
     if (h->params.weight_mode == 1) {
         // extension: w = exp(beta (s - max s)) / sum  (max / log-sum-exp normalisation)
+        if (h->world > 1) return fail(h, MCL_ERR_STATE, "weight_mode 1 runs on single-GPU engines");
         CK(cudaMemsetAsync(h->bbox, 0x80, sizeof(int), h->stream));          // 0x80808080: below every score
-        score_max_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, h->n, h->bbox);
+        score_max_kernel<<<g, 256, 0, h->stream>>>(h->score2, h->n, h->bbox);
         CKL(h);
-        lse_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->bbox, 0.5 * h->params.lse_beta);
+        lse_kernel<<<g, 256, 0, h->stream>>>(h->score2, w, h->n, h->bbox, 0.5 * h->params.lse_beta);
         CKL(h);
-    } else {
-        floor_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(h->score2, w, h->n, h->params.weight_floor);
+    } else if (local > 0) {
+        floor_kernel<<<g, 256, 0, h->stream>>>(h->score2 + lo, w + lo, local, h->params.weight_floor);
         CKL(h);
     }
-    int rc = seq_total(h, w, false);
+    int rc = seq_total(h, h->wcur);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->ess_acc, 0, sizeof(double), h->stream));
-    divide_kernel<<<grid_for(h, h->n, 256), 256, 0, h->stream>>>(w, h->n, h->total, h->ess_acc);
-    CKL(h);
+    if (local > 0) {
+        xdivide_kernel<<<g, 256, 0, h->stream>>>(w, lo, hi, h->total, h->ess_acc);
+        CKL(h);
+    }
     return MCL_OK;
 }
 
 int run_estimate(mcl_engine* h)
 {
     const PoseSoA& p = h->pose[h->cur];
-    estimate_partial_kernel<<<h->est_count, kEstBlock, 0, h->stream>>>(p.x, p.y, p.th, h->weight[h->wcur], h->n,
-                                                                      h->est_partials);
-    CKL(h);
-    estimate_final_kernel<<<1, kEstBlock, 0, h->stream>>>(h->est_partials, h->est_count, h->est_out);
+    const long long chunk_lo = h->lo / kEstChunk, chunk_hi = (h->hi + kEstChunk - 1) / kEstChunk;
+    if (chunk_hi > chunk_lo) {
+        xestimate_partial_kernel<<<(int)(chunk_hi - chunk_lo), kEstBlock, 0, h->stream>>>(
+            p.x, p.y, p.th, h->weight[h->wcur], h->n, chunk_lo, h->xp, h->xl.est, h->xl.est_w2);
+        CKL(h);
+    }
+    int rc = xbarrier(h, 2);
+    if (rc) return rc;
+    xestimate_final_kernel<<<1, kEstBlock, 0, h->stream>>>((const double4*)(h->xblock + h->xl.est),
+                                                          (const double*)(h->xblock + h->xl.est_w2), h->est_count,
+                                                          h->est_out, h->ess_acc);
     CKL(h);
     return MCL_OK;
 }
@@ -853,14 +872,28 @@ int upload_noise(mcl_engine* h, const float* noise3n, const float** dev_out)
     return MCL_OK;
 }
 
-int run_resample_indices(mcl_engine* h, double r, const double* w)
+int run_resample_indices(mcl_engine* h, double r, int wbuf)
 {
-    int rc = seq_total(h, w, true);
+    int rc = seq_total(h, wbuf);
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
-    resample_search_kernel<<<grid_for(h, (h->hi - h->lo + kSearchRun - 1) / kSearchRun, 128), 128, 0, h->stream>>>(h->cum, h->n, r, h->lo, h->hi,
-                                                                                 h->idx, h->overruns);
+    // materialise the exact running sum only where this rank's children draw from, then search
+    const long long n = h->n, n1 = h->n1, n2 = h->n2, local = h->hi - h->lo;
+    xresample_range_kernel<<<1, 32, 0, h->stream>>>(h->cin2, n2, n, r, h->lo, h->hi, h->xrange);
     CKL(h);
+    const long long groups_cap = h->world == 1 ? n2 : std::min<long long>(n2, 2 * ((local + kSliceAlign - 1) / kSliceAlign) + 64);
+    xseq_group_expand_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->q0, h->q1, n1, h->cin2, h->opened, h->cin1,
+                                                                         h->xrange);
+    CKL(h);
+    const long long tiles_cap = std::max<long long>(1, groups_cap * kL2 / kSeqTileChunks);
+    xseq_materialize_kernel<<<(int)std::min<long long>(tiles_cap, (long long)h->sm_count * 32), 128, 0, h->stream>>>(
+        n, n1, h->cin1, h->cum, h->xrange, h->xp, h->xl.w[wbuf]);
+    CKL(h);
+    CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
+    if (local > 0) {
+        xresample_search_kernel<<<grid_for(h, (local + kSearchRun - 1) / kSearchRun, 128), 128, 0, h->stream>>>(
+            h->cum, n, r, h->lo, h->hi, h->xrange, h->idx, h->overruns);
+        CKL(h);
+    }
     return MCL_OK;
 }
 
@@ -872,7 +905,10 @@ int read_counters(mcl_engine* h)
     CK(cudaMemcpyAsync(&h->host_counters[3], h->total, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->host_counters[4], h->ess_acc, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->host_counters[5], h->deferred_counter, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->host_counters[6], h->xblock + h->xl.err, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if ((int)(h->host_counters[6] & 0xffffffffu) != 0)
+        return fail(h, MCL_ERR_COMM, "a cross-rank barrier timed out (a peer rank stopped)");
     h->stats.deferred_evals = (int64_t)h->host_counters[5];
     h->stats.resample_overruns = (int64_t)h->host_counters[0];
     h->stats.gathers = h->count_gathers ? (int64_t)h->host_counters[1] : -1;
@@ -903,7 +939,7 @@ int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r
     h->launches = 0;
     h->collectives = 0;
     cudaEventRecord(h->ev[0], h->stream);
-    int rc = run_resample_indices(h, r, h->weight[h->wcur]);
+    int rc = run_resample_indices(h, r, h->wcur);
     if (rc) return rc;
     cudaEventRecord(h->ev[1], h->stream);
     rc = run_action(h, a, utime, noise_dev, true);
@@ -928,24 +964,21 @@ int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r
 void free_all(mcl_engine* h)
 {
     auto F = [](void* p) { if (p) cudaFree(p); };
-    for (int b = 0; b < 2; ++b) {
-        F(h->parent[b].x); F(h->parent[b].y); F(h->parent[b].th);
-        F(h->weight[b]);
-    }
+    for (int b = 0; b < 2; ++b) { F(h->parent[b].x); F(h->parent[b].y); F(h->parent[b].th); }
     for (size_t r = 0; r < h->peer_pose_block.size(); ++r)
         if (h->peer_pose_block[r] && h->peer_pose_block[r] != h->pose_block) cudaIpcCloseMemHandle(h->peer_pose_block[r]);
-    for (size_t r = 0; r < h->peer_score2.size(); ++r)
-        if (h->peer_score2[r] && h->peer_score2[r] != h->score_block) cudaIpcCloseMemHandle(h->peer_score2[r]);
-    F(h->pose_block); F(h->barrier_word);
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (h->xp.base[r] && h->xp.base[r] != h->xblock) cudaIpcCloseMemHandle(h->xp.base[r]);
+    F(h->pose_block); F(h->barrier_word); F(h->xblock); F(h->fb_count); F(h->xrange);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_action_done) cudaEventDestroy(h->ev_action_done);
     if (h->ev_push_done) cudaEventDestroy(h->ev_push_done);
     F(h->tile_sums); F(h->tile_excl);
-    F(h->score_block); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total); F(h->ebias); F(h->gebias);
-    F(h->opened); F(h->q0); F(h->q1); F(h->g0); F(h->g1); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
+    F(h->score_block); F(h->idx); F(h->cum); F(h->sums); F(h->cin1); F(h->cin2); F(h->total);
+    F(h->opened); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
     if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
     if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
-    F(h->ess_acc); F(h->bbox); F(h->est_partials); F(h->est_out); F(h->map); F(h->map_fast); F(h->beams); F(h->noise); F(h->staging);
+    F(h->ess_acc); F(h->bbox); F(h->est_out); F(h->map); F(h->map_fast); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
     if (h->host_bbox) cudaFreeHost(h->host_bbox);
@@ -1028,9 +1061,8 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
         h->pose[b].th = h->pose_block + (size_t)(3 * b + 2) * n;
         CKB(cudaMalloc((void**)&h->parent[b].x, 4 * n)); CKB(cudaMalloc((void**)&h->parent[b].y, 4 * n));
         CKB(cudaMalloc((void**)&h->parent[b].th, 4 * n));
-        CKB(cudaMalloc((void**)&h->weight[b], 8 * n));
     }
-    CKB(cudaMalloc((void**)&h->score_block, 4 * n * 2));
+    CKB(cudaMalloc((void**)&h->score_block, 4 * n));
     h->score2 = h->score_block;
     CKB(cudaMalloc((void**)&h->idx, 4 * n));
     CKB(cudaMalloc((void**)&h->cum, 8 * n));
@@ -1038,19 +1070,47 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMalloc((void**)&h->sums, 8 * n1)); CKB(cudaMalloc((void**)&h->cin1, 8 * n1));
     CKB(cudaMalloc((void**)&h->tile_sums, 8 * (n1 / kSeqTileChunks + 1)));
     CKB(cudaMalloc((void**)&h->tile_excl, 8 * (n1 / kSeqTileChunks + 1)));
-    CKB(cudaMalloc((void**)&h->ebias, 4 * n1)); CKB(cudaMalloc((void**)&h->q0, 8 * n1));
-    CKB(cudaMalloc((void**)&h->q1, 8 * n1));
-    CKB(cudaMalloc((void**)&h->cin2, 8 * n2)); CKB(cudaMalloc((void**)&h->gebias, 4 * n2));
-    CKB(cudaMalloc((void**)&h->opened, 4 * n2)); CKB(cudaMalloc((void**)&h->g0, 8 * n2));
-    CKB(cudaMalloc((void**)&h->g1, 8 * n2));
+    CKB(cudaMalloc((void**)&h->cin2, 8 * n2));
+    CKB(cudaMalloc((void**)&h->opened, 4 * n2));
+    h->est_count = (int)((h->n + kEstChunk - 1) / kEstChunk);
+    {   // the exchange block: everything another rank may write or read (mcl_shard.cuh)
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        XLayout& L = h->xl;
+        size_t off = 0;
+        L.w[0] = off; off = al(off + 8 * n);
+        L.w[1] = off; off = al(off + 8 * n);
+        L.q0 = off; off = al(off + 8 * n1);
+        L.q1 = off; off = al(off + 8 * n1);
+        L.eb = off; off = al(off + 4 * n1);
+        L.g0 = off; off = al(off + 8 * n2);
+        L.g1 = off; off = al(off + 8 * n2);
+        L.ge = off; off = al(off + 4 * n2);
+        L.tot = off; off = al(off + 8 * kMaxPeers);
+        L.est = off; off = al(off + sizeof(double4) * (size_t)h->est_count);
+        L.est_w2 = off; off = al(off + 8 * (size_t)h->est_count);
+        L.fbraw = off; off = al(off + 8 * (size_t)kMaxPeers * kFbSlots * kL1);
+        L.flags = off; off = al(off + 4 * (size_t)kXFlagSlots * kMaxPeers);
+        L.err = off; off = al(off + 4);
+        L.bytes = off;
+        CKB(cudaMalloc((void**)&h->xblock, L.bytes));
+        CKB(cudaMemset(h->xblock + L.q0, 0, L.bytes - L.q0));
+        h->weight[0] = (double*)(h->xblock + L.w[0]); h->weight[1] = (double*)(h->xblock + L.w[1]);
+        h->q0 = (long long*)(h->xblock + L.q0); h->q1 = (long long*)(h->xblock + L.q1); h->ebias = (int*)(h->xblock + L.eb);
+        h->g0 = (long long*)(h->xblock + L.g0); h->g1 = (long long*)(h->xblock + L.g1); h->gebias = (int*)(h->xblock + L.ge);
+        h->xp.world = 1; h->xp.rank = 0;
+        for (int r = 0; r < kMaxPeers; ++r) h->xp.base[r] = nullptr;
+        h->xp.base[0] = h->xblock;
+        h->xp.lo[0] = 0;
+        for (int r = 1; r <= kMaxPeers; ++r) h->xp.lo[r] = h->n;
+    }
+    CKB(cudaMalloc((void**)&h->fb_count, 4)); CKB(cudaMemset(h->fb_count, 0, 4));
+    CKB(cudaMalloc((void**)&h->xrange, 16)); CKB(cudaMemset(h->xrange, 0, 16));
     CKB(cudaMalloc((void**)&h->total, 8)); CKB(cudaMalloc((void**)&h->fallbacks, 8));
     CKB(cudaMalloc((void**)&h->overruns, 8)); CKB(cudaMalloc((void**)&h->gather_counter, 8));
     CKB(cudaMalloc((void**)&h->deferred_counter, 8)); CKB(cudaMemset(h->deferred_counter, 0, 8));
     CKB(cudaMalloc((void**)&h->ess_acc, 8)); CKB(cudaMalloc((void**)&h->bbox, 16));
     CKB(cudaMemset(h->total, 0, 8)); CKB(cudaMemset(h->fallbacks, 0, 8)); CKB(cudaMemset(h->overruns, 0, 8));
     CKB(cudaMemset(h->gather_counter, 0, 8)); CKB(cudaMemset(h->ess_acc, 0, 8));
-    h->est_count = (int)((h->n + kEstChunk - 1) / kEstChunk);
-    CKB(cudaMalloc((void**)&h->est_partials, sizeof(double4) * (size_t)h->est_count));
     CKB(cudaMalloc((void**)&h->est_out, 16));
     CKB(cudaMallocHost((void**)&h->est_host, 16));
     CKB(cudaMallocHost((void**)&h->host_bbox, 16));
@@ -1124,30 +1184,38 @@ int mcl_comm_unique_id(void* id128_out)
 int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
 {
     if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(h, MCL_ERR_INVALID, "bad comm arguments");
+    if (world > kMaxPeers) return fail(h, MCL_ERR_INVALID, "at most %d ranks (one NVLink domain)", kMaxPeers);
 #ifdef MCL_WITH_NCCL
     CK(cudaSetDevice(h->device));
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
     if (ncclCommInitRank(&h->comm, world, id, rank) != ncclSuccess) return fail(h, MCL_ERR_COMM, "ncclCommInitRank failed");
     h->rank = rank; h->world = world;
-    h->lo = h->n * rank / world;
-    h->hi = h->n * (rank + 1) / world;
+    // slices start at multiples of 8192 particles: chunks, groups and estimate partials never straddle ranks
+    h->xp.world = world; h->xp.rank = rank;
+    for (int r = 0; r <= kMaxPeers; ++r) {
+        long long b = r >= world ? h->n : (h->n * r / world) / kSliceAlign * kSliceAlign;
+        h->xp.lo[r] = b;
+    }
+    h->lo = h->xp.lo[rank];
+    h->hi = h->xp.lo[rank + 1];
     h->stats.local_particles = h->hi - h->lo;
     CK(cudaMalloc((void**)&h->barrier_word, sizeof(int)));
     CK(cudaMemset(h->barrier_word, 0, sizeof(int)));
-    // Map every peer's pose block (CUDA IPC over NVLink) so slices can be pushed by the copy engines.  All ranks must
-    // agree: if any mapping fails (or MCL_NO_PEER_PUSH is set) every rank keeps the NCCL all-gather path.
+    // Map every peer's pose block and exchange block (CUDA IPC over NVLink): pose slices are pushed by the copy engines,
+    // the sharded stages exchange their maps and partials by peer stores.  MCL_NO_PEER_PUSH keeps the poses on NCCL
+    // all-gathers (A/B); the exchange blocks are required.
     h->peer_pose_block.assign(world, nullptr);
     h->peer_pose_block[rank] = h->pose_block;
-    h->peer_score2.assign(world, nullptr);
-    h->peer_score2[rank] = h->score_block;
-    int ok = (world > 1 && world <= kMaxPeers && !std::getenv("MCL_NO_PEER_PUSH")) ? 1 : 0;
+    for (int r = 0; r < kMaxPeers; ++r) h->xp.base[r] = nullptr;
+    h->xp.base[rank] = h->xblock;
+    int ok = world > 1 ? 1 : 0;
     unsigned char* handles_dev = nullptr;
-    const size_t hsz = 2 * sizeof(cudaIpcMemHandle_t);          // per rank: pose block, score array
+    const size_t hsz = 2 * sizeof(cudaIpcMemHandle_t);          // per rank: pose block, exchange block
     std::vector<cudaIpcMemHandle_t> handles(2 * (size_t)world);
     CK(cudaMalloc((void**)&handles_dev, hsz * world));
     if (ok && cudaIpcGetMemHandle(&handles[2 * rank], h->pose_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    if (ok && cudaIpcGetMemHandle(&handles[2 * rank + 1], h->score_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&handles[2 * rank + 1], h->xblock) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     CK(cudaMemcpyAsync(handles_dev + hsz * rank, &handles[2 * rank], hsz, cudaMemcpyHostToDevice, h->stream));
     if (ncclAllGather(handles_dev + hsz * rank, handles_dev, hsz, ncclChar, h->comm, h->stream) != ncclSuccess)
         return fail(h, MCL_ERR_COMM, "NCCL handle exchange failed");
@@ -1159,7 +1227,7 @@ int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
         if (cudaIpcOpenMemHandle(&p, handles[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
         h->peer_pose_block[r] = (float*)p;
         if (cudaIpcOpenMemHandle(&p, handles[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-        h->peer_score2[r] = (int32_t*)p;
+        h->xp.base[r] = (unsigned char*)p;
     }
     CK(cudaMemcpyAsync(h->barrier_word, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (ncclAllReduce(h->barrier_word, h->barrier_word, 1, ncclInt, ncclMin, h->comm, h->stream) != ncclSuccess)
@@ -1167,7 +1235,10 @@ int mcl_comm_init(mcl_engine* h, const void* id128, int rank, int world)
     CK(cudaMemcpyAsync(&ok, h->barrier_word, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(handles_dev);
-    h->peer_push = ok != 0;
+    if (world > 1 && !ok)
+        return fail(h, MCL_ERR_COMM, "CUDA IPC mapping of the peers' exchange blocks failed (all ranks must be GPUs of one NVLink node)");
+    h->xpeer = world > 1;
+    h->peer_push = ok != 0 && !std::getenv("MCL_NO_PEER_PUSH");
     if (h->peer_push) {
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_action_done, cudaEventDisableTiming));
@@ -1242,6 +1313,8 @@ int mcl_map_update(mcl_engine* h, const mcl_pose_t* previous_pose, const mcl_pos
     if (!h || !previous_pose || !pose) return fail(h, MCL_ERR_INVALID, "null argument");
     if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
     if (num_ranges < 0 || (num_ranges > 0 && (!ranges || !thetas || !times))) return fail(h, MCL_ERR_INVALID, "bad scan arrays");
+    if (num_ranges > 65535)
+        return fail(h, MCL_ERR_INVALID, "map update: at most 65535 beams per scan (16-bit per-cell visit counters)");
     if (hit_odds < 0 || hit_odds > 127 || miss_odds < 0 || miss_odds > 127)
         return fail(h, MCL_ERR_INVALID, "hit/miss odds must be in [0, 127] (the parallel form relies on one-signed saturating adds)");
     if (rect_xywh_out) rect_xywh_out[0] = rect_xywh_out[1] = rect_xywh_out[2] = rect_xywh_out[3] = 0;
@@ -1425,6 +1498,8 @@ int mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int6
             int rc = exchange_slices(h, arr, sizeof(float));
             if (rc) return rc;
         }
+        int rc = exchange_slices(h, h->weight[h->wcur], sizeof(double));     // weights too: every rank normalises its own slice
+        if (rc) return rc;
     }
     if (count > 0) {
         int rc = ensure_staging(h, sizeof(mcl_particle_t) * (size_t)count);
@@ -1486,7 +1561,7 @@ int mcl_resample(mcl_engine* h, double r, const double* weights, int32_t* indice
     h->launches = 0;
     double* w = h->weight[h->wcur];
     if (weights) CK(cudaMemcpyAsync(w, weights, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
-    int rc = run_resample_indices(h, r, w);
+    int rc = run_resample_indices(h, r, h->wcur);
     if (rc) return rc;
     GatherArgs g{};
     const int s = h->cur, d = h->cur ^ 1;

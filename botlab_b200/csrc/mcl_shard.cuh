@@ -1,0 +1,535 @@
+// Sharded exact sequential sum, normaliser and estimate: every rank works on ITS slice of the particle order and the
+// ranks exchange only what the sequential dependency needs -- over NVLink, by peer stores into one CUDA-IPC-mapped
+// "exchange block" per rank, ordered by flag barriers in the same block (no collective call on the data path).
+//
+// The reference sums weights left to right in double (particle_filter.cpp:93-99, :126-133); mcl_kernels.cuh (K1) explains
+// how that sum is reproduced exactly from composable "add D[parity]" maps.  Sharded, per stage (resample / normalise):
+//   S1, S2  rank r: plain chunk sums of its slice, scan of its tiles, slice total  -> totals[r] on every rank   (8 B)
+//   -- barrier A --
+//   S3      rank r: binade guess from (sum of the lower ranks' totals + its own scan), level-1 maps of its chunks
+//                   -> q0/q1/ebias[k] on every rank (20 B per 128 particles); the raw weights of the few chunks whose
+//                   running sum may cross a binade edge -> side buffer on every rank (1 KB per such chunk)
+//   S4      rank r: level-2 maps of its groups -> g0/g1/gebias[j] on every rank (20 B per 8192 particles)
+//   -- barrier B --
+//   S5      every rank: the walk over all groups (redundant, and local: everything it can need was pushed)
+//           -> exact total, exact entry sum of every group
+//   resample only: S6/S7 materialise the exact running sum for the groups THIS rank's children draw from (their
+//           weights are read from the owning rank over NVLink), then the search over its own children.
+// Slices start at multiples of kL1 * kL2 = 8192 particles, so chunks, groups and the estimate's 4096-particle partials
+// never straddle ranks; results do not depend on the partition (the maps compose associatively; the walk verifies
+// every assumption against exact values).
+#pragma once
+#include "mcl_kernels.cuh"
+
+namespace mcl {
+
+constexpr int kSliceAlign = kL1 * kL2;          // 8192
+constexpr int kFbSlots = 256;                   // raw-chunk side buffer: slots per source rank
+constexpr int kXFlagSlots = 16;
+
+// Byte offsets inside a rank's exchange block (identical on every rank).
+struct XLayout {
+    size_t w[2];            // weights, double-buffered: [N] doubles each (only the owner's slice is meaningful)
+    size_t q0, q1, eb;      // level-1 maps: [n1] int64, [n1] int64, [n1] int32
+    size_t g0, g1, ge;      // level-2 maps: [n2]
+    size_t tot;             // [kMaxPeers] doubles: approximate slice totals
+    size_t est;             // [est_count] double4 + [est_count] double (sum w^2)
+    size_t est_w2;
+    size_t fbraw;           // [kMaxPeers][kFbSlots][kL1] doubles
+    size_t flags;           // [kXFlagSlots][kMaxPeers] ints
+    size_t err;             // int: barrier timeout
+    size_t bytes;
+};
+
+struct XPeers {
+    int world, rank;
+    unsigned char* base[kMaxPeers];     // exchange block of every rank (own entry = local block)
+    long long lo[kMaxPeers + 1];        // slice boundaries: rank r owns [lo[r], lo[r+1])
+};
+
+__host__ __device__ inline int xowner(const XPeers& xp, long long elem)
+{
+    int r = 0;
+    while (r + 1 < xp.world && elem >= xp.lo[r + 1]) ++r;
+    return r;
+}
+
+// ---- flag barrier -------------------------------------------------------------------------------------------------
+// signal: after everything this rank enqueued before it (kernel boundary), tell every rank "rank `rank` reached `epoch`
+// on slot `slot`".  wait: spin until every rank has.  Epochs only grow, so a fast rank can never be mistaken.
+__global__ void xsignal_kernel(const XPeers xp, size_t flags_off, int slot, int epoch)
+{
+    const int r = threadIdx.x;
+    if (r < xp.world) {
+        __threadfence_system();
+        volatile int* f = reinterpret_cast<volatile int*>(xp.base[r] + flags_off) + slot * kMaxPeers + xp.rank;
+        *f = epoch;
+        __threadfence_system();
+    }
+}
+
+__global__ void xwait_kernel(unsigned char* base, size_t flags_off, size_t err_off, int slot, int epoch, int world)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        volatile int* f = reinterpret_cast<volatile int*>(base + flags_off) + slot * kMaxPeers + r;
+        const long long t0 = clock64();
+        while (*f < epoch) {
+            if (clock64() - t0 > 20000000000ll) {       // ~10 s: a peer died; do not hang the GPU
+                *reinterpret_cast<volatile int*>(base + err_off) = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+// ---- S1: plain per-chunk sums and per-tile totals of the slice's tiles [tile_lo, tile_lo + gridDim.x) -----------------
+__global__ void __launch_bounds__(128) xseq_chunk_sums_kernel(const double* w, long long n, long long n1, long long tile_lo,
+                                                              double* sums, double* tile_sums)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    const long long tidx = tile_lo + blockIdx.x;
+    const long long chunk0 = tidx * kSeqTileChunks;
+    seq_stage(w, n, chunk0 * kL1, tile);
+    __syncthreads();
+    if (threadIdx.x < kSeqTileChunks) {
+        double s = 0.0;
+        if (chunk0 + threadIdx.x < n1) {
+            const double* row = tile + threadIdx.x * kSeqRowPitch;
+#pragma unroll 8
+            for (int i = 0; i < kL1; ++i) s += row[i];
+            sums[chunk0 + threadIdx.x] = s;
+        }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) tile_sums[tidx] = s;
+    }
+}
+
+// ---- S2: exclusive scan of the slice's tile totals (slice-relative) + the slice total to every rank ----------------------
+__global__ void __launch_bounds__(1024) xseq_tile_scan_kernel(const double* tile_sums, long long tile_lo, long long tile_hi,
+                                                              double* tile_excl, const XPeers xp, size_t tot_off)
+{
+    __shared__ double warp_tot[32];
+    __shared__ double carry_s;
+    if (threadIdx.x == 0) carry_s = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (long long base = tile_lo; base < tile_hi; base += 1024) {
+        const long long k = base + threadIdx.x;
+        const double v = k < tile_hi ? tile_sums[k] : 0.0;
+        double inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            double t = warp_tot[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, t, off);
+                if (lane >= off) t += u;
+            }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const double incl = carry_s + (wid ? warp_tot[wid - 1] : 0.0) + inc;
+        if (k < tile_hi) tile_excl[k] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < xp.world)
+        reinterpret_cast<double*>(xp.base[threadIdx.x] + tot_off)[xp.rank] = carry_s;
+}
+
+// ---- S3: level-1 maps of the slice's chunks, pushed to every rank ----------------------------------------------------------
+struct XSeqOut { size_t q0, q1, eb, fbraw; };
+__global__ void __launch_bounds__(128) xseq_chunk_maps_kernel(const double* w, long long n, long long n1, long long tile_lo,
+                                                              const double* sums, const double* tile_excl,
+                                                              const double* totals, int* fb_count, const XPeers xp,
+                                                              const XSeqOut o)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    __shared__ int s_slot[kSeqTileChunks];
+    const long long tidx = tile_lo + blockIdx.x;
+    const long long chunk0 = tidx * kSeqTileChunks;
+    seq_stage(w, n, chunk0 * kL1, tile);
+    __syncthreads();
+    const long long k = chunk0 + threadIdx.x;
+    if (threadIdx.x < kSeqTileChunks) {                 // warp 0, all 32 lanes (shuffles below)
+        double below = 0.0;                             // approximate sum of the lower ranks' slices (fixed order)
+        for (int r = 0; r < xp.rank; ++r) below += totals[r];
+        const double v = k < n1 ? sums[k] : 0.0;
+        double inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)threadIdx.x >= off) inc += t;
+        }
+        const double incl = below + tile_excl[tidx] + inc, excl = incl - v;
+        const double lo = excl * (1.0 - 1e-6), hi = incl * (1.0 + 1e-6);
+        const int elo = dbl_exp(lo), ehi = dbl_exp(hi);
+        int e = (lo > 0.0 && elo == ehi && elo > 60 && elo < 1900) ? elo : 0;
+        long long f0 = 0, f1 = 0;
+        if (k < n1 && e != 0) {
+            const double base0 = __longlong_as_double((long long)e << 52);
+            const double ulp = __longlong_as_double((long long)(e - 52) << 52);
+            const double base1 = base0 + ulp;
+            const double top = base0 + base0;
+            const double* row = tile + threadIdx.x * kSeqRowPitch;
+            double c0 = base0, c1 = base1;
+#pragma unroll 8
+            for (int i = 0; i < kL1; ++i) {
+                const double vv = row[i];
+                c0 = __dadd_rn(c0, vv);
+                c1 = __dadd_rn(c1, vv);
+            }
+            if (c0 < top && c1 < top && c0 >= base0 && c1 >= base1) {
+                f0 = __double_as_longlong(c0) - __double_as_longlong(base0);   // same binade: bit patterns count ulps
+                f1 = __double_as_longlong(c1) - __double_as_longlong(base1);
+            } else {
+                e = 0;
+            }
+        }
+        // chunks that will be added element by element: their raw weights go to every rank's side buffer
+        int slot = -1;
+        if (k < n1 && e == 0 && xp.world > 1) {
+            slot = atomicAdd(fb_count, 1);
+            if (slot >= kFbSlots) slot = -1;
+        }
+        s_slot[threadIdx.x] = slot;
+        if (k < n1) {
+            if (e == 0) f0 = slot;
+            for (int r = 0; r < xp.world; ++r) {
+                reinterpret_cast<long long*>(xp.base[r] + o.q0)[k] = f0;
+                reinterpret_cast<long long*>(xp.base[r] + o.q1)[k] = f1;
+                reinterpret_cast<int*>(xp.base[r] + o.eb)[k] = e;
+            }
+        }
+        __syncwarp();
+        if (xp.world > 1) {
+            for (int c = 0; c < kSeqTileChunks; ++c) {
+                const int sl = s_slot[c];
+                if (sl < 0) continue;
+                const double* row = tile + c * kSeqRowPitch;
+                for (int r = 0; r < xp.world; ++r) {
+                    double* dst = reinterpret_cast<double*>(xp.base[r] + o.fbraw) + ((size_t)xp.rank * kFbSlots + sl) * kL1;
+                    for (int i = threadIdx.x; i < kL1; i += 32) dst[i] = row[i];
+                }
+            }
+        }
+    }
+}
+
+// ---- S4: level-2 maps of the slice's groups [group_lo, group_hi), pushed to every rank ---------------------------------------
+__global__ void xseq_group_maps_kernel(const int* ebias, const long long* q0, const long long* q1, long long n1,
+                                       long long group_lo, long long group_hi, const XPeers xp, size_t g0_off,
+                                       size_t g1_off, size_t ge_off)
+{
+    const long long j = group_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= group_hi) return;
+    const long long first = j * kL2;
+    const long long last = first + kL2 < n1 ? first + kL2 : n1;
+    const int e = ebias[first];
+    bool ok = e != 0;
+    long long a0 = 0, a1 = 0;
+    for (long long k = first; k < last && ok; ++k) {
+        if (ebias[k] != e) { ok = false; break; }
+        const long long f0 = q0[k], f1 = q1[k];
+        a0 += ((a0 & 1) ? f1 : f0);
+        a1 += (((a1 + 1) & 1) ? f1 : f0);
+    }
+    for (int r = 0; r < xp.world; ++r) {
+        reinterpret_cast<long long*>(xp.base[r] + g0_off)[j] = a0;
+        reinterpret_cast<long long*>(xp.base[r] + g1_off)[j] = a1;
+        reinterpret_cast<int*>(xp.base[r] + ge_off)[j] = ok ? e : 0;
+    }
+}
+
+// ---- S5: the walk (one warp; the CTA stages the group maps).  As seq_walk_kernel, except that the raw weights of a
+// chunk that has to be added element by element come from the side buffer (or, failing that, from the owner's weights
+// over NVLink) ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long n1, long long n2, const int* ebias,
+                                                       const long long* q0, const long long* q1, const int* gebias,
+                                                       const long long* g0, const long long* g1, double* cin2, double* cin1,
+                                                       int* opened, double* total, long long* fallback_chunks, int staged,
+                                                       const XPeers xp, size_t w_off, size_t fbraw_off)
+{
+    __shared__ double fb_chunk[kL1];
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    long long* sg0 = reinterpret_cast<long long*>(walk_smem);
+    long long* sg1 = sg0 + (staged ? n2 : 0);
+    int* sge = reinterpret_cast<int*>(sg1 + (staged ? n2 : 0));
+    if (staged) {
+        for (long long j = threadIdx.x; j < n2; j += blockDim.x) { sg0[j] = g0[j]; sg1[j] = g1[j]; sge[j] = gebias[j]; }
+        __syncthreads();
+    }
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    double c = 0.0;
+    long long fallbacks = 0;
+    for (long long jb = 0; jb < n2; jb += 32) {
+        const long long jl = jb + lane;
+        const int ge_l = jl < n2 ? (staged ? sge[jl] : gebias[jl]) : 0;
+        const long long g0_l = jl < n2 ? (staged ? sg0[jl] : g0[jl]) : 0, g1_l = jl < n2 ? (staged ? sg1[jl] : g1[jl]) : 0;
+        const int cnt = (int)(n2 - jb < 32 ? n2 - jb : 32);
+        double cin_l;
+        if (seq_apply_warp(c, cnt, ge_l, g0_l, g1_l, cin_l)) {
+            if (lane < cnt) { cin2[jl] = cin_l; opened[jl] = 0; }
+            continue;
+        }
+        for (int t = 0; t < cnt; ++t) {
+            const long long j = jb + t;
+            const int ge = __shfl_sync(0xffffffffu, ge_l, t);
+            const long long m0 = __shfl_sync(0xffffffffu, g0_l, t), m1 = __shfl_sync(0xffffffffu, g1_l, t);
+            if (lane == 0) cin2[j] = c;
+            if (seq_apply(c, ge, m0, m1)) {
+                if (lane == 0) opened[j] = 0;
+                continue;
+            }
+            if (lane == 0) opened[j] = 1;
+            const long long kfirst = j * kL2;
+            const long long klast = kfirst + kL2 < n1 ? kfirst + kL2 : n1;
+            for (long long kb = kfirst; kb < klast; kb += 32) {
+                const long long kl = kb + lane;
+                const int e_l = kl < klast ? ebias[kl] : 0;
+                const long long f0_l = kl < klast ? q0[kl] : 0, f1_l = kl < klast ? q1[kl] : 0;
+                const int kc = (int)(klast - kb < 32 ? klast - kb : 32);
+                if (seq_apply_warp(c, kc, e_l, f0_l, f1_l, cin_l)) {
+                    if (lane < kc) cin1[kl] = cin_l;
+                    continue;
+                }
+                for (int s = 0; s < kc; ++s) {
+                    const long long k = kb + s;
+                    const int e = __shfl_sync(0xffffffffu, e_l, s);
+                    const long long f0 = __shfl_sync(0xffffffffu, f0_l, s), f1 = __shfl_sync(0xffffffffu, f1_l, s);
+                    if (lane == 0) cin1[k] = c;
+                    if (seq_apply(c, e, f0, f1)) continue;
+                    ++fallbacks;
+                    const long long efirst = k * kL1;
+                    const int owner = xowner(xp, efirst);
+                    // raw weights of the chunk: own slice -> local weights; pushed by the owner -> side buffer; else the
+                    // owner's weights over NVLink
+                    const double* src;
+                    bool bounded = true;
+                    if (owner == xp.rank) src = reinterpret_cast<const double*>(xp.base[xp.rank] + w_off) + efirst;
+                    else if (e == 0 && f0 >= 0) {
+                        src = reinterpret_cast<const double*>(xp.base[xp.rank] + fbraw_off) + ((size_t)owner * kFbSlots + (size_t)f0) * kL1;
+                        bounded = false;            // the side buffer is zero padded past n
+                    } else src = reinterpret_cast<const double*>(xp.base[owner] + w_off) + efirst;
+                    double v_l[kL1 / 32];
+#pragma unroll
+                    for (int q = 0; q < kL1 / 32; ++q) {
+                        const long long gi = efirst + q * 32 + lane;
+                        v_l[q] = (!bounded || gi < n) ? src[q * 32 + lane] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
+                    __syncwarp();
+#pragma unroll 16
+                    for (int i = 0; i < kL1; ++i) c = __dadd_rn(c, fb_chunk[i]);
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        *total = c;
+        *fallback_chunks = fallbacks;
+    }
+}
+
+// ---- resampling: which groups do this rank's children draw from? ---------------------------------------------------------
+// Child m compares U_m = r + m/N with the running sum; its parent lies in the last group whose ENTRY sum is below U_m.
+// range[0], range[1] = first and last such group over the rank's children [lo, hi).
+__global__ void xresample_range_kernel(const double* cin2, long long n2, long long n, double r, long long lo, long long hi,
+                                       long long* range)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double m_inv = __ddiv_rn(1.0, (double)n);
+    auto last_below = [&](double u) {
+        long long a = 0, b = n2;                 // first j with !(cin2[j] < u)
+        while (a < b) {
+            const long long mid = (a + b) >> 1;
+            if (cin2[mid] < u) a = mid + 1; else b = mid;
+        }
+        return a > 0 ? a - 1 : 0;
+    };
+    if (hi <= lo) { range[0] = 0; range[1] = -1; return; }
+    range[0] = last_below(__dadd_rn(r, __dmul_rn((double)lo, m_inv)));
+    range[1] = last_below(__dadd_rn(r, __dmul_rn((double)(hi - 1), m_inv)));
+}
+
+// S6 for the groups in range: entry sums of their chunks (opened groups already have theirs from the walk).
+__global__ void xseq_group_expand_kernel(const long long* q0, const long long* q1, long long n1, const double* cin2,
+                                         const int* opened, double* cin1, const long long* range)
+{
+    const long long j = range[0] + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j > range[1] || opened[j]) return;
+    const long long first = j * kL2;
+    const long long last = first + kL2 < n1 ? first + kL2 : n1;
+    long long bits = __double_as_longlong(cin2[j]);
+    for (long long k = first; k < last; ++k) {
+        cin1[k] = __longlong_as_double(bits);
+        bits += (bits & 1) ? q1[k] : q0[k];
+    }
+}
+
+// S7 for the chunks of the groups in range: exact running sum per element; weights come from the owning rank.
+__global__ void __launch_bounds__(128) xseq_materialize_kernel(long long n, long long n1, const double* cin1, double* cum,
+                                                               const long long* range, const XPeers xp, size_t w_off)
+{
+    __shared__ double tile[kSeqTileChunks * kSeqRowPitch];
+    const long long tile_first = range[0] * kL2 / kSeqTileChunks, tile_last = ((range[1] + 1) * kL2 - 1) / kSeqTileChunks;
+    for (long long tidx = tile_first + blockIdx.x; tidx <= tile_last && range[1] >= range[0]; tidx += gridDim.x) {
+        const long long chunk0 = tidx * kSeqTileChunks;
+        const long long efirst = chunk0 * kL1;
+        if (efirst >= n) break;
+        const double* w = reinterpret_cast<const double*>(xp.base[xowner(xp, efirst)] + w_off);     // a tile never straddles ranks
+        __syncthreads();
+        seq_stage(w, n, efirst, tile);
+        __syncthreads();
+        const long long k = chunk0 + threadIdx.x;
+        if (threadIdx.x < kSeqTileChunks && k < n1) {
+            double* row = tile + threadIdx.x * kSeqRowPitch;
+            double c = cin1[k];
+#pragma unroll 8
+            for (int i = 0; i < kL1; ++i) {
+                c = __dadd_rn(c, row[i]);
+                row[i] = c;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSeqTileChunks * kL1; i += blockDim.x) {
+            const long long g = efirst + i;
+            if (g < n) cum[g] = tile[(i / kL1) * kSeqRowPitch + (i % kL1)];
+        }
+    }
+}
+
+// Systematic search over the materialised range (same indices as resample_search_kernel over the whole array).
+__global__ void xresample_search_kernel(const double* cum, long long n, double r, long long lo, long long hi,
+                                        const long long* range, int32_t* idx, unsigned long long* overruns)
+{
+    const double m_inv = __ddiv_rn(1.0, (double)n);
+    const long long first = range[0] * (long long)kSliceAlign;
+    const long long lim = (range[1] + 1) * (long long)kSliceAlign < n ? (range[1] + 1) * (long long)kSliceAlign : n;
+    const long long runs = (hi - lo + kSearchRun - 1) / kSearchRun;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < runs; t += (long long)gridDim.x * blockDim.x) {
+        const long long m0 = lo + t * kSearchRun;
+        const long long m1 = m0 + kSearchRun < hi ? m0 + kSearchRun : hi;
+        long long a = first;
+        for (long long m = m0; m < m1; ++m) {
+            const double u = __dadd_rn(r, __dmul_rn((double)m, m_inv));
+            int steps = 0;
+            if (m != m0)
+                while (a < lim && u > cum[a] && steps < 32) { ++a; ++steps; }
+            if (m == m0 || steps == 32) {
+                long long b = lim;
+                while (a < b) {
+                    const long long mid = (a + b) >> 1;
+                    if (u > cum[mid]) a = mid + 1; else b = mid;
+                }
+            }
+            long long out = a;
+            if (out >= n) { out = n - 1; atomicAdd(overruns, 1ull); }
+            idx[m] = (int32_t)out;
+        }
+    }
+}
+
+// ---- normaliser and estimate over the slice -----------------------------------------------------------------------------------
+// particle_filter.cpp:136-138: w /= wSum (IEEE double division, correctly rounded on both sides).  ess_acc collects the
+// slice's sum of squares (a statistic; the estimate's final reduction replaces it with the deterministic global one).
+__global__ void xdivide_kernel(double* w, long long lo, long long hi, const double* wsum, double* ess_acc)
+{
+    const double s = *wsum;
+    double sq = 0.0;
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        const double q = __ddiv_rn(w[i], s);
+        w[i] = q;
+        sq += q * q;
+    }
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(ess_acc, sq);
+}
+
+// Partials of (sum w x, sum w y, sum w sinf, sum w cosf) and of sum w^2 over the slice's 4096-particle chunks
+// [chunk_lo, chunk_lo + gridDim.x), pushed to every rank.
+__global__ void __launch_bounds__(kEstBlock) xestimate_partial_kernel(const float* x, const float* y, const float* th,
+                                                                      const double* w, long long n, long long chunk_lo,
+                                                                      const XPeers xp, size_t est_off, size_t w2_off)
+{
+    __shared__ double4 red[kEstBlock];
+    __shared__ double red2[kEstBlock];
+    const long long cidx = chunk_lo + blockIdx.x;
+    const long long base = cidx * kEstChunk;
+    double4 acc = make_double4(0, 0, 0, 0);
+    double acc2 = 0.0;
+    for (int k = threadIdx.x; k < kEstChunk; k += kEstBlock) {
+        const long long i = base + k;
+        if (i < n) {
+            const double wi = w[i];
+            float s, c;
+            glibc_sincosf(th[i], &s, &c);
+            acc.x = __dadd_rn(acc.x, __dmul_rn(wi, (double)x[i]));
+            acc.y = __dadd_rn(acc.y, __dmul_rn(wi, (double)y[i]));
+            acc.z = __dadd_rn(acc.z, __dmul_rn(wi, (double)s));
+            acc.w = __dadd_rn(acc.w, __dmul_rn(wi, (double)c));
+            acc2 = __dadd_rn(acc2, __dmul_rn(wi, wi));
+        }
+    }
+    red[threadIdx.x] = acc;
+    red2[threadIdx.x] = acc2;
+    __syncthreads();
+    for (int off = kEstBlock / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            double4 o = red[threadIdx.x + off], m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[threadIdx.x] = m;
+            red2[threadIdx.x] += red2[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < xp.world) {
+        reinterpret_cast<double4*>(xp.base[threadIdx.x] + est_off)[cidx] = red[0];
+        reinterpret_cast<double*>(xp.base[threadIdx.x] + w2_off)[cidx] = red2[0];
+    }
+}
+
+// out4 = (x, y, theta, unused) as floats, ess_acc = sum w^2; single block, fixed order.
+__global__ void __launch_bounds__(kEstBlock) xestimate_final_kernel(const double4* partials, const double* w2, int count,
+                                                                    float* out4, double* ess_acc)
+{
+    __shared__ double4 red[kEstBlock];
+    __shared__ double red2[kEstBlock];
+    double4 acc = make_double4(0, 0, 0, 0);
+    double acc2 = 0.0;
+    for (int k = threadIdx.x; k < count; k += kEstBlock) {
+        const double4 p = partials[k];
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        acc2 += w2[k];
+    }
+    red[threadIdx.x] = acc;
+    red2[threadIdx.x] = acc2;
+    __syncthreads();
+    for (int off = kEstBlock / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            double4 o = red[threadIdx.x + off], m = red[threadIdx.x];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[threadIdx.x] = m;
+            red2[threadIdx.x] += red2[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out4[0] = (float)red[0].x;
+        out4[1] = (float)red[0].y;
+        out4[2] = (float)atan2(red[0].z, red[0].w);
+        out4[3] = 0.0f;
+        *ess_acc = red2[0];
+    }
+}
+
+}  // namespace mcl

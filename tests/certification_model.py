@@ -63,6 +63,7 @@ class Plan:
         self.t_dir = F(3.0 * (1.0 + self.eps) + 4.0 * U * rc_max + 1e-4)
         self.t_dir_neg = F(5.0 * (1.0 + self.eps) + 4.0 * U * rc_max + 1e-4)
         self.rho_lo, self.rho_hi, self.max_shift, self.coord_hi = F(rho_lo), F(rho_hi), F(shift), F(cm - 1.0)
+        self.rho_abs, self.ang_room = F(rho_max * (1 + 1e-6)), F(9.5) - F(float(np.abs(thetas[valid]).max()))
         # window-dependent part (plan_set_window): everything below is in window-relative cells
         self.x0, self.y0 = x0, y0
         x2_min = 3.0 * self.eps + 1e-3
@@ -133,7 +134,8 @@ def fast_pass(grid, plan, particle, ranges, thetas, ratios, min_range, fast_cell
             fma32(dsy * one, plan.rho_lo, gyb * one)[0], fma32(dsy * one, plan.rho_hi, gyb * one)[0]]
     lo, hi = min(ends), max(ends)
     ok = (lo >= 1.0 and hi <= plan.coord_hi and abs(dsx) <= plan.max_shift and abs(dsy) <= plan.max_shift
-          and abs(th0) <= F(3.15) and abs(dth) <= F(3.15))
+          and abs(th0) <= F(3.15) and abs(dth) <= F(3.15)
+          and fma32(plan.rho_abs, abs(dth), abs(th0)) <= plan.ang_room)
     if not ok:
         return np.zeros(n, np.int64), np.zeros(n, bool)
     sx = fma32(dsx * one, rho, sxb * one) if interp else sxb * one

@@ -554,6 +554,20 @@ def test_two_pass_hostile_scans(real_map):
             e.close()
 
 
+def test_scan_with_more_than_2048_beams(real_map):
+    """Both certified passes index beams with 11 bits in their deferral queues; a longer scan must take the exact path
+    (or a wider encoding), never a truncated beam index: scores equal the oracle's."""
+    nb = 2500
+    r0, th0, t0 = synth.make_scan(real_map, (0.5, -0.25, 0.3), num_beams=nb, seed=9)
+    cloud = synth.make_particles(3000, (0.5, -0.25, 0.3), seed=9, parent_utime=int(t0[0]), pose_utime=int(t0[-1]))
+    want, _, _ = port.likelihood(port_grid(real_map), cloud, r0, th0, t0)
+    for path in (0, 2):
+        e = make_engine(len(cloud), real_map, sensor_path=path)
+        e.import_particles(cloud)
+        assert np.array_equal(e.score(r0, th0, t0), want), path
+        e.close()
+
+
 def test_fast_trig_error_bound():
     """kFastTrigErr (mcl_device.cuh) must bound the SFU sine/cosine error over EVERY float the float pass can feed it."""
     e = engine.Engine(16)
@@ -710,14 +724,22 @@ def test_map_update_edge_cases(real_map):
     e.close()
 
 
-def test_config4_full_size_two_pass_equals_exact():
-    """BASELINE configs[3] at full size (16 M particles x 360 beams, 2000 x 2000 grid): the default two-pass sensor path
-    and the literal restatement give the same 16 M scores, hence the same weight sum, estimate and resampled cloud."""
+@pytest.mark.parametrize("placement", ["interior", "bench"])
+def test_config4_full_size_two_pass_equals_exact(placement):
+    """BASELINE configs[3] at full size (16 M particles x 360 beams, 2000 x 2000 grid): the default sensor path (the
+    score-table pass where the window fits: bench.py's own workload; else the two-pass path), the two-pass path and the
+    literal restatement give the same 16 M scores, hence the same weight sum, estimate and resampled cloud -- and a
+    sub-sample of those scores (every 10 007th particle) equals the ORACLE's, so the three cannot be wrong together."""
     n, side = synth.CONFIGS["config4"]
-    rng = np.random.default_rng(4)
-    grid = synth.make_map(side, seed=synth.MAP_SEED + 4)
-    truth = synth.find_free_pose(grid, rng)
-    r, th, t = synth.make_scan(grid, truth, seed=4)
+    if placement == "bench":
+        import bench
+        _, grid, truth, scans = bench.build_workload("config4")
+        _, r, th, t = scans[1]
+    else:
+        rng = np.random.default_rng(4)
+        grid = synth.make_map(side, seed=synth.MAP_SEED + 4)
+        truth = synth.find_free_pose(grid, rng)
+        r, th, t = synth.make_scan(grid, truth, seed=4)
     am = engine.ActionModel()
     am.update(*truth, int(t[0]) - 100_000)
     assert am.update(truth[0] + 0.02, truth[1] + 0.01, truth[2] + 0.01, int(t[-1]))
@@ -727,22 +749,26 @@ def test_config4_full_size_two_pass_equals_exact():
         e.init_at_pose(*truth, utime=int(t[0]) - 100_000, seed=21)
         est = e.update(am, int(t[-1]), r, th, t, 0.8401877171547095 / n)
         st = e.stats()
-        assert st["sensor_path"] == {0: 3, 2: 2, 1: 1}[path]
+        assert st["sensor_path"] == {0: (3 if placement == "bench" else 2), 2: 2, 1: 1}[path]
         scores = e.score(r, th, t)                   # same cloud, same scan: the stage alone, all 16 M scores
+        sub = e.export_particles(stride=10_007)
         am2 = engine.ActionModel()
         am2.c = type(am.c).from_buffer_copy(am.c)
         est2 = e.update(am2, int(t[-1]) + 1, r, th, t, 0.3 / n)      # resamples from the weights of the first update
         out[path] = (scores, st["weight_sum"], (est.x, est.y, est.theta), (est2.x, est2.y, est2.theta),
-                     e.export_particles(stride=1009), st["deferred_evals"], st["evals"])
+                     e.export_particles(stride=1009), st["deferred_evals"], st["evals"], sub)
         e.close()
     b = out[1]
-    for a in (out[0], out[2]):
+    want, _, _ = port.likelihood(port_grid(grid), b[7], r, th, t)       # oracle on ~1600 of the 16 M particles
+    for a in (out[0], out[2], out[1]):
+        assert np.array_equal(a[0][::10_007], want)
         assert np.array_equal(a[0], b[0])
         assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
         for k in ("pose", "parent_pose"):
             for f in ("x", "y", "theta"):
                 assert np.array_equal(a[4][k][f], b[4][k][f])
         assert np.array_equal(a[4]["weight"], b[4]["weight"])
+    for a in (out[0], out[2]):
         assert 0 < a[5] < 0.2 * a[6] and b[5] == 0
 
 
@@ -843,12 +869,16 @@ def test_scoring_follows_device_map_updates(path):
     e = make_engine(len(cloud), grid, sensor_path=path)
     e.import_particles(cloud)
     cells = grid.cells.copy()
+    seen = set()
 
     def check(tag):
         g = synth.GridSpec(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
         want, _, _ = port.likelihood(port_grid(g), cloud, r, th, t)
         assert np.array_equal(e.score(r, th, t), want), tag
-        assert e.stats()["sensor_path"] == (3 if path == 0 else 2)
+        # (path 0: the score-table pass, until a map whose table overflows shared memory -- the random map of the last
+        # step -- sends it back to the two-pass path; that launch itself scores everything exactly)
+        seen.add(e.stats()["sensor_path"])
+        assert e.stats()["sensor_path"] in ((2, 3) if path == 0 else (2,))
 
     check("initial")
     prv = (pose[0] - 0.03, pose[1], pose[2], int(t[0]))
@@ -866,4 +896,5 @@ def test_scoring_follows_device_map_updates(path):
     cells = np.where(rng.random(cells.shape) < 0.01, 50, -5).astype(np.int8)
     e.set_map(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
     check("set_map")
+    assert (3 in seen) == (path == 0)
     e.close()

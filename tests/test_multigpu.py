@@ -10,9 +10,15 @@ import pytest
 from conftest import ROOT
 
 
+SLICE_ALIGN = 8192      # kSliceAlign (mcl_shard.cuh): chunks, groups and estimate partials never straddle ranks
+
+
 def slice_bounds(n, rank, world):
-    """Rank r owns the global particle slice [n*r/world, n*(r+1)/world) (mcl_comm_init)."""
-    return n * rank // world, n * (rank + 1) // world
+    """Rank r owns the global particle slice [b(r), b(r+1)), b(r) = n*r/world rounded down to a multiple of 8192,
+    b(world) = n (mcl_comm_init)."""
+    def b(r):
+        return n if r >= world else (n * r // world) // SLICE_ALIGN * SLICE_ALIGN
+    return b(rank), b(rank + 1)
 
 
 def test_slices_partition_the_cloud():
@@ -22,7 +28,8 @@ def test_slices_partition_the_cloud():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
-            assert max(sizes) - min(sizes) <= 1
+            assert all(a % SLICE_ALIGN == 0 for a, _ in edges)
+            assert max(sizes) - min(sizes) < 2 * SLICE_ALIGN
 
 
 GLOO_WORKER = r'''
@@ -74,7 +81,7 @@ def _run_worker(world, out, particles):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("particles", [40_001, 262_144])
+@pytest.mark.parametrize("particles", [40_001, 262_144, 1_000_003])
 def test_results_do_not_depend_on_gpu_count(tmp_path, particles):
     import torch
     ngpu = torch.cuda.device_count()
@@ -94,5 +101,6 @@ def test_results_do_not_depend_on_gpu_count(tmp_path, particles):
         assert np.array_equal(o["cloud"]["weight"].view(np.uint64), base["cloud"]["weight"].view(np.uint64))
         assert np.array_equal(o["estimates"], base["estimates"])
         if world > 1:
-            # one pose exchange (a copy-engine push; three NCCL all-gathers without CUDA IPC) + one score exchange
-            assert int(o["collectives"]) in (2, 4) and int(o["local"]) in (particles // world, particles // world + 1)
+            # one pose exchange (a copy-engine push) + five flag barriers (two per sequential sum, one for the estimate)
+            assert int(o["collectives"]) == 6
+            assert int(o["local"]) == slice_bounds(particles, 0, world)[1]
