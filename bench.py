@@ -4,19 +4,23 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config config4] [--impl engine|reference]
 
 A step = one full ParticleFilter::updateFilter over the whole particle cloud with a synthetic scan.
-Workload (default): BASELINE.json configs[3] -- 16M particles x 360 beams on a 2000x2000 5 cm grid; the same total work
-is sharded across N GPUs (strong scaling) with the map replicated.
+Workload (default): BASELINE.json configs[3] -- 16M particles x 360 beams on a 2000x2000 5 cm grid, SURVEY.md 8d's
+tracking cloud (truth + N(0, 0.10 m), N(0, 0.05 rad)); the same total work is sharded across N GPUs (strong scaling)
+with the map replicated.
 
 `value`      whole-job evals/s with everything resident in HBM (updates enqueued back to back, CUDA events on the
              engine's stream, max over ranks).
 `e2e`        the same metric through the reference-facing C-ABI call mcl_update() with HOST scan buffers: per step the
              scan is prepared and copied H2D, the pose estimate copied D2H, and the call blocks.
-`roofline`   sensor stage (the dominant launches: score_fast_kernel + score_deferred_kernel, back to back on one
-             stream): algorithmic bytes per update (32 B x map reads + 36 B x particles + map bytes) / the
-             stage's mean CUDA-event duration, against MEASURED_PEAKS.json's HBM copy rate; plus the L2-gather
-             microbenchmark measured on this device in this run as a second denominator.
+`roofline`   sensor stage (the dominant kernel).  Its map reads are shared-memory lookups, so it is bound by instruction
+             issue: achieved warp instructions/s (instructions per 32 evaluations from the committed ncu capture of
+             that kernel x this run's evaluations / this run's CUDA-event time) against 4 schedulers x SMs x the SM
+             clock sampled in this run; plus the shared-memory wavefront fraction and the HBM share.
+`digest`     sums mod 2^64 over all ranks of the last update's indices / scores / weights / poses: equal across GPU
+             counts iff the clouds are bit-identical.
 `cpu_baseline` the reference's ParticleFilter::updateFilter (oracle/_ref when built, else the C port), 1 thread, on a
-             bounded particle sub-sample of the same workload.
+             bounded particle sub-sample of the same workload (1 M particles at config 4).
+`configs`    short entries for the other BASELINE configs (1, 2, 3 on one GPU; the 64 M-particle config 5 on eight).
 """
 import argparse
 import json
@@ -35,7 +39,6 @@ from botlab_b200 import synth  # noqa: E402
 
 METRIC = "particle_beam_evals_per_sec"
 UNIT = "evals/s"
-CPU_SAMPLE_PARTICLES = 100_000
 
 
 def build_workload(config, seed=0):
@@ -102,17 +105,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def recorded_traffic(config, world, n):
-    """DRAM bytes of one sensor-kernel launch from the committed ncu capture of this very workload, else None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def kernel_figures():
+    """Per-kernel figures taken from the committed ncu captures (profiles/r02_kernel_figures.json): warp instructions
+    and shared-memory wavefronts per 32 evaluations of the sensor kernels, with the capture each came from."""
+    path = os.path.join(ROOT, "profiles", "r02_kernel_figures.json")
     try:
         with open(path) as f:
-            rec = json.load(f).get(f"{config}_{world}gpu")
-        if rec and rec["particles"] == n:
-            return rec["dram_bytes_read"] + rec["dram_bytes_write"]
-    except (OSError, ValueError, KeyError):
-        pass
-    return None
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 def measured_peaks():
@@ -123,13 +124,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tracking_cloud(n, truth, t_first, seed=5):
+    """SURVEY.md 8d cloud of the tracking configs: truth + N(0, 0.10 m) / N(0, 0.05 rad), then one reference-sigma action
+    step so that parent_pose != pose; pose.utime = the first scan's start."""
+    return synth.make_particles(n, truth, seed=seed, sigma_xy=0.10, sigma_theta=0.05, parent_utime=int(t_first) - 100_000,
+                                pose_utime=int(t_first))
+
+
 # ---------------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_update(grid, truth, scans, n_sample, updates, threads=1):
     """Times the reference's ParticleFilter::updateFilter on the host.  Returns (evals/s, kind, seconds, evals)."""
     from oracle import ref, port
-    cloud = synth.make_particles(n_sample, truth, seed=5, parent_utime=900_000, pose_utime=900_000)
-    cloud["parent_pose"] = cloud["pose"]
     pose0, r0, th0, t0 = scans[0]
+    cloud = tracking_cloud(n_sample, truth, 900_000 + 100_000)
+    cloud["pose"]["utime"] = 900_000
+    cloud["parent_pose"] = cloud["pose"]
     total_s, total_evals = 0.0, 0
     if ref.available():
         kind = "reference"
@@ -167,12 +176,29 @@ def cpu_reference_update(grid, truth, scans, n_sample, updates, threads=1):
     return total_evals / total_s, kind, total_s, total_evals
 
 
+def cpu_sample_size(n, updates, budget_s):
+    """Particles per CPU update so that `updates` reference updates take about budget_s (the reference runs about
+    3e7 evals/s on one core, flat in N), never more than the cloud or 1 M, never fewer than 100 K
+    (or the cloud)."""
+    per_update = budget_s * 3.0e7 / (max(updates, 1) * 357.0)
+    return int(min(n, max(min(n, 100_000), min(1_000_000, per_update))))
+
+
+def workload_name(config, n, valid, grid, uniform):
+    return (f"{config}: {n} particles x 360 beams ({valid} valid), {grid.width}x{grid.height} int8 grid, "
+            + ("uniform cloud re-initialised every step (global localisation)" if uniform
+               else "tracking cloud (truth + N(0, 0.10 m), N(0, 0.05 rad))"))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, grid, truth, scans = build_workload(args.config)
-    n_sample = min(n, CPU_SAMPLE_PARTICLES)
+    if args.particles:
+        n = args.particles
+    uniform = args.config == "config5" or args.uniform
+    n_sample = cpu_sample_size(n, args.steps + min(args.warmup, 1), 150.0)
     valid = int((scans[0][1] > np.float32(0.15)).sum())
     for _ in range(min(args.warmup, 1)):
         cpu_reference_update(grid, truth, scans, min(n_sample, 20_000), 1)
@@ -183,11 +209,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps * (n / n_sample), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic)", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {n} particles x 360 beams ({valid} valid), "
-                               f"{grid.width}x{grid.height} int8 grid, tracking cloud",
-                   "note": "ms_per_step extrapolated linearly from the sub-sample to the full cloud; the reference's "
-                           "ParticleFilter is single-threaded (no threads anywhere in src/slam), so 1 core is all it can use"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic), int32 scores, int8 map",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n, valid, grid, uniform)},
+        "details": {"note": "ms_per_step extrapolated linearly from the sub-sample to the full cloud; the reference's "
+                            "ParticleFilter is single-threaded (no threads anywhere in src/slam), so 1 core is all it can use"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,55 +223,75 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------- engine arm
-def run_engine(args):
-    import torch
-    import torch.distributed as dist
+class Harness:
+    """torch.distributed plumbing shared by the measurements of one bench.py process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        tns = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(tns, op=self.dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    def sum_u64(self, vals):
+        """Sum mod 2^64 over ranks (int64 adds wrap)."""
+        as_i64 = [v - (1 << 64) if v >= (1 << 63) else v for v in vals]
+        if self.world == 1:
+            return [v & ((1 << 64) - 1) for v in as_i64]
+        tns = self.torch.tensor(as_i64, dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(tns, op=self.dist.ReduceOp.SUM)
+        return [int(v) & ((1 << 64) - 1) for v in tns.tolist()]
+
+    def make_engine(self, n, args):
+        from botlab_b200 import engine
+        e = engine.Engine(n, device=self.local_rank, lanes_per_particle=args.lanes, map_tile=args.tile,
+                          sensor_path=args.sensor_path)
+        if self.world > 1:
+            t = self.torch
+            uid = t.tensor(list(engine.comm_unique_id()) if self.rank == 0 else [0] * 128, dtype=t.uint8, device="cuda")
+            self.dist.broadcast(uid, 0)
+            e.comm_init(bytes(uid.cpu().tolist()), self.rank, self.world)
+        return e
+
+
+def measure(hx, args, config, steps, warmup, particles=0, uniform=False, want_roofline=True):
+    """One workload on the process's ranks: e2e arm (blocking C-ABI updates with host scan buffers), resident arm
+    (updates enqueued back to back), a counted pass for the algorithmic figures.  Returns the JSON fields (rank 0)."""
     from botlab_b200 import engine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    n, grid, truth, scans = build_workload(args.config)
-    if args.particles:
-        n = args.particles
-    e = engine.Engine(n, device=local_rank, lanes_per_particle=args.lanes, map_tile=args.tile,
-                      sensor_path=args.sensor_path)
-    if world > 1:
-        if rank == 0:
-            uid = torch.tensor(list(engine.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        else:
-            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    torch = hx.torch
+    rank, world = hx.rank, hx.world
+    n, grid, truth, scans = build_workload(config)
+    if particles:
+        n = particles
+    e = hx.make_engine(n, args)
     e.set_map(grid.cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
     pose0, r0, th0, t0 = scans[0]
-    uniform = args.config == "config5" or args.uniform     # global localisation: uniformly initialised cloud
+    uniform = uniform or config == "config5"
     if uniform:
         e.init_uniform(utime=int(t0[0]), seed=42)
     else:
-        e.init_at_pose(*pose0, utime=int(t0[0]), seed=42)
+        e.import_particles(tracking_cloud(n, truth, t0[0]))      # every rank imports the same seeded cloud
     am = engine.ActionModel()
     am.update(*pose0, int(t0[0]))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        tns = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
-        return float(tns.item())
-
-    stream = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", hx.local_rank))
     step_no = [0]
 
     def next_inputs():
@@ -263,19 +309,19 @@ def run_engine(args):
 
     valid = int((r0 > np.float32(0.15)).sum())
     h2d = valid * 16 + 64            # prepared beams (16 B each) + scalars
-    d2h = 16 + 40                    # pose estimate + counters
+    d2h = 16 + 56                    # pose estimate + counters
 
     # ---- e2e arm: blocking C-ABI calls with host scan buffers ---------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         r, th, t, ut = next_inputs()
         e.update(am, ut, r, th, t, 0.5 / n)
-    clocks = ClockSampler(local_rank)
-    barrier()
+    clocks = ClockSampler(hx.local_rank)
+    hx.barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     score_ms, stage_ms, evals_e2e, launches = [], [], 0, 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         r, th, t, ut = next_inputs()
         if uniform:
             e.init_uniform(utime=ut - 100_000, seed=1000 + step_no[0])   # every step scores a fresh uniform cloud
@@ -286,27 +332,28 @@ def run_engine(args):
         evals_e2e += n * int((r > np.float32(0.15)).sum())
         launches += st["kernel_launches"]
     ev1.record(stream)
-    barrier()
-    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    hx.barrier()
+    e2e_ms = hx.max_over_ranks(ev0.elapsed_time(ev1))
 
     # ---- resident arm: scan uploaded once, updates enqueued back to back ------------------------------------------
     r, th, t, ut = next_inputs()
     e.upload_scan(r, th, t, ut)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         e.update_enqueue(am, ut)
-    barrier()
+    hx.barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record(stream)
-    for k in range(args.steps):
+    for k in range(steps):
         if uniform:
             e.init_uniform(utime=ut - 100_000, seed=2000 + k)
         e.update_enqueue(am, ut)
     ev3.record(stream)
-    barrier()
-    res_ms = max_over_ranks(ev2.elapsed_time(ev3))
+    hx.barrier()
+    res_ms = hx.max_over_ranks(ev2.elapsed_time(ev3))
     clock_info = clocks.stop()
-    evals_res = n * int((r > np.float32(0.15)).sum()) * args.steps
+    evals_res = n * int((r > np.float32(0.15)).sum()) * steps
     est = e.read_estimate()
+    digest = hx.sum_u64(e.digest())
 
     # ---- algorithmic traffic of the sensor kernel: one untimed counted pass --------------------------------------
     e.set_gather_counting(True)
@@ -318,64 +365,134 @@ def run_engine(args):
     st = e.stats()
     e.set_gather_counting(False)
     gathers = st["gathers"]
-    alg_bytes = 32 * gathers + 36 * local_n + grid.width * grid.height
     mean_score_s = float(np.mean(score_ms)) * 1e-3
-    peak, peak_kind = measured_peaks()
-    achieved = alg_bytes / mean_score_s / 1e9
-    gather_peak = e.measure_gather_peak(grid.width * grid.height, 1 << 31)
-
-    line = None
+    out = None
     if rank == 0:
         stage = np.mean(np.array(stage_ms), axis=0)
-        line = {
-            "metric": METRIC, "value": evals_res / (res_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": res_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic), int32 scores, int8 map",
-            "data": "synthetic",
-            "config": {"workload": f"{args.config}: {n} particles x 360 beams ({valid} valid), "
-                                   f"{grid.width}x{grid.height} int8 grid, "
-                                   + ("uniform cloud re-initialised every step (global localisation)" if uniform
-                                      else "tracking cloud"),
-                       "updates_per_sec": args.steps / (res_ms * 1e-3),
+        out = {
+            "value": evals_res / (res_ms * 1e-3), "ms_per_step": res_ms / steps, "n_gpus": world, "steps": steps,
+            "warmup": warmup,
+            "config": {"workload": workload_name(config, n, valid, grid, uniform)},
+            "details": {"updates_per_sec": steps / (res_ms * 1e-3),
                        "l2_policy": "inputs larger than L2: 28 B/particle of pose+parent+score state streams from HBM "
-                                    f"every step ({28 * n / 1e6:.0f} MB); the int8 map is L2/shared-memory resident by design",
+                                    f"every step ({28 * n / 1e6:.0f} MB); the int8 map is shared-memory resident by design"
+                                    if 28 * n > 126e6 else
+                                    "particle state smaller than L2 (it is rewritten by every update; no flush between steps)",
                        "lanes_per_particle": st["lanes_per_particle"], "map_tile_used": st["map_tile_used"],
                        "sensor_path": st["sensor_path"], "deferred_fraction": st["deferred_evals"] / max(st["evals"], 1),
-                       "certification_eps_cells": st["fast_eps"],
-                       "particles_per_gpu": local_n},
+                       "certification_eps_cells": st["fast_eps"], "particles_per_gpu": local_n},
             "e2e": {"value": evals_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "updates_per_sec": args.steps / (e2e_ms * 1e-3)},
-            "gpu_launches": launches,
-            "clocks": clock_info,
-            "roofline": {"bound": "hbm",
-                         "kernel": {3: "score_table_kernel (sensor stage)",
-                                    2: "score_fast_kernel + score_deferred_kernel (sensor stage)"}.get(
-                                        st["sensor_path"], "score_kernel (sensor stage)"),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": recorded_traffic(args.config, world, n),
-                         "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": alg_bytes, "map_reads_per_launch": gathers,
-                         "kernel_ms": mean_score_s * 1e3,
-                         "l2_gather": {"achieved_sectors_per_s": gathers / mean_score_s,
-                                       "peak_sectors_per_s": gather_peak,
-                                       "frac": gathers / mean_score_s / gather_peak,
-                                       "peak_kind": "measured in this run: random 1-byte ld.global.cg over the map footprint"}},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
+                    "updates_per_sec": steps / (e2e_ms * 1e-3)},
+            "gpu_launches": launches, "clocks": clock_info,
             "stage_ms": {"resample": float(stage[0]), "action": float(stage[1]), "score": float(stage[2]),
                          "normalize": float(stage[3]), "estimate": float(stage[4])},
             "estimate": [est.x, est.y, est.theta],
+            "digest": {"resample_indices": f"{digest[0]:016x}", "scores": f"{digest[1]:016x}",
+                       "weights": f"{digest[2]:016x}", "poses": f"{digest[3]:016x}",
+                       "what": "sums mod 2^64 over all ranks of mixed (global particle index, bit pattern) pairs after "
+                               "the last resident update: equal across GPU counts iff the clouds are bit-identical"},
         }
+    if want_roofline:
+        # measured on every rank (it launches kernels), reported by rank 0
+        gather_peak = e.measure_gather_peak(grid.width * grid.height, 1 << 31)
+        if rank == 0:
+            out["roofline"] = roofline(st, gathers, local_n, grid, mean_score_s, clock_info, gather_peak)
+    e.close()
+    return out, (n, grid, truth, scans)
+
+
+def roofline(st, gathers, local_n, grid, score_s, clock_info, gather_peak):
+    """What bounds the sensor stage (the dominant kernel).  The map reads are shared-memory lookups, so neither HBM nor
+    L2 is the roofline: the kernel is bound by instruction issue.  achieved = warp instructions per second = (warp
+    instructions per 32 evaluations, from the committed ncu capture of this kernel) x evaluations / 32 / the stage's
+    CUDA-event time measured in this run; peak = 4 schedulers x SMs x the SM clock sampled in this run.  Beside it: the
+    shared-memory wavefront rate against one wavefront per clock per SM, and the HBM share (particle state + map once)."""
+    fig = kernel_figures()
+    kern = {3: "score_table_kernel", 2: "score_fast_kernel+score_deferred_kernel"}.get(st["sensor_path"], "score_kernel")
+    f = fig.get(kern, {})
+    sm_mhz = clock_info.get("sm_mhz") or 1965.0
+    sms = 148
+    evals = st["evals"]
+    peak_issue = 4 * sms * sm_mhz * 1e6
+    peak, peak_kind = measured_peaks()
+    hbm_bytes = 36 * local_n + grid.width * grid.height
+    out = {"bound": "issue", "kernel": kern + " (sensor stage)", "kernel_ms": score_s * 1e3, "unit": "Gwarp-inst/s",
+           "peak": peak_issue / 1e9,
+           "peak_kind": f"4 warp schedulers x {sms} SMs x {sm_mhz:.0f} MHz (SM clock sampled by nvidia-smi during this run)",
+           "traffic": None,
+           "traffic_note": "DRAM bytes need a profiler: see traffic_ncu (from the committed capture), not measured in this run",
+           "traffic_ncu": f.get("dram_bytes_per_launch"),
+           "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved": hbm_bytes / score_s / 1e9, "peak": peak,
+                   "unit": "GB/s", "frac": hbm_bytes / score_s / 1e9 / peak, "peak_kind": peak_kind,
+                   "what": "36 B x particles + map bytes once (SURVEY.md 8d without the map-read term, which is "
+                           "served from shared memory)"},
+           "map_reads_per_launch": gathers,
+           "l2_gather_reference": {"map_reads_per_s": gathers / score_s, "l2_random_sector_rate": gather_peak,
+                                   "ratio": gathers / score_s / gather_peak,
+                                   "what": "the rate the SURVEY's L2-gather design would be bound by (random 1-byte "
+                                           "ld.global.cg over the map footprint, measured in this run); the kernel "
+                                           "does not touch L2 for map reads, so this is context, not a roofline fraction"}}
+    if f.get("warp_inst_per_32_evals"):
+        ach = f["warp_inst_per_32_evals"] * evals / 32.0 / score_s
+        out.update({"achieved": ach / 1e9, "frac": ach / peak_issue,
+                    "warp_inst_per_32_evals": f["warp_inst_per_32_evals"], "figures_from": f.get("source")})
+        if f.get("smem_wavefronts_per_32_evals"):
+            wf = f["smem_wavefronts_per_32_evals"] * evals / 32.0 / score_s
+            out["smem"] = {"achieved_wavefronts_per_s": wf, "peak_wavefronts_per_s": sms * sm_mhz * 1e6,
+                           "frac": wf / (sms * sm_mhz * 1e6), "what": "shared-memory wavefronts against 1 per clock per SM"}
+    else:
+        out.update({"achieved": None, "frac": None,
+                    "note": "no committed instruction figure for this kernel family (profiles/r02_kernel_figures.json)"})
+    return out
+
+
+def run_engine(args):
+    hx = Harness()
+    rank, world = hx.rank, hx.world
+    head, (n, grid, truth, scans) = measure(hx, args, args.config, args.steps, args.warmup, particles=args.particles,
+                                            uniform=args.uniform)
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32+f64 (reference arithmetic), int32 scores, int8 map",
+                "data": "synthetic"}
+        for k in ("config", "details", "e2e", "gpu_launches", "clocks", "roofline", "stage_ms", "estimate", "digest"):
+            line[k] = head[k]
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_sample = min(n, CPU_SAMPLE_PARTICLES)
+        n_sample = cpu_sample_size(n, 2, 25.0)
         v, kind, sec, ev = cpu_reference_update(grid, truth, scans, n_sample, 2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
                                 "sample": f"2 updateFilter calls on a {n_sample}-particle sub-sample of the same "
                                           f"workload ({sec:.1f} s of CPU)", "host_cores_available": os.cpu_count()}
+    # ---- the other BASELINE configs, briefly (device-timed; their own CPU baselines at BASELINE.md 3's sizes) ----------
+    if args.config == "config4" and not args.no_extra and not args.particles:
+        extra = []
+        if world == 1:
+            for cfg, k, cpu_updates in (("config1", 50, 5), ("config2", 20, 5), ("config3", 10, 1)):
+                res, (cn, cgrid, ctruth, cscans) = measure(hx, args, cfg, k, 3, want_roofline=False)
+                entry = {"config": res["config"], "details": res["details"], "value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"],
+                         "steps": k, "warmup": 3, "e2e": res["e2e"], "stage_ms": res["stage_ms"],
+                         "gpu_launches": res["gpu_launches"]}
+                if not args.no_cpu:
+                    v, kind, sec, ev = cpu_reference_update(cgrid, ctruth, cscans, cn, cpu_updates)
+                    entry["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                             "sample": f"{cpu_updates} updateFilter calls at full size ({cn} particles, "
+                                                       f"{sec:.1f} s of CPU)"}
+                extra.append(entry)
+        elif world == 8:
+            res, _ = measure(hx, args, "config5", 3, 3, want_roofline=False)
+            if rank == 0:
+                extra.append({"config": res["config"], "details": res["details"], "value": res["value"], "unit": UNIT,
+                              "ms_per_step": res["ms_per_step"], "steps": 3, "warmup": 3, "e2e": res["e2e"],
+                              "stage_ms": res["stage_ms"], "estimate": res["estimate"], "digest": res["digest"]})
+        if rank == 0:
+            line["configs"] = extra
     if rank == 0:
         print(json.dumps(line))
-    e.close()
     if world > 1:
-        dist.destroy_process_group()
+        hx.dist.destroy_process_group()
 
 
 def main():
@@ -387,8 +504,10 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
-    ap.add_argument("--sensor-path", type=int, default=0, help="0 = certified float pass + exact re-evaluation, 1 = exact only")
+    ap.add_argument("--sensor-path", type=int, default=0,
+                    help="0 = auto (score-table pass where it fits, else two-pass), 1 = exact only, 2 = two-pass only")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short entries for the other BASELINE configs")
     ap.add_argument("--uniform", action="store_true", help="uniform cloud (global localisation) on any config")
     ap.add_argument("--particles", type=int, default=0, help="override the config's particle count")
     args = ap.parse_args()

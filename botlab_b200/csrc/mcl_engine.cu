@@ -1818,6 +1818,24 @@ int mcl_debug_fast_trig_error(mcl_engine* h, float lo, float hi, double* max_sin
     return MCL_OK;
 }
 
+int mcl_debug_digest(mcl_engine* h, uint64_t* digest4_out)
+{
+    if (!h || !digest4_out) return fail(h, MCL_ERR_INVALID, "bad arguments");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    CK(cudaSetDevice(h->device));
+    { int rc = ensure_staging(h, 32); if (rc) return rc; }
+    CK(cudaMemsetAsync(h->staging, 0, 32, h->stream));
+    const PoseSoA& p = h->pose[h->cur];
+    if (h->hi > h->lo) {
+        xdigest_kernel<<<grid_for(h, h->hi - h->lo, 256), 256, 0, h->stream>>>(h->idx, h->score2, h->weight[h->wcur], p.x, p.y, p.th,
+                                                                             h->lo, h->hi, (unsigned long long*)h->staging);
+        CKL(h);
+    }
+    CK(cudaMemcpyAsync(digest4_out, h->staging, 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
 int mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* s, float* c)
 {
     if (!h || !x || !s || !c || n < 1) return fail(h, MCL_ERR_INVALID, "bad arguments");

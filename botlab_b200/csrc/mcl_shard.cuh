@@ -247,9 +247,49 @@ __global__ void xseq_group_maps_kernel(const int* ebias, const long long* q0, co
     }
 }
 
-// ---- S5: the walk (one warp; the CTA stages the group maps).  As seq_walk_kernel, except that the raw weights of a
-// chunk that has to be added element by element come from the side buffer (or, failing that, from the owner's weights
-// over NVLink) ------------------------------------------------------------------------------------------------------------
+// Advances the exact running sum c over the longest valid prefix of up to cnt consecutive maps (lane l holds map l:
+// exponent e_l and (m0_l, m1_l)).  A map is valid while it assumes c's binade and the sum stays inside that binade.
+// Returns L in [0, cnt]: maps 0 .. L-1 were applied, c = the sum after them, and for every lane l <= L cin_l = the exact
+// sum at the entry of map l (so lane L, the first map that did not apply, knows where it starts).
+__device__ __forceinline__ int seq_apply_prefix(double& c, int cnt, int e_l, long long m0_l, long long m1_l, double& cin_l)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = dbl_exp(c);
+    const bool mine_ok = lane < cnt && e_l == e && e_l != 0;
+    const unsigned okmask = __ballot_sync(0xffffffffu, mine_ok);
+    const int l0 = okmask == 0xffffffffu ? 32 : __ffs(~okmask) - 1;          // leading maps in c's binade
+    const long long bits = __double_as_longlong(c);
+    cin_l = c;
+    if (l0 == 0) return 0;
+    long long p0 = lane < l0 ? m0_l : 0, p1 = lane < l0 ? m1_l : 0;          // inclusive prefix composition
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const long long q0 = __shfl_up_sync(0xffffffffu, p0, off), q1 = __shfl_up_sync(0xffffffffu, p1, off);
+        if (lane >= off) {
+            long long r0, r1;
+            seq_compose(q0, q1, p0, p1, r0, r1);
+            p0 = r0; p1 = r1;
+        }
+    }
+    const long long incl = bits + ((bits & 1) ? p1 : p0);
+    // weights are non-negative, so the sums grow with the lane: the maps that leave the binade form a suffix
+    const bool stay = lane >= l0 || ((((incl >> 52) & 0x7ff) == e) && incl >= bits);
+    const unsigned smask = __ballot_sync(0xffffffffu, stay);
+    const int l1 = smask == 0xffffffffu ? 32 : __ffs(~smask) - 1;
+    const int L = l1 < l0 ? l1 : l0;
+    long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = bits;
+    cin_l = __longlong_as_double(excl);
+    if (L > 0) c = __longlong_as_double(__shfl_sync(0xffffffffu, incl, L - 1));
+    return L;
+}
+
+// ---- S5: the walk (one warp; the CTA stages the group maps).  Runs of maps that stay inside one binade advance up to
+// 32 at a time (seq_apply_prefix); the map that does not apply is opened into the next level down -- a group into its
+// chunks, a chunk into its raw weights (real sequential double adds) -- and the walk resumes right behind it.  The raw
+// weights of such a chunk come from the rank's own slice, from the side buffer its owner filled, or from the owner's
+// weights over NVLink.  Produces the exact entry sum of every group (cin2), of every chunk of the groups that had to
+// be opened (cin1, flagged in opened[j]), the exact total and the number of chunks added element by element.
 __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long n1, long long n2, const int* ebias,
                                                        const long long* q0, const long long* q1, const int* gebias,
                                                        const long long* g0, const long long* g1, double* cin2, double* cin1,
@@ -257,6 +297,8 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
                                                        const XPeers xp, size_t w_off, size_t fbraw_off)
 {
     __shared__ double fb_chunk[kL1];
+    __shared__ long long sc0[kL2], sc1[kL2];      // level-1 maps of the group being opened
+    __shared__ int sce[kL2];
     extern __shared__ __align__(16) unsigned char walk_smem[];
     long long* sg0 = reinterpret_cast<long long*>(walk_smem);
     long long* sg1 = sg0 + (staged ? n2 : 0);
@@ -269,70 +311,67 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
     const int lane = threadIdx.x;
     double c = 0.0;
     long long fallbacks = 0;
-    for (long long jb = 0; jb < n2; jb += 32) {
-        const long long jl = jb + lane;
+    long long j = 0;
+    while (j < n2) {
+        const long long jl = j + lane;
+        const int cnt = (int)(n2 - j < 32 ? n2 - j : 32);
         const int ge_l = jl < n2 ? (staged ? sge[jl] : gebias[jl]) : 0;
         const long long g0_l = jl < n2 ? (staged ? sg0[jl] : g0[jl]) : 0, g1_l = jl < n2 ? (staged ? sg1[jl] : g1[jl]) : 0;
-        const int cnt = (int)(n2 - jb < 32 ? n2 - jb : 32);
         double cin_l;
-        if (seq_apply_warp(c, cnt, ge_l, g0_l, g1_l, cin_l)) {
-            if (lane < cnt) { cin2[jl] = cin_l; opened[jl] = 0; }
-            continue;
+        const int L = seq_apply_prefix(c, cnt, ge_l, g0_l, g1_l, cin_l);
+        if (lane < L) { cin2[jl] = cin_l; opened[jl] = 0; }
+        j += L;
+        if (L == cnt) continue;
+        // group j does not apply as a whole: open it
+        if (lane == 0) { cin2[j] = c; opened[j] = 1; }
+        const long long kfirst = j * kL2;
+        const int kcnt = (int)((kfirst + kL2 < n1 ? kfirst + kL2 : n1) - kfirst);
+        for (int i = lane; i < kL2; i += 32) {
+            const bool in = i < kcnt;
+            sce[i] = in ? ebias[kfirst + i] : 0; sc0[i] = in ? q0[kfirst + i] : 0; sc1[i] = in ? q1[kfirst + i] : 0;
         }
-        for (int t = 0; t < cnt; ++t) {
-            const long long j = jb + t;
-            const int ge = __shfl_sync(0xffffffffu, ge_l, t);
-            const long long m0 = __shfl_sync(0xffffffffu, g0_l, t), m1 = __shfl_sync(0xffffffffu, g1_l, t);
-            if (lane == 0) cin2[j] = c;
-            if (seq_apply(c, ge, m0, m1)) {
-                if (lane == 0) opened[j] = 0;
-                continue;
+        __syncwarp();
+        int kd = 0;
+        while (kd < kcnt) {
+            const int kb = kcnt - kd < 32 ? kcnt - kd : 32;
+            const int ki = kd + lane;
+            const int e_l = lane < kb ? sce[ki] : 0;
+            const long long f0_l = lane < kb ? sc0[ki] : 0, f1_l = lane < kb ? sc1[ki] : 0;
+            const int K = seq_apply_prefix(c, kb, e_l, f0_l, f1_l, cin_l);
+            if (lane < K) cin1[kfirst + ki] = cin_l;
+            kd += K;
+            if (K == kb) continue;
+            // chunk kfirst + kd is added element by element
+            const long long k = kfirst + kd;
+            if (lane == 0) cin1[k] = c;
+            ++fallbacks;
+            const long long efirst = k * kL1;
+            const int owner = xowner(xp, efirst);
+            const int e = sce[kd];
+            const long long f0 = sc0[kd];
+            const double* src;
+            bool bounded = true;
+            if (owner == xp.rank) src = reinterpret_cast<const double*>(xp.base[xp.rank] + w_off) + efirst;
+            else if (e == 0 && f0 >= 0) {
+                src = reinterpret_cast<const double*>(xp.base[xp.rank] + fbraw_off) + ((size_t)owner * kFbSlots + (size_t)f0) * kL1;
+                bounded = false;            // the side buffer is zero padded past n
+            } else src = reinterpret_cast<const double*>(xp.base[owner] + w_off) + efirst;
+            double v_l[kL1 / 32];
+#pragma unroll
+            for (int q = 0; q < kL1 / 32; ++q) {                      // all loads in flight before the adds
+                const long long gi = efirst + q * 32 + lane;
+                v_l[q] = (!bounded || gi < n) ? src[q * 32 + lane] : 0.0;
             }
-            if (lane == 0) opened[j] = 1;
-            const long long kfirst = j * kL2;
-            const long long klast = kfirst + kL2 < n1 ? kfirst + kL2 : n1;
-            for (long long kb = kfirst; kb < klast; kb += 32) {
-                const long long kl = kb + lane;
-                const int e_l = kl < klast ? ebias[kl] : 0;
-                const long long f0_l = kl < klast ? q0[kl] : 0, f1_l = kl < klast ? q1[kl] : 0;
-                const int kc = (int)(klast - kb < 32 ? klast - kb : 32);
-                if (seq_apply_warp(c, kc, e_l, f0_l, f1_l, cin_l)) {
-                    if (lane < kc) cin1[kl] = cin_l;
-                    continue;
-                }
-                for (int s = 0; s < kc; ++s) {
-                    const long long k = kb + s;
-                    const int e = __shfl_sync(0xffffffffu, e_l, s);
-                    const long long f0 = __shfl_sync(0xffffffffu, f0_l, s), f1 = __shfl_sync(0xffffffffu, f1_l, s);
-                    if (lane == 0) cin1[k] = c;
-                    if (seq_apply(c, e, f0, f1)) continue;
-                    ++fallbacks;
-                    const long long efirst = k * kL1;
-                    const int owner = xowner(xp, efirst);
-                    // raw weights of the chunk: own slice -> local weights; pushed by the owner -> side buffer; else the
-                    // owner's weights over NVLink
-                    const double* src;
-                    bool bounded = true;
-                    if (owner == xp.rank) src = reinterpret_cast<const double*>(xp.base[xp.rank] + w_off) + efirst;
-                    else if (e == 0 && f0 >= 0) {
-                        src = reinterpret_cast<const double*>(xp.base[xp.rank] + fbraw_off) + ((size_t)owner * kFbSlots + (size_t)f0) * kL1;
-                        bounded = false;            // the side buffer is zero padded past n
-                    } else src = reinterpret_cast<const double*>(xp.base[owner] + w_off) + efirst;
-                    double v_l[kL1 / 32];
 #pragma unroll
-                    for (int q = 0; q < kL1 / 32; ++q) {
-                        const long long gi = efirst + q * 32 + lane;
-                        v_l[q] = (!bounded || gi < n) ? src[q * 32 + lane] : 0.0;
-                    }
-#pragma unroll
-                    for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
-                    __syncwarp();
+            for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
+            __syncwarp();
 #pragma unroll 16
-                    for (int i = 0; i < kL1; ++i) c = __dadd_rn(c, fb_chunk[i]);
-                    __syncwarp();
-                }
-            }
+            for (int i = 0; i < kL1; ++i) c = __dadd_rn(c, fb_chunk[i]);
+            __syncwarp();
+            kd += 1;
         }
+        __syncwarp();
+        j += 1;
     }
     if (lane == 0) {
         *total = c;
@@ -529,6 +568,36 @@ __global__ void __launch_bounds__(kEstBlock) xestimate_final_kernel(const double
         out4[2] = (float)atan2(red[0].z, red[0].w);
         out4[3] = 0.0f;
         *ess_acc = red2[0];
+    }
+}
+
+// Order-independent, position-sensitive digest of the rank's slice: sums (mod 2^64) of mixed (global index, bit pattern)
+// pairs of the resample indices, the half-unit scores, the weights and the poses.  Slices partition the cloud, so the
+// sum of the ranks' digests does not depend on the GPU count iff the results do not.
+__device__ __forceinline__ unsigned long long xmix(unsigned long long i, unsigned long long v)
+{
+    unsigned long long z = (i + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^ v;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void xdigest_kernel(const int32_t* idx, const int32_t* score2, const double* w, const float* x, const float* y,
+                               const float* th, long long lo, long long hi, unsigned long long* out4)
+{
+    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        d0 += xmix((unsigned long long)i, (unsigned long long)(unsigned)idx[i]);
+        d1 += xmix((unsigned long long)i, (unsigned long long)(unsigned)score2[i]);
+        d2 += xmix((unsigned long long)i, (unsigned long long)__double_as_longlong(w[i]));
+        d3 += xmix((unsigned long long)i, ((unsigned long long)__float_as_uint(x[i]) << 32) ^ ((unsigned long long)__float_as_uint(y[i]) << 16) ^
+                                              (unsigned long long)__float_as_uint(th[i]));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out4 + 0, d0); atomicAdd(out4 + 1, d1); atomicAdd(out4 + 2, d2); atomicAdd(out4 + 3, d3);
     }
 }
 

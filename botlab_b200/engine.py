@@ -23,7 +23,7 @@ SYMBOLS = [
     "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
-    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error", "mcl_debug_fast_margin",
+    "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error", "mcl_debug_fast_margin", "mcl_debug_digest",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
         L.mcl_debug_sincosf.argtypes = [vp, vp, i64, vp, vp]
         L.mcl_debug_fast_trig_error.argtypes = [vp, fp, fp, vp, vp]
         L.mcl_debug_fast_margin.argtypes = [vp, vp, vp, vp]
+        L.mcl_debug_digest.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -323,6 +324,12 @@ class Engine:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._ck(self._L.mcl_debug_fast_margin(self.h, C.addressof(a), C.addressof(b), C.addressof(c)))
         return a.value, b.value, c.value
+
+    def digest(self):
+        """Four 64-bit position-sensitive sums over this rank's slice (indices, scores, weights, poses)."""
+        out = (C.c_uint64 * 4)()
+        self._ck(self._L.mcl_debug_digest(self.h, out))
+        return [int(v) for v in out]
 
     def comm_init(self, unique_id, rank, world):
         buf = (C.c_byte * 128).from_buffer_copy(bytes(unique_id))

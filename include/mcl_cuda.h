@@ -187,6 +187,11 @@ int  mcl_set_gather_counting(mcl_engine* h, int on);   /* debug counter of map r
 /* Roofline denominator measured on this device: uniformly random 1-byte reads over a footprint of map_bytes, L1
  * bypassed, one per lane.  Returns sectors (32 B) per second. */
 int  mcl_measure_gather_peak(mcl_engine* h, int64_t footprint_bytes, int64_t reads, double* sectors_per_s_out);
+/* Digest of this rank's slice of the last update: four 64-bit sums (mod 2^64) of mixed (global particle index, bit
+ * pattern) pairs of the resample indices, the half-unit scores, the normalised weights and the poses.  The sum over the
+ * ranks is independent of the GPU count iff the clouds are bit-identical (bench.py prints it; the multi-GPU parity test
+ * compares whole clouds). */
+int  mcl_debug_digest(mcl_engine* h, uint64_t* digest4_out);
 /* glibc-sincosf restatement evaluated on the device for n floats (test hook for the trig parity contract). */
 int  mcl_debug_sincosf(mcl_engine* h, const float* x, int64_t n, float* sin_out, float* cos_out);
 /* Largest absolute error of the SFU sine / cosine the certified float pass uses, over EVERY float in [lo, hi] against
