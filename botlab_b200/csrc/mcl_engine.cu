@@ -872,15 +872,21 @@ int upload_noise(mcl_engine* h, const float* noise3n, const float** dev_out)
     return MCL_OK;
 }
 
-int run_resample_indices(mcl_engine* h, double r, int wbuf)
+// children / clo / chi: the draws U_m = r + m / children, m in [clo, chi), this call resolves (the filter's resampling:
+// children = N and the rank's slice; a weighted export: any number of draws); indices go to idx_out[m].
+int run_resample_indices(mcl_engine* h, double r, int wbuf, long long children = -1, long long clo = 0, long long chi = 0,
+                         int32_t* idx_out = nullptr)
 {
     int rc = seq_total(h, wbuf);
     if (rc) return rc;
     // materialise the exact running sum only where this rank's children draw from, then search
-    const long long n = h->n, n1 = h->n1, n2 = h->n2, local = h->hi - h->lo;
-    xresample_range_kernel<<<1, 32, 0, h->stream>>>(h->cin2, n2, n, r, h->lo, h->hi, h->xrange);
+    const long long n = h->n, n1 = h->n1, n2 = h->n2;
+    if (children < 0) { children = n; clo = h->lo; chi = h->hi; idx_out = h->idx; }
+    const long long local = chi - clo;
+    xresample_range_kernel<<<1, 32, 0, h->stream>>>(h->cin2, n2, children, r, clo, chi, h->xrange);
     CKL(h);
-    const long long groups_cap = h->world == 1 ? n2 : std::min<long long>(n2, 2 * ((local + kSliceAlign - 1) / kSliceAlign) + 64);
+    const long long groups_cap = (h->world == 1 || children != n) ? n2
+                               : std::min<long long>(n2, 2 * ((local + kSliceAlign - 1) / kSliceAlign) + 64);
     xseq_group_expand_kernel<<<(int)((n2 + 127) / 128), 128, 0, h->stream>>>(h->q0, h->q1, n1, h->cin2, h->opened, h->cin1,
                                                                          h->xrange);
     CKL(h);
@@ -891,7 +897,7 @@ int run_resample_indices(mcl_engine* h, double r, int wbuf)
     CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
     if (local > 0) {
         xresample_search_kernel<<<grid_for(h, (local + kSearchRun - 1) / kSearchRun, 128), 128, 0, h->stream>>>(
-            h->cum, n, r, h->lo, h->hi, h->xrange, h->idx, h->overruns);
+            h->cum, n, children, r, clo, chi, h->xrange, idx_out, h->overruns);
         CKL(h);
     }
     return MCL_OK;
@@ -1513,6 +1519,32 @@ int mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int6
         CK(cudaMemcpyAsync(aos, h->staging, sizeof(mcl_particle_t) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    if (n_out) *n_out = count;
+    return MCL_OK;
+}
+
+int mcl_export_weighted(mcl_engine* h, mcl_particle_t* aos, int64_t count, double u01, int64_t* n_out)
+{
+    if (!h) return fail(h, MCL_ERR_INVALID, "null engine");
+    if (!aos || count < 1 || count > h->n || !(u01 >= 0.0 && u01 < 1.0)) return fail(h, MCL_ERR_INVALID, "bad export arguments");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "no particles");
+    if (h->world > 1) return fail(h, MCL_ERR_STATE, "weighted export runs on single-GPU engines");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_staging(h, sizeof(mcl_particle_t) * (size_t)count + 4 * (size_t)count + 64);
+    if (rc) return rc;
+    int32_t* pick = (int32_t*)((char*)h->staging + ((sizeof(mcl_particle_t) * (size_t)count + 63) & ~(size_t)63));
+    // systematic draw of `count` particles over the weights' exact running sum (the filter's own resampling rule,
+    // particle_filter.cpp:84-103, with `count` draws instead of N): draw m sits at (u01 + m) / count of the total mass
+    rc = run_resample_indices(h, u01 / (double)count, h->wcur, count, 0, count, pick);
+    if (rc) return rc;
+    const PoseSoA& p = h->pose[h->cur];
+    const PoseSoA& q = h->parent[h->cur];
+    soa_to_aos_idx_kernel<<<grid_for(h, count, 256), 256, 0, h->stream>>>((AosParticle*)h->staging, count, pick,
+                                                                         1.0 / (double)count, h->pose_utime, h->parent_utime,
+                                                                         p.x, p.y, p.th, q.x, q.y, q.th);
+    CKL(h);
+    CK(cudaMemcpyAsync(aos, h->staging, sizeof(mcl_particle_t) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     if (n_out) *n_out = count;
     return MCL_OK;
 }

@@ -1265,6 +1265,22 @@ __global__ void soa_to_aos_kernel(AosParticle* aos, long long count, long long s
     }
 }
 
+// particles_t export of a drawn sub-sample: particle k = cloud[idx[k]] with weight w_out (a weighted draw carries
+// equal weights).
+__global__ void soa_to_aos_idx_kernel(AosParticle* aos, long long count, const int32_t* idx, double w_out, long long utime,
+                                      long long putime, const float* x, const float* y, const float* th, const float* px,
+                                      const float* py, const float* pth)
+{
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count; k += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx[k];
+        AosParticle p;
+        p.utime = utime; p.x = x[i]; p.y = y[i]; p.th = th[i]; p.pad0 = 0;
+        p.putime = putime; p.px = px[i]; p.py = py[i]; p.pth = pth[i]; p.pad1 = 0;
+        p.w = w_out;
+        aos[k] = p;
+    }
+}
+
 __global__ void score_to_double_kernel(const int32_t* score2, double* out, long long n)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

@@ -382,11 +382,11 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
 // ---- resampling: which groups do this rank's children draw from? ---------------------------------------------------------
 // Child m compares U_m = r + m/N with the running sum; its parent lies in the last group whose ENTRY sum is below U_m.
 // range[0], range[1] = first and last such group over the rank's children [lo, hi).
-__global__ void xresample_range_kernel(const double* cin2, long long n2, long long n, double r, long long lo, long long hi,
-                                       long long* range)
+__global__ void xresample_range_kernel(const double* cin2, long long n2, long long children, double r, long long lo,
+                                       long long hi, long long* range)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double m_inv = __ddiv_rn(1.0, (double)n);
+    const double m_inv = __ddiv_rn(1.0, (double)children);
     auto last_below = [&](double u) {
         long long a = 0, b = n2;                 // first j with !(cin2[j] < u)
         while (a < b) {
@@ -448,10 +448,11 @@ __global__ void __launch_bounds__(128) xseq_materialize_kernel(long long n, long
 }
 
 // Systematic search over the materialised range (same indices as resample_search_kernel over the whole array).
-__global__ void xresample_search_kernel(const double* cum, long long n, double r, long long lo, long long hi,
-                                        const long long* range, int32_t* idx, unsigned long long* overruns)
+// children: the number of draws the offsets U_m = r + m / children are spread over (N for the filter's resampling).
+__global__ void xresample_search_kernel(const double* cum, long long n, long long children, double r, long long lo,
+                                        long long hi, const long long* range, int32_t* idx, unsigned long long* overruns)
 {
-    const double m_inv = __ddiv_rn(1.0, (double)n);
+    const double m_inv = __ddiv_rn(1.0, (double)children);
     const long long first = range[0] * (long long)kSliceAlign;
     const long long lim = (range[1] + 1) * (long long)kSliceAlign < n ? (range[1] + 1) * (long long)kSliceAlign : n;
     const long long runs = (hi - lo + kSearchRun - 1) / kSearchRun;

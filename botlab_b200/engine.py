@@ -20,7 +20,7 @@ assert POSE_DTYPE.itemsize == 24 and PARTICLE_DTYPE.itemsize == 56
 SYMBOLS = [
     "mcl_default_params", "mcl_create", "mcl_destroy", "mcl_last_error", "mcl_stream", "mcl_sync",
     "mcl_comm_unique_id", "mcl_comm_init", "mcl_set_map", "mcl_update_map_rect", "mcl_read_map_rect", "mcl_map_update", "mcl_init_at_pose",
-    "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_action_reset", "mcl_action_update",
+    "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_export_weighted", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
     "mcl_set_gather_counting", "mcl_measure_gather_peak", "mcl_debug_sincosf", "mcl_debug_fast_trig_error", "mcl_debug_fast_margin", "mcl_debug_digest",
@@ -93,6 +93,7 @@ def lib():
         L.mcl_init_uniform.argtypes = [vp, i64, C.c_uint64]
         L.mcl_import_particles.argtypes = [vp, vp, i64]
         L.mcl_export_particles.argtypes = [vp, vp, i64, i64, vp]
+        L.mcl_export_weighted.argtypes = [vp, vp, i64, dp, vp]
         L.mcl_action_reset.argtypes = [vp]
         L.mcl_action_reset.restype = None
         L.mcl_action_update.argtypes = [vp, vp]
@@ -324,6 +325,13 @@ class Engine:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._ck(self._L.mcl_debug_fast_margin(self.h, C.addressof(a), C.addressof(b), C.addressof(c)))
         return a.value, b.value, c.value
+
+    def export_weighted(self, count, u01=0.5):
+        """`count` particles drawn by systematic sampling over the weights, each with weight 1/count."""
+        out = np.zeros(count, PARTICLE_DTYPE)
+        got = C.c_int64()
+        self._ck(self._L.mcl_export_weighted(self.h, _p(out), count, u01, C.addressof(got)))
+        return out[:got.value]
 
     def digest(self):
         """Four 64-bit position-sensitive sums over this rank's slice (indices, scores, weights, poses)."""

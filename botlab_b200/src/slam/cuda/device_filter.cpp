@@ -10,9 +10,21 @@ int defaultDevice(void)
     return s ? std::atoi(s) : 0;
 }
 
-DeviceFilter::DeviceFilter(int64_t numParticles, int device, const mcl_params* params)
-: engine_(nullptr), numParticles_(numParticles), mirrored_(nullptr), mirroredGeneration_(0)
+bool defaultLegacyEqualUtime(void)
 {
+    const char* s = std::getenv("B200_MCL_LEGACY_UTIME");
+    return s && std::atoi(s) != 0;
+}
+
+DeviceFilter::DeviceFilter(int64_t numParticles, int device, const mcl_params* params)
+: engine_(nullptr), numParticles_(numParticles), mirroredGeneration_(0), mirroredSeq_(0)
+{
+    mcl_params defaults;
+    if (!params) {
+        mcl_default_params(&defaults);
+        defaults.legacy_equal_utime = defaultLegacyEqualUtime() ? 1 : 0;
+        params = &defaults;
+    }
     int rc = mcl_create(params, numParticles, device, &engine_);
     if (rc != MCL_OK) throw EngineError(rc, std::string("mcl_create: ") + mcl_last_error(nullptr));
 }
@@ -29,21 +41,30 @@ void DeviceFilter::check(int rc) const
 
 void DeviceFilter::syncMap(const OccupancyGrid& map)
 {
-    if (mirrored_ != &map || mirroredGeneration_ != map.generation()) {
+    // generations are process-wide unique, so an equal generation means: the grid state this mirror was filled from,
+    // plus cell writes -- and those carry sequence numbers, of which this mirror remembers the last one it has seen
+    bool full = mirroredGeneration_ != map.generation();
+    int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+    if (!full) {
+        bool needFull = false;
+        if (!map.changesSince(mirroredSeq_, x0, y0, x1, y1, needFull)) { mirroredSeq_ = map.writeSeq(); return; }
+        full = needFull;
+    }
+    if (full) {
         check(mcl_set_map(engine_, map.data(), map.widthInCells(), map.heightInCells(), map.originInGlobalFrame().x,
                           map.originInGlobalFrame().y, map.metersPerCell(), map.cellsPerMeter()));
-        mirrored_ = &map;
         mirroredGeneration_ = map.generation();
-        map.clearDirty();
-        return;
-    }
-    int x0, y0, x1, y1;
-    if (map.dirtyRect(x0, y0, x1, y1)) {
+    } else {
         check(mcl_update_map_rect(engine_, x0, y0, x1 - x0 + 1, y1 - y0 + 1,
                                   map.data() + static_cast<std::size_t>(y0) * map.widthInCells() + x0,
                                   map.widthInCells()));
-        map.clearDirty();
     }
+    mirroredSeq_ = map.writeSeq();
+}
+
+void DeviceFilter::noteMirrorIsAheadOf(const OccupancyGrid& map, uint64_t seq)
+{
+    if (mirroredGeneration_ == map.generation() && seq == mirroredSeq_ + 2) mirroredSeq_ = seq;
 }
 
 }  // namespace b200

@@ -83,8 +83,8 @@ void Mapping::clearAlongRay(int x1, int y1, int x2, int y2, OccupancyGrid& map)
 }
 
 // The same update on the filter's map mirror: bring the mirror up to date with any host-side writes, run
-// mcl_map_update, read the rectangle that may have changed back into the host grid (without marking it dirty: the
-// mirror already holds those values).
+// mcl_map_update, read the rectangle that may have changed back into the host grid and register it as written (any other
+// mirror of the grid picks it up; this one is told it already holds those values).
 void Mapping::updateMapOnDevice(const lidar_t& scan, const pose_xyt_t& pose, OccupancyGrid& map)
 {
     b200::DeviceFilter& dev = deviceFilter_->device();
@@ -95,8 +95,10 @@ void Mapping::updateMapOnDevice(const lidar_t& scan, const pose_xyt_t& pose, Occ
     int rect[4] = {0, 0, 0, 0};
     dev.check(mcl_map_update(dev.engine(), &prev, &cur, initialized_ ? 1 : 0, scan.ranges.data(), scan.thetas.data(),
                              scan.times.data(), scan.num_ranges, kMaxLaserDistance_, kHitOdds_, kMissOdds_, rect));
-    if (rect[2] > 0 && rect[3] > 0)
+    if (rect[2] > 0 && rect[3] > 0) {
         dev.check(mcl_read_map_rect(dev.engine(), rect[0], rect[1], rect[2], rect[3],
                                     map.mirrorData() + static_cast<std::size_t>(rect[1]) * map.widthInCells() + rect[0],
                                     map.widthInCells()));
+        dev.noteMirrorIsAheadOf(map, map.noteExternalWrite(rect[0], rect[1], rect[0] + rect[2] - 1, rect[1] + rect[3] - 1));
+    }
 }

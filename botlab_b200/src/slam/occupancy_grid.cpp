@@ -1,18 +1,26 @@
 #include <slam/occupancy_grid.hpp>
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
 
+namespace {
+std::atomic<uint64_t> g_nextGeneration(1);     // process-wide: no two grid states ever share a generation
+const std::size_t kHistory = 32;
+}
+
 OccupancyGrid::OccupancyGrid(void)
-: width_(0), height_(0), metersPerCell_(0.05f), cellsPerMeter_(1.0 / metersPerCell_), globalOrigin_(0, 0), generation_(0)
+: width_(0), height_(0), metersPerCell_(0.05f), cellsPerMeter_(1.0 / metersPerCell_), globalOrigin_(0, 0), generation_(0),
+  writeSeq_(0), historyFloor_(0)
 {
     wholeGridChanged();
 }
 
 OccupancyGrid::OccupancyGrid(float widthInMeters, float heightInMeters, float metersPerCell)
-: metersPerCell_(metersPerCell), globalOrigin_(-widthInMeters / 2.0f, -heightInMeters / 2.0f), generation_(0)
+: metersPerCell_(metersPerCell), globalOrigin_(-widthInMeters / 2.0f, -heightInMeters / 2.0f), generation_(0),
+  writeSeq_(0), historyFloor_(0)
 {
     if (!(widthInMeters > 0.0f) || !(heightInMeters > 0.0f) || !(metersPerCell > 0.0f) ||
         metersPerCell > widthInMeters || metersPerCell > heightInMeters)
@@ -24,10 +32,33 @@ OccupancyGrid::OccupancyGrid(float widthInMeters, float heightInMeters, float me
     wholeGridChanged();
 }
 
+OccupancyGrid::OccupancyGrid(const OccupancyGrid& o)
+: cells_(o.cells_), width_(o.width_), height_(o.height_), metersPerCell_(o.metersPerCell_), cellsPerMeter_(o.cellsPerMeter_),
+  globalOrigin_(o.globalOrigin_), generation_(0), writeSeq_(0), historyFloor_(0)
+{
+    wholeGridChanged();
+}
+
+OccupancyGrid& OccupancyGrid::operator=(const OccupancyGrid& o)
+{
+    if (this != &o) {
+        cells_ = o.cells_;
+        width_ = o.width_; height_ = o.height_;
+        metersPerCell_ = o.metersPerCell_; cellsPerMeter_ = o.cellsPerMeter_;
+        globalOrigin_ = o.globalOrigin_;
+        wholeGridChanged();
+    }
+    return *this;
+}
+
 void OccupancyGrid::wholeGridChanged(void)
 {
-    ++generation_;
-    clearDirty();
+    generation_ = g_nextGeneration.fetch_add(1);
+    open_.x0 = open_.y0 = INT_MAX;
+    open_.x1 = open_.y1 = INT_MIN;
+    open_.firstSeq = open_.lastSeq = writeSeq_;
+    history_.clear();
+    historyFloor_ = writeSeq_;
 }
 
 void OccupancyGrid::setOrigin(float x, float y)
@@ -60,18 +91,37 @@ void OccupancyGrid::setLogOdds(int x, int y, CellOdds value)
     cells_[cellIndex(x, y)] = value;
 }
 
-bool OccupancyGrid::dirtyRect(int& x0, int& y0, int& x1, int& y1) const
+bool OccupancyGrid::changesSince(uint64_t seq, int& x0, int& y0, int& x1, int& y1, bool& needFull) const
 {
-    if (dirtyX1_ < dirtyX0_ || dirtyY1_ < dirtyY0_) return false;
-    x0 = std::max(dirtyX0_, 0); y0 = std::max(dirtyY0_, 0);
-    x1 = std::min(dirtyX1_, width_ - 1); y1 = std::min(dirtyY1_, height_ - 1);
+    needFull = false;
+    if (seq >= writeSeq_) return false;
+    if (open_.x1 >= open_.x0) {            // close the rectangle being collected: it becomes one history entry
+        history_.push_back(open_);
+        open_.x0 = open_.y0 = INT_MAX;
+        open_.x1 = open_.y1 = INT_MIN;
+        if (history_.size() > kHistory) {
+            historyFloor_ = history_.front().lastSeq;
+            history_.erase(history_.begin());
+        }
+    }
+    if (seq < historyFloor_) { needFull = true; return true; }
+    int ax0 = INT_MAX, ay0 = INT_MAX, ax1 = INT_MIN, ay1 = INT_MIN;
+    for (std::size_t i = 0; i < history_.size(); ++i) {
+        const Span& sp = history_[i];
+        if (sp.lastSeq <= seq) continue;
+        ax0 = std::min(ax0, sp.x0); ay0 = std::min(ay0, sp.y0);
+        ax1 = std::max(ax1, sp.x1); ay1 = std::max(ay1, sp.y1);
+    }
+    x0 = std::max(ax0, 0); y0 = std::max(ay0, 0);
+    x1 = std::min(ax1, width_ - 1); y1 = std::min(ay1, height_ - 1);
     return x1 >= x0 && y1 >= y0;
 }
 
-void OccupancyGrid::clearDirty(void) const
+uint64_t OccupancyGrid::noteExternalWrite(int x0, int y0, int x1, int y1)
 {
-    dirtyX0_ = dirtyY0_ = INT_MAX;
-    dirtyX1_ = dirtyY1_ = INT_MIN;
+    touch(x0, y0);
+    touch(x1, y1);
+    return writeSeq_;
 }
 
 occupancy_grid_t OccupancyGrid::toLCM(void) const

@@ -1,6 +1,7 @@
 // OccupancyGrid -- host-side int8 log-odds grid with the reference's public interface (src/slam/occupancy_grid.hpp:
-// 62-194 in the reference) plus what the device mirror needs: a dirty rectangle of cells written since the mirror was
-// last refreshed.  The map changes on every SLAM iteration, even with --localization-only (the mode test at
+// 62-194 in the reference) plus what device mirrors need: a process-wide unique generation (whole-grid changes) and a
+// short history of written rectangles stamped with a write sequence, so that ANY number of mirrors can each ask "what
+// changed since I last looked".  The map changes on every SLAM iteration, even with --localization-only (the mode test at
 // slam.cpp:276 is always true), so ParticleFilter patches the mirror with mcl_update_map_rect before each update.
 #ifndef B200_SLAM_OCCUPANCY_GRID_HPP
 #define B200_SLAM_OCCUPANCY_GRID_HPP
@@ -20,6 +21,9 @@ public:
     OccupancyGrid(void);
     /// Grid centred on the global origin.  \pre all three > 0 and metersPerCell <= both extents
     OccupancyGrid(float widthInMeters, float heightInMeters, float metersPerCell);
+    /// Copies get a generation of their own: a mirror of the source is never mistaken for a mirror of the copy.
+    OccupancyGrid(const OccupancyGrid& other);
+    OccupancyGrid& operator=(const OccupancyGrid& other);
 
     int   widthInCells(void) const { return width_; }
     float widthInMeters(void) const { return width_ * metersPerCell_; }
@@ -47,13 +51,18 @@ public:
 
     // ---- device-mirror support (not in the reference) ----
     const CellOdds* data(void) const { return cells_.data(); }
-    /// Writable storage for values read back FROM the device mirror: writing through it does not mark cells dirty.
-    CellOdds* mirrorData(void) { return cells_.data(); }
-    /// Bumped whenever the geometry or the whole content changes (ctor, reset, setOrigin, fromLCM, loadFromFile).
+    /// Drawn from a process-wide counter whenever the geometry or the whole content changes (ctors, copies, reset,
+    /// setOrigin, fromLCM, loadFromFile): equal generations mean the same grid object in the same whole-grid state.
     uint64_t generation(void) const { return generation_; }
-    /// Bounding box [x0,x1] x [y0,y1] of cells written since clearDirty(); false if none.
-    bool dirtyRect(int& x0, int& y0, int& x1, int& y1) const;
-    void clearDirty(void) const;
+    /// Sequence number of the last cell write (setLogOdds, non-const operator(), noteExternalWrite).
+    uint64_t writeSeq(void) const { return writeSeq_; }
+    /// Bounding box [x0,x1] x [y0,y1] of the cells written after write sequence `seq`.  Returns false when nothing was.
+    /// needFull is set when the history no longer reaches back to `seq` (the caller must take the whole grid).
+    bool changesSince(uint64_t seq, int& x0, int& y0, int& x1, int& y1, bool& needFull) const;
+    /// Writable storage for values read back FROM a device mirror, followed by noteExternalWrite(rect): the cells count
+    /// as written (other mirrors will pick them up); the returned sequence is what the originating mirror has seen.
+    CellOdds* mirrorData(void) { return cells_.data(); }
+    uint64_t noteExternalWrite(int x0, int y0, int x1, int y1);
 
 private:
     std::vector<CellOdds> cells_;
@@ -64,15 +73,23 @@ private:
     Point<float> globalOrigin_;
 
     uint64_t generation_;
-    mutable int dirtyX0_, dirtyY0_, dirtyX1_, dirtyY1_;
+    uint64_t writeSeq_;
+    // rectangle of the writes since the last changesSince() call, and a short history of the closed ones
+    struct Span { uint64_t firstSeq, lastSeq; int x0, y0, x1, y1; };
+    mutable Span open_;
+    mutable std::vector<Span> history_;
+    mutable uint64_t historyFloor_;     // writes with a sequence <= this are no longer in history_
 
     int cellIndex(int x, int y) const { return y * width_ + x; }
     void touch(int x, int y)
     {
-        if (x < dirtyX0_) dirtyX0_ = x;
-        if (x > dirtyX1_) dirtyX1_ = x;
-        if (y < dirtyY0_) dirtyY0_ = y;
-        if (y > dirtyY1_) dirtyY1_ = y;
+        ++writeSeq_;
+        if (open_.x1 < open_.x0) open_.firstSeq = writeSeq_;
+        open_.lastSeq = writeSeq_;
+        if (x < open_.x0) open_.x0 = x;
+        if (x > open_.x1) open_.x1 = x;
+        if (y < open_.y0) open_.y0 = y;
+        if (y > open_.y1) open_.y1 = y;
     }
     void wholeGridChanged(void);
 };

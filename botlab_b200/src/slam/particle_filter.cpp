@@ -6,10 +6,17 @@
 #include <stdexcept>
 
 ParticleFilter::ParticleFilter(int numParticles)
-: kNumParticles_(numParticles), seed_(0x6d636cULL), maxExported_(numParticles), injectedNoise_(nullptr)
+: kNumParticles_(numParticles), seed_(0x6d636cULL), maxExported_(numParticles), exportWeighted_(false), injectedNoise_(nullptr)
 {
     if (numParticles <= 1) throw std::invalid_argument("ParticleFilter needs more than one particle");
     device_.reset(new b200::DeviceFilter(numParticles, b200::defaultDevice()));
+}
+
+ParticleFilter::ParticleFilter(int numParticles, const mcl_params& params)
+: kNumParticles_(numParticles), seed_(0x6d636cULL), maxExported_(numParticles), exportWeighted_(false), injectedNoise_(nullptr)
+{
+    if (numParticles <= 1) throw std::invalid_argument("ParticleFilter needs more than one particle");
+    device_.reset(new b200::DeviceFilter(numParticles, b200::defaultDevice(), &params));
 }
 
 ParticleFilter::~ParticleFilter(void) = default;
@@ -67,6 +74,18 @@ particles_t ParticleFilter::particles(void) const
 {
     particles_t out;
     const int64_t cap = maxExported_ > 0 ? maxExported_ : kNumParticles_;
+    if (exportWeighted_ && cap < kNumParticles_) {
+        // a weighted draw of `cap` particles (equal weights) instead of every k-th one: what a viewer of a large cloud
+        // wants to see is where the probability mass is
+        out.particles.resize(static_cast<std::size_t>(cap));
+        int64_t n = 0;
+        device_->check(mcl_export_weighted(device_->engine(), reinterpret_cast<mcl_particle_t*>(out.particles.data()), cap,
+                                           0.5, &n));
+        out.particles.resize(static_cast<std::size_t>(n));
+        out.num_particles = static_cast<int32_t>(n);
+        out.utime = posteriorPose_.utime;
+        return out;
+    }
     const int64_t stride = (kNumParticles_ + cap - 1) / cap;
     out.particles.resize(static_cast<std::size_t>((kNumParticles_ + stride - 1) / stride));
     int64_t n = 0;

@@ -21,6 +21,9 @@ class ParticleFilter
 public:
     /// \pre numParticles > 1
     ParticleFilter(int numParticles);
+    /// Extension: explicit engine parameters (e.g. legacy_equal_utime = 1 for the unmodified reference's de-facto
+    /// behaviour); the one-argument form takes the defaults and the B200_MCL_LEGACY_UTIME environment knob.
+    ParticleFilter(int numParticles, const mcl_params& params);
     ~ParticleFilter(void);
 
     /// Cloud ~ pose + N(0, 0.01) per coordinate, last particle exactly at pose, weights 1/N.
@@ -42,6 +45,9 @@ public:
     // ---- extensions (not in the reference) ----
     void setMaxExportedParticles(int64_t n) { maxExported_ = n; }
     int64_t maxExportedParticles(void) const { return maxExported_; }
+    /// particles() of a cloud larger than maxExportedParticles(): false (default) = every k-th particle with its weight;
+    /// true = a systematic weighted draw of maxExportedParticles() particles, each with weight 1/count.
+    void setExportWeighted(bool on) { exportWeighted_ = on; }
     /// Seeds both the device Philox stream (used from the next initializeFilterAtPose) and libc rand().
     void setSeed(uint64_t seed);
     mcl_stats stats(void) const;
@@ -60,6 +66,7 @@ private:
     std::unique_ptr<b200::DeviceFilter> device_;
     uint64_t seed_;
     int64_t maxExported_;
+    bool exportWeighted_;
     const float* injectedNoise_;
 };
 

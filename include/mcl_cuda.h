@@ -140,6 +140,12 @@ int  mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n);
 /* With mcl_comm_init'd engines export is COLLECTIVE (every rank calls it): parent poses are exchanged first. */
 int  mcl_export_particles(mcl_engine* h, mcl_particle_t* aos, int64_t max_n, int64_t stride, int64_t* n_out);
 
+/* A WEIGHTED sub-sample for SLAM_PARTICLES consumers (botgui draws the cloud from stack arrays, drawing_functions.cpp:
+ * 123-125, so it cannot take millions): `count` particles drawn by systematic sampling over the normalised weights
+ * (the filter's own resampling rule with `count` draws, offset u01 in [0, 1)), each exported with weight 1/count.
+ * The weights must sum to 1 (after mcl_init_*, mcl_update or mcl_normalize).  Single-GPU engines. */
+int  mcl_export_weighted(mcl_engine* h, mcl_particle_t* aos, int64_t count, double u01, int64_t* n_out);
+
 /* ---- host-side scalar part of the action model: ActionModel::updateAction (action_model.cpp:22-75) ------------- */
 void mcl_action_reset(mcl_action_t* a);
 int  mcl_action_update(mcl_action_t* a, const mcl_pose_t* odometry);   /* returns moved (1/0) */

@@ -125,6 +125,24 @@ int main(int argc, char** argv)
                     "\"launches\": %d, \"ms_total\": %.4f",
                     cloud.num_particles, wsum, (long long)st.updates, (long long)st.evals, st.kernel_launches,
                     st.ms_total);
+        // several mirrors of one grid: the filter's engine and the stand-alone SensorModel's engine both
+        // mirror `map`; writes one of them has already picked up must still reach the other, and a grid assigned from
+        // another grid must be re-mirrored even though both were constructed alike
+        {
+            for (int y = 96; y < 104; ++y)
+                for (int x = 112; x < 120; ++x) map.setLogOdds(x, y, (CellOdds)90);      // a block 0.6 m in front of (0, 0)
+            pose.x += 0.05f; pose.utime += 100000;
+            pf.updateFilter(pose, marchScan(map, pose.x, pose.y, pose.theta, pose.utime), map);   // the filter's mirror syncs first
+            SensorModel fresh;                                                       // full upload of the current grid
+            const double incremental = sm.likelihood(kp[0], ks, map), full = fresh.likelihood(kp[0], ks, map);
+            OccupancyGrid a(10.0f, 10.0f, 0.05f), b(10.0f, 10.0f, 0.05f);
+            for (int x = 20; x < 180; ++x) b.setLogOdds(x, 130, (CellOdds)70);
+            SensorModel follower;
+            const double before = follower.likelihood(kp[0], ks, a);
+            a = b;                                                                   // same object, new content
+            const double after = follower.likelihood(kp[0], ks, a), want = fresh.likelihood(kp[0], ks, b);
+            std::printf(", \"mirrors\": [%.17g, %.17g, %.17g, %.17g, %.17g]", incremental, full, before, after, want);
+        }
         // action-only mode
         pose.x += 0.05f; pose.utime += 100000;
         const pose_xyt_t ao = pf.updateFilterActionOnly(pose);

@@ -356,6 +356,28 @@ def test_export_stride_and_cap():
     e.close()
 
 
+def test_export_weighted_subsample(real_map):
+    """a weighted sub-sample for SLAM_PARTICLES consumers.  mcl_export_weighted draws `count` particles by
+    systematic sampling over the weights' sequential running sum; the picks equal a numpy restatement of the rule."""
+    n, count, u01 = 50_000, 777, 0.3125
+    cloud = synth.make_particles(n, (0.5, -0.25, 0.3), seed=21)
+    w = synth.filter_shaped_weights(n, seed=21)
+    cloud["weight"] = w
+    e = make_engine(n, real_map)
+    e.import_particles(cloud)
+    got = e.export_weighted(count, u01)
+    cum = np.cumsum(w)                                   # sequential double sum, like the reference's loop
+    step = 1.0 / count
+    u = (u01 / count) + np.arange(count, dtype=np.float64) * step
+    idx = np.minimum(np.searchsorted(cum, u, side="left"), n - 1)
+    assert len(got) == count and np.array_equal(got["weight"], np.full(count, 1.0 / count))
+    for k in ("pose", "parent_pose"):
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(got[k][f], cloud[k][f][idx]), (k, f)
+    assert (np.diff(idx) >= 0).all() and len(np.unique(idx)) > count // 2
+    e.close()
+
+
 def test_import_rejects_mixed_utimes():
     p = synth.make_particles(100, (0, 0, 0), seed=8)
     p["pose"]["utime"][50] += 1
