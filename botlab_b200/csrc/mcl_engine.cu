@@ -118,6 +118,9 @@ struct mcl_engine {
     // map mirror
     int8_t* map = nullptr;
     int8_t* map_fast = nullptr;         // the fast pass's derived view of the map (derive_fast_map_kernel), same pitch
+    int8_t* map_lf = nullptr;           // likelihood field (sensor_mode 1), same pitch; rebuilt lazily after map changes
+    uint16_t* dt_steps = nullptr;       // distance-transform scratch: [H][W] steps
+    bool lf_dirty = true;
     DevGrid grid{};
     float meters_per_cell = 0.05f;
     bool have_map = false;
@@ -319,6 +322,7 @@ int join_pushes(mcl_engine* h)
 // Refreshes the fast pass's derived map over the rectangle [x0, x0+w) x [y0, y0+hgt) widened by the 2-cell look-ahead.
 int refresh_fast_map(mcl_engine* h, int x0, int y0, int w, int hgt)
 {
+    h->lf_dirty = true;
     const int xa = std::max(0, x0 - 2), ya = std::max(0, y0 - 2);
     const int xb = std::min(h->grid.width, x0 + w + 2), yb = std::min(h->grid.height, y0 + hgt + 2);
     if (xb <= xa || yb <= ya) return MCL_OK;
@@ -521,6 +525,30 @@ FastPlan fast_plan(const mcl_engine* h, long long x0, long long y0, long long w,
     return fp;
 }
 
+// ---- distance transform of the mirror (mcl_kernels.cuh: dt_*_kernel) ------------------------------------------------------
+int run_distance_transform(mcl_engine* h, int thr)
+{
+    const int W = h->grid.width, H = h->grid.height;
+    if (!h->dt_steps) CK(cudaMalloc((void**)&h->dt_steps, sizeof(uint16_t) * (size_t)W * H));
+    dt_columns_kernel<<<(W + 127) / 128, 128, 0, h->stream>>>(h->map, W, H, h->grid.pitch, thr, h->dt_steps);
+    CKL(h);
+    dt_rows_kernel<<<(H + 127) / 128, 128, 0, h->stream>>>(W, H, h->dt_steps);
+    CKL(h);
+    return MCL_OK;
+}
+
+int refresh_likelihood_field(mcl_engine* h)
+{
+    if (!h->lf_dirty) return MCL_OK;
+    int rc = run_distance_transform(h, 1);          // steps to the nearest OCCUPIED cell
+    if (rc) return rc;
+    lf_field_kernel<<<grid_for(h, (long long)h->grid.width * h->grid.height, 256), 256, 0, h->stream>>>(
+        h->dt_steps, h->grid.width, h->grid.height, h->grid.pitch, h->map_lf);
+    CKL(h);
+    h->lf_dirty = false;
+    return MCL_OK;
+}
+
 // ---- table sensor path (mcl_table.cuh) ------------------------------------------------------------------------------
 // Launch order on the engine's stream: bbox_kernel -> table_plan_kernel (one thread: window + budget, in device memory)
 // -> score_table_kernel.  No host round trip: the host only needs to know whether the table pass is APPLICABLE, and
@@ -534,17 +562,19 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
 {
     const long long local = h->hi - h->lo;
     const int lanes = h->params.lanes_per_particle;
-    const bool cand = h->params.sensor_path == 0 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
-                      local >= kTabMinParticles && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
+    const bool lf = h->params.sensor_mode == 1;
+    const bool cand = (lf || (h->params.sensor_path == 0 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
+                              local >= kTabMinParticles)) && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
                       std::isfinite(h->max_range) && !std::getenv("MCL_NO_TABLE");
-    if (!cand) return 0;
+    if (!cand) return lf ? fail(h, MCL_ERR_INVALID, "the likelihood-field mode needs a finite scan of at most %d beams", kTabMaxBeams) : 0;
+    if (lf) { int rc = refresh_likelihood_field(h); if (rc) return rc; }
     if (h->tab_hint_pending && cudaEventQuery(h->ev_tab_hint) == cudaSuccess) {
         h->tab_hint_pending = false;
         h->tab_ok = h->tab_hint->plan.ok != 0;
         if (h->tab_hint->build[1] != 0) { h->tab_ok = false; h->tab_blocked = 64; }
         if (h->tab_ok) h->stats_eps = h->tab_hint->plan.eps;
     }
-    if (h->tab_blocked > 0) { --h->tab_blocked; return 0; }
+    if (h->tab_blocked > 0 && !lf) { --h->tab_blocked; return 0; }
     const size_t smem_total = (size_t)h->max_smem_optin - 1024;      // static shared memory of the kernel stays below 1 KB
     TabPlanIn in{};
     in.grid = h->grid;
@@ -565,7 +595,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
         CK(cudaStreamSynchronize(h->stream));
         h->tab_hint_pending = false;
         h->tab_ok = h->tab_hint->plan.ok != 0;
-        if (!h->tab_ok) return 0;
+        if (!h->tab_ok && !lf) return 0;      // (likelihood-field mode: the kernel then scores every ray exactly, from the field)
         h->stats_eps = h->tab_hint->plan.eps;
     }
     TabArgs a{};
@@ -575,6 +605,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     a.beams = sa.beams; a.num_beams = sa.num_beams;
     a.grid = sa.grid;
     a.fast_cells = sa.fast_cells;
+    a.lf_cells = lf ? h->map_lf : nullptr;
     a.plan = h->tab_plan;
     a.gather_counter = sa.gather_counter;
     a.deferred_counter = sa.deferred_counter;
@@ -984,7 +1015,7 @@ void free_all(mcl_engine* h)
     F(h->opened); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
     if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
     if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
-    F(h->ess_acc); F(h->bbox); F(h->est_out); F(h->map); F(h->map_fast); F(h->beams); F(h->noise); F(h->staging);
+    F(h->ess_acc); F(h->bbox); F(h->est_out); F(h->map); F(h->map_fast); F(h->map_lf); F(h->dt_steps); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
     if (h->host_bbox) cudaFreeHost(h->host_bbox);
@@ -1013,6 +1044,7 @@ void mcl_default_params(mcl_params* p)
     p->map_tile = 0;
     p->sensor_path = 0;
     p->weight_mode = 0;
+    p->sensor_mode = 0;
     p->lse_beta = 0.05;
 }
 
@@ -1265,10 +1297,17 @@ int mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float
     CK(cudaSetDevice(h->device));
     const int pitch = (width + 15) & ~15;     // 16-byte rows: aligned word loads for the tile stager (and TMA-ready)
     if (!h->map || h->grid.pitch != pitch || h->grid.height != height) {
-        if (h->map) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->map); cudaFree(h->map_fast); h->map = h->map_fast = nullptr; }
+        if (h->map) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(h->map); cudaFree(h->map_fast); cudaFree(h->map_lf); cudaFree(h->dt_steps);
+            h->map = h->map_fast = h->map_lf = nullptr; h->dt_steps = nullptr;
+        }
         CK(cudaMalloc((void**)&h->map, (size_t)pitch * height + 16));
         CK(cudaMalloc((void**)&h->map_fast, (size_t)pitch * height + 16));
+        CK(cudaMalloc((void**)&h->map_lf, (size_t)pitch * height + 16));
     }
+    if (h->dt_steps && (h->grid.width != width || h->grid.height != height)) { cudaFree(h->dt_steps); h->dt_steps = nullptr; }
+    CK(cudaMemsetAsync(h->map_lf, 0, (size_t)pitch * height + 16, h->stream));
     CK(cudaMemsetAsync(h->map, 0, (size_t)pitch * height + 16, h->stream));
     CK(cudaMemsetAsync(h->map_fast, 0, (size_t)pitch * height + 16, h->stream));
     CK(cudaMemcpy2DAsync(h->map, pitch, cells, width, width, height, cudaMemcpyHostToDevice, h->stream));
@@ -1307,6 +1346,33 @@ int mcl_read_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, int8_t* dst
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpy2DAsync(dst, dst_stride, h->map + (size_t)y0 * h->grid.pitch + x0, h->grid.pitch, w, hgt,
                          cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+// ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:73-188) of the mirror.
+int mcl_distance_grid(mcl_engine* h, float* out)
+{
+    if (!h || !out) return fail(h, MCL_ERR_INVALID, "null argument");
+    if (!h->have_map) return fail(h, MCL_ERR_STATE, "mcl_set_map has not been called");
+    CK(cudaSetDevice(h->device));
+    const int W = h->grid.width, H = h->grid.height;
+    int rc = run_distance_transform(h, 0);          // the reference's sources: log-odds >= 0 (occupied or unknown)
+    if (rc) return rc;
+    h->lf_dirty = true;                             // the scratch no longer holds the likelihood field's steps
+    // d_k = fl(d_{k-1} + 0.1f): the reference adds 0.1f once per step (:179)
+    std::vector<float> table((size_t)W + H + 2);
+    table[0] = 0.0f;
+    for (size_t k = 1; k < table.size(); ++k) table[k] = table[k - 1] + 0.1f;
+    const size_t cells = (size_t)W * H;
+    rc = ensure_staging(h, sizeof(float) * (cells + table.size()));
+    if (rc) return rc;
+    float* dtab = (float*)h->staging + cells;
+    CK(cudaMemcpyAsync(dtab, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice, h->stream));
+    dt_to_float_kernel<<<grid_for(h, (long long)cells, 256), 256, 0, h->stream>>>(h->dt_steps, (long long)cells, dtab,
+                                                                                (int)table.size(), (float*)h->staging);
+    CKL(h);
+    CK(cudaMemcpyAsync(out, h->staging, sizeof(float) * cells, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return MCL_OK;
 }

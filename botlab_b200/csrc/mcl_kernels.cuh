@@ -1120,6 +1120,60 @@ __global__ void derive_fast_map_kernel(const int8_t* cells, int8_t* out, int wid
 }
 
 // =================================================================================================================
+// Obstacle-distance grid of the mirror: planning/obstacle_distance_grid.cpp:73-188 runs a four-connected brushfire from
+// every cell with log-odds >= 0 (occupied OR unknown) over the free cells, all steps costing the same, so a free cell's
+// distance is its Manhattan distance (in steps) to the nearest such cell -- which two separable sweeps compute exactly:
+// down and up every column, then left and right along every row.  thr selects the sources: cells >= thr (0 = the
+// reference's rule; 1 = occupied cells only, for the likelihood field).  65535 = no source anywhere.
+// =================================================================================================================
+constexpr unsigned kDtInf = 65535u;
+__global__ void dt_columns_kernel(const int8_t* cells, int width, int height, int pitch, int thr, uint16_t* steps)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= width) return;
+    unsigned d = kDtInf;
+    for (int y = 0; y < height; ++y) {
+        d = (int)cells[(size_t)y * pitch + x] >= thr ? 0u : min(d + 1u, kDtInf);
+        steps[(size_t)y * width + x] = (uint16_t)d;
+    }
+    d = kDtInf;
+    for (int y = height - 1; y >= 0; --y) {
+        d = min((unsigned)steps[(size_t)y * width + x], min(d + 1u, kDtInf));
+        steps[(size_t)y * width + x] = (uint16_t)d;
+    }
+}
+__global__ void dt_rows_kernel(int width, int height, uint16_t* steps)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= height) return;
+    uint16_t* row = steps + (size_t)y * width;
+    unsigned d = kDtInf;
+    for (int x = 0; x < width; ++x) { d = min((unsigned)row[x], min(d + 1u, kDtInf)); row[x] = (uint16_t)d; }
+    d = kDtInf;
+    for (int x = width - 1; x >= 0; --x) { d = min((unsigned)row[x], min(d + 1u, kDtInf)); row[x] = (uint16_t)d; }
+}
+// steps -> the reference's float distances: d_k = fl(d_{k-1} + 0.1f) (obstacle_distance_grid.cpp:179; the table is
+// built on the host), -1 where the brushfire never arrives.
+__global__ void dt_to_float_kernel(const uint16_t* steps, long long count, const float* table, int table_len, float* out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned d = steps[i];
+        out[i] = d == kDtInf ? -1.0f : table[min((int)d, table_len - 1)];
+    }
+}
+// Likelihood field of the non-parity sensor mode: u = max(0, 127 - 8 d^2), d = steps to the nearest OCCUPIED cell
+// (> 0): 127 on a wall, 119 / 95 / 55 one / two / three steps away, 0 beyond.
+__host__ __device__ inline int lf_value(unsigned d) { return d >= 4u ? 0 : 127 - 8 * (int)(d * d); }
+__global__ void lf_field_kernel(const uint16_t* steps, int width, int height, int pitch, int8_t* lf)
+{
+    const long long total = (long long)width * height;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+        lf[(size_t)y * pitch + x] = (int8_t)lf_value(steps[i]);
+    }
+}
+
+// =================================================================================================================
 // K5  map update on the device mirror: Mapping::updateMap (mapping.cpp:17-127).
 // The reference raises the endpoint cell of every ray by hitOdds (saturating at 127), THEN lowers every cell of each
 // ray's Bresenham walk (start cell up to, not including, the endpoint cell) by missOdds (saturating at -128), one ray

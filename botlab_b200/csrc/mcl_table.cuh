@@ -232,6 +232,7 @@ struct TabConst {
     unsigned kbase;         // shared address of K minus the bias of both axes
     unsigned k0;            // shared address of T / 8: the K tile stores class + k0
     unsigned k129;          // k0 + kTabFixed
+    unsigned lf;            // likelihood-field mode (gather counting only)
 };
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c)
@@ -281,7 +282,7 @@ __device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, flo
     const bool dir_ok = x2_pos & (fabsf(__fsub_rn(fabsf(u8), kTabB2)) > d8);
     const bool certain = (K == tc.k0) | (cell_ok & ((K < tc.k129) | dir_ok));
     add = certain ? (int)v : 0;
-    if (COUNT) gathers += certain ? (K - tc.k0 - 2u < 127u ? 1 : 3) : 0;
+    if (COUNT) gathers += certain ? ((K - tc.k0 - 2u < 127u) | (tc.lf != 0u) ? 1 : 3) : 0;
     return certain;
 }
 
@@ -293,6 +294,7 @@ struct TabArgs {
     int num_beams;
     DevGrid grid;                   // the mirror itself (exact path, table build)
     const int8_t* fast_cells;       // derived map: -1 = nothing positive within two cells
+    const int8_t* lf_cells;         // likelihood-field mode (sensor_mode 1): the field u (0..127), same pitch; else null
     const TabPlan* plan;
     unsigned long long* gather_counter;
     unsigned long long* deferred_counter;
@@ -308,6 +310,7 @@ struct TabCold {
     const uint16_t* ktile;      // class tile (null: not built -- read the mirror)
     int x0, y0, w, h, pitch_k;
     unsigned k0;
+    int lf;                     // likelihood-field mode: a ray scores 2 u(endpoint cell), no neighbour steps
     unsigned long long deferred, gathers;
 };
 
@@ -345,7 +348,7 @@ __device__ __noinline__ void tab_drain_round(unsigned entry, bool active, float 
         const int ex = f2i_x86(e1x), ey = f2i_x86(e1y);                                   // sensor_model.cpp:34-35
         int v, g = 1;
         const int odds = tab_cell_value(cold, ex, ey);                                    // :41
-        if (odds > 0) {
+        if (odds > 0 || cold->lf) {
             v = 2 * odds;
         } else {
             const int xx = f2i_x86(__fadd_rn(__fmul_rn(2.0f, px), sx));                   // :37-38
@@ -484,6 +487,20 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
                 K = 0u;        // the reference's (truncated) endpoint cell and its neighbours are all outside the grid
             } else if (gxc < 0 || gyc < 0) {
                 K = 1u;        // truncation toward zero differs from the floor here: never certified (tab_eval, EDGE 2)
+            } else if (a.lf_cells) {
+                // likelihood field: every class is uniform (the ray scores the field value of its endpoint cell);
+                // class 0 = the field is 0 on the cell and on its eight neighbours (certain whatever the exact cell)
+                auto lfc = [&](int cx, int cy) -> int {
+                    return ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) ? (int)__ldg(a.lf_cells + (size_t)cy * gp + cx) : 0;
+                };
+                const int u = lfc(gxc, gyc);
+                if (u > 0) K = 1u + (unsigned)u;
+                else {
+                    int mx = 0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) mx = max(mx, lfc(gxc + dx, gyc + dy));
+                    K = mx > 0 ? 1u : 0u;
+                }
             } else {
                 int f;
                 if (gxc < W && gyc < H) {
@@ -536,6 +553,8 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
             if (s_overflow) atomicAdd(a.build_info + 1, 1);
         }
         s_cold.grid = a.grid; s_cold.sbeams = sbeams; s_cold.deferred = 0ull; s_cold.gathers = 0ull;
+        s_cold.lf = a.lf_cells ? 1 : 0;
+        if (a.lf_cells) s_cold.grid.cells = a.lf_cells;         // the exact path reads the field outside the window
         s_cold.ktile = degrade ? nullptr : ktile;
         s_cold.x0 = pl.x0; s_cold.y0 = pl.y0; s_cold.w = pl.w; s_cold.h = pl.h; s_cold.pitch_k = pl.pitch_k;
         s_cold.k0 = k0;
@@ -549,6 +568,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     tc.kbase = sk - pl.bias_y * tc.pitch2 - pl.bias_x * 2u;
     tc.k0 = k0;
     tc.k129 = k0 + (unsigned)kTabFixed;
+    tc.lf = a.lf_cells ? 1u : 0u;
     const double gx = (double)a.grid.origin_x, gy = (double)a.grid.origin_y, cpm_d = (double)cpm;
     const int nwords = (nb + 31) / 32;
     uint16_t* q = squeue + warp * kTabQueue;

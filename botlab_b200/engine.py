@@ -19,7 +19,7 @@ assert POSE_DTYPE.itemsize == 24 and PARTICLE_DTYPE.itemsize == 56
 # every symbol include/mcl_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "mcl_default_params", "mcl_create", "mcl_destroy", "mcl_last_error", "mcl_stream", "mcl_sync",
-    "mcl_comm_unique_id", "mcl_comm_init", "mcl_set_map", "mcl_update_map_rect", "mcl_read_map_rect", "mcl_map_update", "mcl_init_at_pose",
+    "mcl_comm_unique_id", "mcl_comm_init", "mcl_set_map", "mcl_update_map_rect", "mcl_read_map_rect", "mcl_map_update", "mcl_distance_grid", "mcl_init_at_pose",
     "mcl_init_uniform", "mcl_import_particles", "mcl_export_particles", "mcl_export_weighted", "mcl_action_reset", "mcl_action_update",
     "mcl_resample", "mcl_apply_action", "mcl_score", "mcl_normalize", "mcl_estimate", "mcl_update",
     "mcl_update_action_only", "mcl_upload_scan", "mcl_update_enqueue", "mcl_read_estimate", "mcl_get_stats",
@@ -30,7 +30,7 @@ SYMBOLS = [
 class Params(C.Structure):
     _fields_ = [("min_range", C.c_float), ("weight_floor", C.c_double), ("init_std", C.c_double),
                 ("legacy_equal_utime", C.c_int), ("lanes_per_particle", C.c_int), ("map_tile", C.c_int),
-                ("sensor_path", C.c_int), ("weight_mode", C.c_int), ("reserved0", C.c_int), ("lse_beta", C.c_double),
+                ("sensor_path", C.c_int), ("weight_mode", C.c_int), ("sensor_mode", C.c_int), ("lse_beta", C.c_double),
                 ("reserved", C.c_int * 4)]
 
 
@@ -89,6 +89,7 @@ def lib():
         L.mcl_update_map_rect.argtypes = [vp, ip, ip, ip, ip, vp, ip]
         L.mcl_read_map_rect.argtypes = [vp, ip, ip, ip, ip, vp, ip]
         L.mcl_map_update.argtypes = [vp, vp, vp, ip, vp, vp, vp, ip, fp, ip, ip, vp]
+        L.mcl_distance_grid.argtypes = [vp, vp]
         L.mcl_init_at_pose.argtypes = [vp, fp, fp, fp, i64, C.c_uint64]
         L.mcl_init_uniform.argtypes = [vp, i64, C.c_uint64]
         L.mcl_import_particles.argtypes = [vp, vp, i64]
@@ -325,6 +326,12 @@ class Engine:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._ck(self._L.mcl_debug_fast_margin(self.h, C.addressof(a), C.addressof(b), C.addressof(c)))
         return a.value, b.value, c.value
+
+    def distance_grid(self, width, height):
+        """The reference's ObstacleDistanceGrid of the device mirror, (H, W) float32."""
+        out = np.zeros((height, width), np.float32)
+        self._ck(self._L.mcl_distance_grid(self.h, _p(out)))
+        return out
 
     def export_weighted(self, count, u01=0.5):
         """`count` particles drawn by systematic sampling over the weights, each with weight 1/count."""

@@ -53,7 +53,11 @@ typedef struct {
                                    (particle_filter.cpp:116-141): the parity mode.  1 = scores as log-likelihoods:
                                    w = exp(lse_beta (score - max score)) / sum, normalised by a max / log-sum-exp reduction
                                    (an extension: it changes results, so it is never the default) */
-    int    reserved0;
+    int    sensor_mode;         /* 0 (default) = the reference's beam-end scoring (sensor_model.cpp:28-59): the parity mode.
+                                   1 = likelihood field (an extension, never the default): a ray scores u(endpoint cell),
+                                   u = max(0, 127 - 8 d^2), d = four-connected steps to the nearest occupied cell -- a
+                                   distance grid computed like planning/obstacle_distance_grid.cpp:73-188 (brushfire),
+                                   one table lookup per beam; pairs naturally with weight_mode 1 */
     double lse_beta;            /* inverse temperature of weight_mode 1 (default 0.05 per score unit) */
     int    reserved[4];
 } mcl_params;
@@ -123,6 +127,11 @@ int  mcl_read_map_rect(mcl_engine* h, int x0, int y0, int w, int hgt, int8_t* ds
 int  mcl_map_update(mcl_engine* h, const mcl_pose_t* previous_pose, const mcl_pose_t* pose, int initialized,
                     const float* ranges, const float* thetas, const int64_t* times, int num_ranges,
                     float max_laser_distance, int hit_odds, int miss_odds, int* rect_xywh_out);
+
+/* ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:73-188) of the device mirror: out[y*width+x] =
+ * the reference's float distance of cell (x, y) -- 0 for cells with log-odds >= 0, else 0.1f accumulated once per
+ * four-connected step to the nearest such cell, -1 where the brushfire never arrives.  Bit-identical to the reference. */
+int  mcl_distance_grid(mcl_engine* h, float* out);
 
 /* ---- particle state -------------------------------------------------------------------------------------------- */
 /* ParticleFilter::initializeFilterAtPose (particle_filter.cpp:16-34) with the intended weight 1.0/N and a seeded

@@ -443,3 +443,81 @@ int orc_ray_scores(const orc_grid* g, const orc_particle* p, const float* ranges
     free(rays);
     return nr;
 }
+
+/* ---- planning/obstacle_distance_grid.cpp:44-188 -- ObstacleDistanceGrid::setDistances ----------------------------------
+ * initializeDistances: free cells (log-odds < 0) start at -1, every other cell (log-odds >= 0: occupied OR unknown) at 0
+ * (:52-67).  enqueue_obstacle_cells expands every non-free cell (:133-152); expand_node visits the four neighbours and
+ * gives an unvisited (-1) one the distance node.distance + 0.1f (:154-188; "should be 0.05" says the reference -- kept).
+ * The priority queue orders nodes by distance and every step costs the same, so a cell is reached first along a
+ * shortest four-connected path: the literal queue below (FIFO = the same order up to ties between equal distances,
+ * which cannot change the value a cell gets) restates it.  thr generalises the source rule: sources are cells with
+ * log-odds >= thr (thr = 0: the reference).  Returns the number of cells the brushfire never reached (left at -1). */
+long orc_distance_grid(const int8_t* cells, int32_t width, int32_t height, int thr, float* out)
+{
+    const long n = (long)width * height;
+    int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    long head = 0, tail = 0;
+    for (long i = 0; i < n; ++i) out[i] = cells[i] >= thr ? 0.0f : -1.0f;
+    static const int dx[4] = {1, -1, 0, 0}, dy[4] = {0, 0, 1, -1};
+    for (int pass = 0; pass < 2; ++pass) {
+        /* pass 0: expand every source cell in scan order (enqueue_obstacle_cells); pass 1: drain the queue */
+        long count = pass == 0 ? n : 0;
+        for (long i = 0; pass == 0 ? i < count : head < tail; ++i) {
+            long c;
+            if (pass == 0) { c = i; if (!(cells[c] >= thr)) continue; }
+            else c = queue[head++];
+            const int x = (int)(c % width), y = (int)(c / width);
+            for (int k = 0; k < 4; ++k) {
+                const int ax = x + dx[k], ay = y + dy[k];
+                if (ax < 0 || ax >= width || ay < 0 || ay >= height) continue;
+                const long a = (long)ay * width + ax;
+                if (out[a] == -1.0f) {
+                    out[a] = out[c] + 0.1f;
+                    queue[tail++] = (int32_t)a;
+                }
+            }
+        }
+    }
+    long unreached = 0;
+    for (long i = 0; i < n; ++i) unreached += out[i] == -1.0f;
+    free(queue);
+    return unreached;
+}
+
+/* ---- likelihood-field sensor mode (an EXTENSION of the engine, mcl_params.sensor_mode = 1; not in the reference) ---------
+ * field u(cell) = max(0, 127 - 8 d^2), d = four-connected steps to the nearest OCCUPIED cell (log-odds > 0), i.e. the
+ * brushfire above with thr = 1; a ray scores u at the reference's own endpoint cell (sensor_model.cpp:34-35: the
+ * truncated float coordinates), 0 outside the grid; a particle's score is the sum over its valid rays. */
+static int lf_value_from_distance(float d)
+{
+    if (d < 0.0f) return 0;
+    const int steps = (int)(d * 10.0f + 0.5f);
+    return steps >= 4 ? 0 : 127 - 8 * steps * steps;
+}
+
+void orc_likelihood_field(const orc_grid* g, const orc_particle* p, int n, const float* ranges, const float* thetas,
+                          const int64_t* times, int nb, double* out)
+{
+    const long cellsn = (long)g->width * g->height;
+    float* dist = (float*)malloc(sizeof(float) * (size_t)(cellsn > 0 ? cellsn : 1));
+    orc_distance_grid(g->cells, g->width, g->height, 1, dist);
+    float* rays = (float*)malloc(sizeof(float) * 4 * (size_t)(nb > 0 ? nb : 1));
+    for (int i = 0; i < n; ++i) {
+        const int k = orc_moving_scan(ranges, thetas, times, nb, &p[i].parent_pose, &p[i].pose, rays);
+        double score = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const float ox = rays[4 * j], oy = rays[4 * j + 1], range = rays[4 * j + 2], theta = rays[4 * j + 3];
+            const float sx = (float)(((double)ox - (double)g->origin_x) * (double)g->cells_per_meter);
+            const float sy = (float)(((double)oy - (double)g->origin_y) * (double)g->cells_per_meter);
+            float sn, cs;
+            sincosf(theta, &sn, &cs);
+            const float cpm = g->cells_per_meter;
+            const int ex = f2i((range * cs) * cpm + sx), ey = f2i((range * sn) * cpm + sy);
+            if (ex >= 0 && ex < g->width && ey >= 0 && ey < g->height)
+                score += (double)lf_value_from_distance(dist[(size_t)ey * g->width + ex]);
+        }
+        out[i] = score;
+    }
+    free(rays);
+    free(dist);
+}

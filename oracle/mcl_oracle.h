@@ -66,4 +66,9 @@ long   orc_map_update(int8_t* cells, int32_t width, int32_t height, float origin
                       const orc_pose* previous, const orc_pose* pose, int initialized, const float* ranges,
                       const float* thetas, const int64_t* times, int nb, float max_laser_distance, int hit_odds,
                       int miss_odds);
+/* ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:44-188); thr = 0 is the reference's rule. */
+long   orc_distance_grid(const int8_t* cells, int32_t width, int32_t height, int thr, float* out);
+/* The engine's likelihood-field sensor mode (extension): see mcl_oracle.c. */
+void   orc_likelihood_field(const orc_grid* g, const orc_particle* p, int n, const float* ranges, const float* thetas,
+                            const int64_t* times, int nb, double* out);
 #endif

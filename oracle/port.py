@@ -127,6 +127,30 @@ def map_update(cells, origin_x, origin_y, cells_per_meter, previous, pose, initi
     return out
 
 
+def distance_grid(cells, thr=0):
+    """ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:44-188): float32 [H, W]."""
+    cells = np.ascontiguousarray(cells, np.int8)
+    out = np.zeros(cells.shape, np.float32)
+    L = lib()
+    L.orc_distance_grid.restype = C.c_long
+    L.orc_distance_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p]
+    L.orc_distance_grid(_p(cells), cells.shape[1], cells.shape[0], thr, _p(out))
+    return out
+
+
+def likelihood_field(grid, particles, ranges, thetas, times):
+    """Scores of the engine's likelihood-field sensor mode (extension; see mcl_oracle.c)."""
+    particles = np.ascontiguousarray(particles, PARTICLE_DTYPE)
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    thetas = np.ascontiguousarray(thetas, np.float32)
+    times = np.ascontiguousarray(times, np.int64)
+    out = np.zeros(particles.shape[0], np.float64)
+    L = lib()
+    L.orc_likelihood_field.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_likelihood_field(grid.ptr, _p(particles), particles.shape[0], _p(ranges), _p(thetas), _p(times), len(ranges), _p(out))
+    return out
+
+
 def ray_scores(grid, particle, ranges, thetas, times):
     """Per-ray scores of one particle over its valid beams, in scan order (their sum is likelihood()'s entry)."""
     part = np.ascontiguousarray(particle, PARTICLE_DTYPE).reshape(1)

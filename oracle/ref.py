@@ -64,6 +64,7 @@ def lib():
         L.ref_pf_pose_estimate.argtypes = [vp, vp]
         L.ref_pf_action_params.argtypes = [vp, vp]
         L.ref_map_update.argtypes = [vp, vp, vp, ip, vp, vp, vp, ip, fp, ip, ip]
+        L.ref_distance_grid.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -139,6 +140,14 @@ def map_update(grid, previous, pose, initialized, scan, max_laser_distance=5.0, 
     b = np.ascontiguousarray(pose, POSE_DTYPE).reshape(1)
     lib().ref_map_update(grid.h, _p(a), _p(b), 1 if initialized else 0, _p(scan.ranges), _p(scan.thetas),
                          _p(scan.times), len(scan.ranges), max_laser_distance, hit_odds, miss_odds)
+
+
+def distance_grid(grid):
+    """ObstacleDistanceGrid::setDistances of the compiled reference on `grid` (a RefGrid): float32 [H, W]."""
+    w, h = grid.info()["width"], grid.info()["height"]
+    out = np.zeros((h, w), np.float32)
+    lib().ref_distance_grid(grid.h, _p(out))
+    return out
 
 
 def moving_scan(scan, begin, end):

@@ -28,6 +28,7 @@
 #include <slam/occupancy_grid.hpp>
 #include <slam/mapping.hpp>
 #include <common/pose_trace.hpp>
+#include <planning/obstacle_distance_grid.hpp>
 #undef private
 #include <lcmtypes/lidar_t.hpp>
 #include <lcmtypes/occupancy_grid_t.hpp>
@@ -430,6 +431,16 @@ void ref_map_update(void* gp, const ref_pose* previous, const ref_pose* pose, in
     mapper.initialized_ = initialized != 0;
     const lidar_t scan = make_scan(ranges, thetas, times, nb);
     mapper.updateMap(scan, to_pose(*pose), *(OccupancyGrid*)gp);
+}
+
+// ---- ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:73-92) of a reference OccupancyGrid ----
+void ref_distance_grid(void* gp, float* out)
+{
+    const OccupancyGrid& grid = *(OccupancyGrid*)gp;
+    ObstacleDistanceGrid dist;
+    dist.setDistances(grid);
+    for (int y = 0; y < grid.heightInCells(); ++y)
+        for (int x = 0; x < grid.widthInCells(); ++x) out[(size_t)y * grid.widthInCells() + x] = dist(x, y);
 }
 
 int ref_sizeof_particle(void) { return (int)sizeof(particle_t); }

@@ -55,7 +55,30 @@ def mapping_golden():
     np.savez_compressed(os.path.join(OUT, "mapping.npz"), **out)
 
 
+def distance_golden():
+    """ObstacleDistanceGrid::setDistances (planning/obstacle_distance_grid.cpp:73-92) of the executed reference on four
+    small grids (tests/test_oracle.py::_distance_cases builds the same inputs)."""
+    rng = np.random.default_rng(77)
+    cases = {
+        "synth": synth.make_map(120, seed=5).cells,
+        "random": np.where(rng.random((90, 140)) < 0.03, 60, np.where(rng.random((90, 140)) < 0.5, -9, 0)).astype(np.int8),
+        "all_free": np.full((40, 60), -5, np.int8),
+    }
+    d = np.full((30, 30), -5, np.int8); d[11, 17] = 0
+    cases["one_unknown"] = d
+    out = {}
+    for name, cells in cases.items():
+        g = ref.RefGrid.from_cells(cells, 0.0, 0.0, 0.05)
+        out[name + "_cells"] = cells
+        out[name + "_dist"] = ref.distance_grid(g)
+    np.savez_compressed(os.path.join(OUT, "distance.npz"), **out)
+
+
 def main():
+    if "--distance-only" in sys.argv:
+        distance_golden()
+        print("distance.npz written")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "mapping":
         mapping_golden()
         print("mapping golden written to", OUT)
@@ -197,6 +220,7 @@ def main():
             traj[f"{variant}_{step}_estimate"] = np.array(est)
             traj[f"{variant}_{step}_particles"] = pf.particles()
     np.savez_compressed(os.path.join(OUT, "trajectory.npz"), **traj)
+    distance_golden()
     print("golden vectors written to", OUT)
 
 

@@ -688,6 +688,44 @@ def test_batch_windows_equal_exact_and_oracle(side, n):
         e.close()
 
 
+def test_config5_shape_full_size():
+    """BASELINE configs[4] at one GPU's share of its shape: 8 M uniformly initialised particles on the 4000 x 4000 grid
+    (what each of eight GPUs holds of the 64 M), scored behind per-batch windows.  A sub-sample of the scores (every
+    10 007th particle) equals the ORACLE's, before and after a full update; the exact-only path agrees everywhere."""
+    n, side = 8_000_000, 4000
+    grid = synth.make_map(side, seed=synth.MAP_SEED + 5)
+    rng = np.random.default_rng(55)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=55)
+    pg = port_grid(grid)
+    am = engine.ActionModel()
+    am.update(0.0, 0.0, 0.0, int(t[0]) - 100_000)
+    assert am.update(0.02, 0.01, 0.01, int(t[-1]))
+    out = {}
+    for path in (0, 1):
+        e = make_engine(n, grid, sensor_path=path)
+        e.init_uniform(utime=int(t[0]) - 100_000, seed=11)
+        s0 = e.score(r, th, t)
+        st = e.stats()
+        assert st["map_tile_used"] == 3 and st["sensor_path"] == (2 if path == 0 else 1), st
+        sub0 = e.export_particles(stride=10_007)
+        est = e.update(am, int(t[-1]), r, th, t, 0.37 / n)
+        assert e.stats()["map_tile_used"] == 3
+        s1 = e.score(r, th, t)
+        sub1 = e.export_particles(stride=10_007)
+        out[path] = (s0, sub0, s1, sub1, (est.x, est.y, est.theta), e.stats()["weight_sum"])
+        e.close()
+    a, b = out[0], out[1]
+    want0, _, _ = port.likelihood(pg, a[1], r, th, t)
+    want1, _, _ = port.likelihood(pg, a[3], r, th, t)
+    assert np.array_equal(a[0][::10_007], want0) and np.array_equal(a[2][::10_007], want1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[4] == b[4] and a[5] == b[5]
+    for k in ("pose", "parent_pose"):
+        for f in ("x", "y", "theta"):
+            assert np.array_equal(a[3][k][f], b[3][k][f])
+    assert np.array_equal(a[3]["weight"], b[3]["weight"])
+
+
 # ------------------------------------------------------------------------------- map update on the device mirror
 @pytest.mark.parametrize("hit,miss,max_laser", [(3, 1, 5.0), (4, 1, 5.0), (127, 100, 8.0), (0, 0, 5.0)])
 def test_map_update_matches_oracle(hit, miss, max_laser):
@@ -920,3 +958,60 @@ def test_scoring_follows_device_map_updates(path):
     check("set_map")
     assert (3 in seen) == (path == 0)
     e.close()
+
+
+# ------------------------------------------------- next row: distance grid + likelihood-field sensor mode
+@pytest.mark.parametrize("name", ["real", "synth700", "all_free"])
+def test_distance_grid_equals_the_oracle(name, real_map):
+    """mcl_distance_grid (two separable sweeps on the device mirror) == ObstacleDistanceGrid::setDistances as the oracle
+    restates it (itself bit-equal to the executed reference: tests/test_oracle.py), bit for bit."""
+    grid = {"real": real_map, "synth700": synth.make_map(700, seed=31),
+            "all_free": synth.GridSpec(np.full((50, 80), -3, np.int8), 0.0, 0.0, 0.05)}[name]
+    e = make_engine(16, grid)
+    got = e.distance_grid(grid.width, grid.height)
+    want = port.distance_grid(grid.cells)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    e.close()
+
+
+@pytest.mark.parametrize("side,n,kind", [(200, 30_000, "tracking"), (600, 50_000, "tracking"), (300, 20_000, "uniform")])
+def test_likelihood_field_mode_equals_the_oracle(side, n, kind, real_map):
+    """sensor_mode = 1 (an extension, never the default): a ray scores the field value u = max(0, 127 - 8 d^2) of its
+    endpoint cell, d = steps to the nearest occupied cell.  Scores equal the oracle's restatement exactly (the float
+    pass only takes cells it can certify; the rest go through the exact endpoint), they follow map changes, and the
+    log-sum-exp normaliser turns them into weights."""
+    grid = real_map if side == 200 else synth.make_map(side, seed=side)
+    rng = np.random.default_rng(side)
+    truth = synth.find_free_pose(grid, rng)
+    r, th, t = synth.make_scan(grid, truth, seed=side, max_range=5.0)
+    if kind == "tracking":
+        cloud = synth.make_particles(n, truth, seed=3, sigma_xy=0.15, sigma_theta=0.08, parent_utime=int(t[0]), pose_utime=int(t[-1]))
+    else:
+        cloud = synth.make_uniform_particles(n, grid, seed=3, utime=int(t[-1]))
+        cloud["parent_pose"]["utime"] = int(t[0])
+        cloud["parent_pose"]["x"] += np.float32(0.02)
+    e = make_engine(n, grid, sensor_mode=1, weight_mode=1, lse_beta=0.02)
+    e.import_particles(cloud)
+    s = e.score(r, th, t)
+    want = port.likelihood_field(port_grid(grid), cloud, r, th, t)
+    assert np.array_equal(s, want)
+    st = e.stats()
+    assert st["sensor_path"] == 3 and st["deferred_evals"] < 0.2 * st["evals"]
+    assert want.max() > 20 * 127 * (1 if kind == "tracking" else 0)          # the tracking cloud really sits on the walls
+    w = e.normalize()
+    v = np.exp(0.02 * (s - s.max()))
+    assert np.abs(w - v / v.sum()).max() <= 1e-12
+    # the field follows the mirror: a wall across the map changes the scores the way the oracle says
+    cells = grid.cells.copy()
+    cells[grid.height // 2, :] = 90
+    e.update_map_rect(0, grid.height // 2, cells[grid.height // 2:grid.height // 2 + 1, :])
+    g2 = synth.GridSpec(cells, grid.origin_x, grid.origin_y, grid.meters_per_cell, grid.cells_per_meter)
+    want2 = port.likelihood_field(port_grid(g2), cloud, r, th, t)
+    assert np.array_equal(e.score(r, th, t), want2) and not np.array_equal(want2, want)
+    e.close()
+    # the default mode of the same engine build is untouched
+    e0 = make_engine(n, grid)
+    e0.import_particles(cloud)
+    ref_scores, _, _ = port.likelihood(port_grid(grid), cloud, r, th, t)
+    assert np.array_equal(e0.score(r, th, t), ref_scores)
+    e0.close()

@@ -236,3 +236,34 @@ def test_port_vs_reference_sensor_geometries(case):
     a = ref.likelihood(rg, cloud, ref.Scan(r, th, t))
     b, _, _ = port.likelihood(port_grid(grid), cloud, r, th, t)
     assert np.array_equal(a, b)
+
+
+# ---- obstacle distance grid (next row: likelihood-field sensor mode) ------------------------------------------------------
+def _distance_cases():
+    rng = np.random.default_rng(77)
+    a = synth.make_map(120, seed=5).cells
+    b = np.where(rng.random((90, 140)) < 0.03, 60, np.where(rng.random((90, 140)) < 0.5, -9, 0)).astype(np.int8)
+    c = np.full((40, 60), -5, np.int8)                    # all free: the brushfire never starts
+    d = np.full((30, 30), -5, np.int8); d[11, 17] = 0     # one unknown cell is a source too (log-odds >= 0)
+    return {"synth": a, "random": b, "all_free": c, "one_unknown": d}
+
+
+@pytest.mark.parametrize("name", ["synth", "random", "all_free", "one_unknown"])
+def test_distance_grid_equals_the_compiled_reference(name):
+    """oracle orc_distance_grid == ObstacleDistanceGrid::setDistances of the executed reference, bit for bit (the 0.1f
+    accumulation included), on the committed fixture and -- where oracle/_ref is built -- live."""
+    cells = _distance_cases()[name]
+    got = port.distance_grid(cells)
+    gold = load_golden("distance")
+    assert np.array_equal(gold[name + "_cells"], cells)
+    assert np.array_equal(got.view(np.uint32), gold[name + "_dist"].view(np.uint32))
+    if name == "all_free":
+        assert (got == -1.0).all()
+    if name == "one_unknown":
+        d = np.float32(0.0)
+        for _ in range(11 + 17):                             # (0, 0) is 28 four-connected steps from the source
+            d = np.float32(d + np.float32(0.1))
+        assert got[11, 17] == 0.0 and got[11, 18] == np.float32(0.1) and got[0, 0] == d
+    if ref.available():
+        g = ref.RefGrid.from_cells(cells, 0.0, 0.0, 0.05)
+        assert np.array_equal(ref.distance_grid(g).view(np.uint32), got.view(np.uint32))
