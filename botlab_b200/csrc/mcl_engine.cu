@@ -150,11 +150,45 @@ struct mcl_engine {
     uint64_t seed = 0x5eedULL;
     uint32_t update_no = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // MCL_PROFILE=1: CUDA events around the parts of an update (blocking mcl_update only), averaged and printed to
+    // stderr by mcl_destroy
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<const char*> prof_label;
+    size_t prof_n = 0;
+    std::vector<double> prof_sum;
+    long prof_updates = 0;
     int launches = 0;
     int collectives = 0;
 };
 
 namespace {
+
+void prof_mark(mcl_engine* h, const char* label)
+{
+    if (!h->prof) return;
+    if (h->prof_n == h->prof_ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_ev.push_back(e);
+        h->prof_label.push_back(label);
+        h->prof_sum.push_back(0.0);
+    }
+    h->prof_label[h->prof_n] = label;
+    cudaEventRecord(h->prof_ev[h->prof_n++], h->stream);
+}
+
+void prof_collect(mcl_engine* h)          // after a stream synchronisation
+{
+    if (!h->prof) return;
+    for (size_t i = 1; i < h->prof_n; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]);
+        h->prof_sum[i] += ms;
+    }
+    ++h->prof_updates;
+    h->prof_n = 0;
+}
 
 int fail(mcl_engine* h, int code, const char* fmt, ...)
 {
@@ -234,14 +268,17 @@ int seq_total(mcl_engine* h, int wbuf)
     const long long tile_hi = (h->hi + kL1 * kSeqTileChunks - 1) / (kL1 * kSeqTileChunks);
     const long long group_lo = h->lo / kSliceAlign, group_hi = (h->hi + kSliceAlign - 1) / kSliceAlign;
     const int tiles = (int)(tile_hi - tile_lo);
+    prof_mark(h, "seq:begin");
     if (tiles > 0) {
         xseq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_sums);
         CKL(h);
     }
     xseq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tile_lo, tile_hi, h->tile_excl, h->xp, h->xl.tot);
     CKL(h);
+    prof_mark(h, "seq:S1+S2");
     int rc = xbarrier(h, 0);
     if (rc) return rc;
+    prof_mark(h, "seq:barrierA");
     CK(cudaMemsetAsync(h->fb_count, 0, sizeof(int), h->stream));
     if (tiles > 0) {
         XSeqOut o{h->xl.q0, h->xl.q1, h->xl.eb, h->xl.fbraw};
@@ -252,8 +289,10 @@ int seq_total(mcl_engine* h, int wbuf)
             h->ebias, h->q0, h->q1, n1, group_lo, group_hi, h->xp, h->xl.g0, h->xl.g1, h->xl.ge);
         CKL(h);
     }
+    prof_mark(h, "seq:S3+S4");
     rc = xbarrier(h, 1);
     if (rc) return rc;
+    prof_mark(h, "seq:barrierB");
     {
         const size_t walk_smem = (size_t)n2 * 20;                    // g0, g1 (8 B each) + gebias (4 B) per group
         const int staged = walk_smem + 4096 <= (size_t)h->max_smem_optin ? 1 : 0;
@@ -263,6 +302,7 @@ int seq_total(mcl_engine* h, int wbuf)
             h->fallbacks, staged, h->xp, h->xl.w[wbuf], h->xl.fbraw);
         CKL(h);
     }
+    prof_mark(h, "seq:walk");
     return MCL_OK;
 }
 
@@ -818,6 +858,7 @@ int run_normalize(mcl_engine* h)
         floor_kernel<<<g, 256, 0, h->stream>>>(h->score2 + lo, w + lo, local, h->params.weight_floor);
         CKL(h);
     }
+    prof_mark(h, "normalise:floor");
     int rc = seq_total(h, h->wcur);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->ess_acc, 0, sizeof(double), h->stream));
@@ -976,20 +1017,26 @@ int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r
     h->launches = 0;
     h->collectives = 0;
     cudaEventRecord(h->ev[0], h->stream);
+    prof_mark(h, "update:begin");
     int rc = run_resample_indices(h, r, h->wcur);
     if (rc) return rc;
+    prof_mark(h, "resample:range+expand+materialise+search");
     cudaEventRecord(h->ev[1], h->stream);
     rc = run_action(h, a, utime, noise_dev, true);
     if (rc) return rc;
+    prof_mark(h, "action");
     cudaEventRecord(h->ev[2], h->stream);
     rc = run_score(h);
     if (rc) return rc;
+    prof_mark(h, "score (+ join pose pushes)");
     cudaEventRecord(h->ev[3], h->stream);
     rc = run_normalize(h);
     if (rc) return rc;
+    prof_mark(h, "normalise:divide");
     cudaEventRecord(h->ev[4], h->stream);
     rc = run_estimate(h);
     if (rc) return rc;
+    prof_mark(h, "estimate (partials, barrier, final)");
     cudaEventRecord(h->ev[5], h->stream);
     h->stats.kernel_launches = h->launches;
     h->stats.collectives = h->collectives;
@@ -1066,6 +1113,7 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     if (!h) return fail(nullptr, MCL_ERR_INVALID, "out of host memory");
     if (params) h->params = *params; else mcl_default_params(&h->params);
     h->device = device;
+    h->prof = std::getenv("MCL_PROFILE") != nullptr;
     h->n = num_particles;
     h->lo = 0; h->hi = num_particles;
     auto bail = [&](int rc) { g_last_error = h->err; free_all(h); delete h; return rc; };
@@ -1188,6 +1236,13 @@ void mcl_destroy(mcl_engine* h)
 #endif
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->prof && h->prof_updates > 0 && h->rank == 0) {
+        fprintf(stderr, "MCL_PROFILE rank 0 of %d, %lld particles, %ld blocking updates, mean ms per part:\n", h->world,
+                (long long)h->n, h->prof_updates);
+        for (size_t i = 1; i < h->prof_sum.size(); ++i)
+            fprintf(stderr, "  %-48s %8.4f\n", h->prof_label[i], h->prof_sum[i] / (double)h->prof_updates);
+    }
+    for (auto e : h->prof_ev) cudaEventDestroy(e);
 #ifdef MCL_WITH_NCCL
     if (h->comm) ncclCommDestroy(h->comm);
 #endif
@@ -1779,6 +1834,7 @@ int mcl_update(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, con
         if (rc) return rc;
         rc = read_counters(h);
         if (rc) return rc;
+        prof_collect(h);
         float ms = 0;
         float* slots[5] = {&h->stats.ms_resample, &h->stats.ms_action, &h->stats.ms_score, &h->stats.ms_normalize,
                            &h->stats.ms_estimate};
@@ -1811,7 +1867,9 @@ int mcl_update_enqueue(mcl_engine* h, const mcl_action_t* a, int64_t odometry_ut
         s ^= s >> 33; s *= 0xff51afd7ed558ccdULL; s ^= s >> 33;
         r = ((double)(s >> 11) * (1.0 / 9007199254740992.0)) / (double)h->n;
     }
-    return enqueue_update(h, a, odometry_utime, r, nullptr);
+    const int rc = enqueue_update(h, a, odometry_utime, r, nullptr);
+    h->prof_n = 0;
+    return rc;
 }
 
 int mcl_read_estimate(mcl_engine* h, mcl_pose_t* pose_out)

@@ -81,7 +81,7 @@ def test_host_classes_drive_the_engine(built, tmp_path, real_map):
     assert np.abs(track[:, 5] - track[:, 2]).max() < 0.10
     assert (track[:, 6] == 1000000 + 100000 * np.arange(1, 7)).all() and (track[:, 7] == 1).all()
     assert out["exported"] == 1000 and 0.0 < out["exported_weight"] < 1.0        # every 20th particle of 20000
-    assert out["updates"] == 7 and out["evals"] == 20000 * 360 and out["launches"] > 0
+    assert out["updates"] == 6 and out["evals"] == 20000 * 360 and out["launches"] > 0
     inc, full, before, after, want = out["mirrors"]
     assert inc == full and inc != out["kat_scores"][0]        # the second mirror saw the block the first one consumed
     assert before == 0.0 and after == want and want > 0.0     # an assigned-to grid is mirrored again
