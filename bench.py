@@ -41,11 +41,20 @@ METRIC = "particle_beam_evals_per_sec"
 UNIT = "evals/s"
 
 
-def build_workload(config, seed=0):
+INTERIOR_POSE = [False]     # --pose interior: the robot in the middle of the map instead of wherever the seed put it
+
+
+def build_workload(config, seed=0, interior=None):
     n, side = synth.CONFIGS[config]
     grid = synth.make_map(side, seed=synth.MAP_SEED + int(config[-1]))
     rng = np.random.default_rng(1234 + seed)
     truth = synth.find_free_pose(grid, rng)
+    if INTERIOR_POSE[0] if interior is None else interior:
+        # The seeded pose of configs 3-5 lies 1.5-5 m from the map's corner, so a window around the cloud is clipped
+        # by the grid; this variant keeps the whole 8 m reach inside the map (the largest window the scan can ask for).
+        cx, cy = grid.origin_x + 0.5 * grid.width * grid.meters_per_cell, grid.origin_y + 0.5 * grid.height * grid.meters_per_cell
+        while max(abs(truth[0] - cx), abs(truth[1] - cy)) > 0.15 * grid.width * grid.meters_per_cell:
+            truth = synth.find_free_pose(grid, rng)
     scans = []
     pose = truth
     t = 1_000_000
@@ -187,7 +196,8 @@ def cpu_sample_size(n, updates, budget_s):
 def workload_name(config, n, valid, grid, uniform):
     return (f"{config}: {n} particles x 360 beams ({valid} valid), {grid.width}x{grid.height} int8 grid, "
             + ("uniform cloud re-initialised every step (global localisation)" if uniform
-               else "tracking cloud (truth + N(0, 0.10 m), N(0, 0.05 rad))"))
+               else "tracking cloud (truth + N(0, 0.10 m), N(0, 0.05 rad))")
+            + (", robot in the map's interior" if INTERIOR_POSE[0] else ""))
 
 
 def run_reference(args):
@@ -510,7 +520,10 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short entries for the other BASELINE configs")
     ap.add_argument("--uniform", action="store_true", help="uniform cloud (global localisation) on any config")
     ap.add_argument("--particles", type=int, default=0, help="override the config's particle count")
+    ap.add_argument("--pose", default="seeded", choices=["seeded", "interior"],
+                    help="interior: the robot in the middle of the map (the seeded pose of configs 3-5 is near a corner)")
     args = ap.parse_args()
+    INTERIOR_POSE[0] = args.pose == "interior"
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -101,12 +101,17 @@ struct mcl_engine {
     TabPlan* tab_plan = nullptr;
     int* tab_box = nullptr;             // bounding box of the cloud (ordered-int atomics); table_plan_kernel re-arms it
     int* tab_build = nullptr;           // [0] table entries needed, [1] CTAs whose table overflowed
-    struct TabHint { TabPlan plan; int build[2]; };
+    struct TabHint { TabPlan plan; int build[8]; };
     TabHint* tab_hint = nullptr;        // pinned
     cudaEvent_t ev_tab_hint = nullptr;
     bool tab_hint_pending = false;
     bool tab_ok = false;                // the last plan the host has seen allows the table pass
     int tab_blocked = 0;                // updates to keep off the table pass after an overflow
+    int tab_variant = 0;                // kTabSingle16 .. kTabBatch8 (mcl_table.cuh): what the next pass launches
+    int tab_excluded = 0;               // variants whose score table overflowed on this cloud
+    int tab_batch = kTabBatch;          // kTabBatch, or kTabBatchSmall for sparse clouds
+    int4* tab_bboxes = nullptr;         // bounding box per batch
+    size_t tab_bboxes_cap = 0;
     bool scan_finite = true;
 
     // estimate
@@ -119,6 +124,9 @@ struct mcl_engine {
     int8_t* map = nullptr;
     int8_t* map_fast = nullptr;         // the fast pass's derived view of the map (derive_fast_map_kernel), same pitch
     int8_t* map_lf = nullptr;           // likelihood field (sensor_mode 1), same pitch; rebuilt lazily after map changes
+    uint8_t* map_cls = nullptr;         // class map of the score-table pass (mcl_table.cuh: derive_class_map_kernel): the grid
+    unsigned long long* map_pack = nullptr;     // plus a four-cell apron, cpitch bytes per row; score-table entries of its cells
+    int cpitch = 0;
     uint16_t* dt_steps = nullptr;       // distance-transform scratch: [H][W] steps
     bool lf_dirty = true;
     DevGrid grid{};
@@ -360,6 +368,24 @@ int join_pushes(mcl_engine* h)
 }
 
 // Refreshes the fast pass's derived map over the rectangle [x0, x0+w) x [y0, y0+hgt) widened by the 2-cell look-ahead.
+// Classes (and score-table entries) of the cells whose 5 x 5 neighbourhood meets the changed rectangle, apron included.
+int refresh_class_map(mcl_engine* h, int x0, int y0, int w, int hgt)
+{
+    const bool lf = h->params.sensor_mode == 1;
+    const int xa = std::max(-kTabApron, x0 - 2), ya = std::max(-kTabApron, y0 - 2);
+    const int xb = std::min(h->grid.width + kTabApron, x0 + w + 2), yb = std::min(h->grid.height + kTabApron, y0 + hgt + 2);
+    if (xb <= xa || yb <= ya) return MCL_OK;
+    TabArgs a{};
+    a.grid = h->grid;
+    a.fast_cells = h->map_fast;
+    a.lf_cells = lf ? h->map_lf : nullptr;
+    const long long total = (long long)(xb - xa) * (yb - ya);
+    derive_class_map_kernel<<<grid_for(h, total, 256), 256, 0, h->stream>>>(a, h->map_cls, h->map_pack, h->cpitch, xa, ya, xb - xa,
+                                                                           yb - ya);
+    CKL(h);
+    return MCL_OK;
+}
+
 int refresh_fast_map(mcl_engine* h, int x0, int y0, int w, int hgt)
 {
     h->lf_dirty = true;
@@ -370,6 +396,8 @@ int refresh_fast_map(mcl_engine* h, int x0, int y0, int w, int hgt)
     derive_fast_map_kernel<<<grid_for(h, total, 256), 256, 0, h->stream>>>(h->map, h->map_fast, h->grid.width, h->grid.height,
                                                                           h->grid.pitch, xa, ya, xb - xa, yb - ya);
     CKL(h);
+    // (likelihood-field mode derives its classes from the field, which is rebuilt lazily: refresh_likelihood_field)
+    if (h->params.sensor_mode != 1) return refresh_class_map(h, xa - 2, ya - 2, xb - xa + 4, yb - ya + 4);
     return MCL_OK;
 }
 
@@ -586,7 +614,7 @@ int refresh_likelihood_field(mcl_engine* h)
         h->dt_steps, h->grid.width, h->grid.height, h->grid.pitch, h->map_lf);
     CKL(h);
     h->lf_dirty = false;
-    return MCL_OK;
+    return refresh_class_map(h, -kTabApron, -kTabApron, h->grid.width + 2 * kTabApron, h->grid.height + 2 * kTabApron);
 }
 
 // ---- table sensor path (mcl_table.cuh) ------------------------------------------------------------------------------
@@ -595,27 +623,55 @@ int refresh_likelihood_field(mcl_engine* h)
 // takes that from the plan of the previous update (copied to pinned memory behind the kernel); the kernel itself
 // verifies the plan and sends every evaluation down the exact path when it does not hold, so a stale hint costs time,
 // never correctness.  The first scoring pass after the cloud was (re)initialised plans synchronously.
-constexpr long long kTabMinParticles = 1024;
+constexpr long long kTabMinParticles = 64;
 
-// returns 1 when the table kernel has been launched, 0 when the caller should use the other kernel families, < 0 on error
+// returns 1 (one window) or 2 (one window per batch) when the table kernel has been launched, 0 when the caller should use
+// the other kernel families, < 0 on error
 int run_score_table(mcl_engine* h, ScoreArgs& sa)
 {
     const long long local = h->hi - h->lo;
     const int lanes = h->params.lanes_per_particle;
     const bool lf = h->params.sensor_mode == 1;
     const bool cand = (lf || (h->params.sensor_path == 0 && h->params.map_tile != 1 && (lanes == 0 || lanes == 1) &&
-                              local >= kTabMinParticles)) && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
+                              local >= kTabMinParticles)) && local < (1ll << 31) && h->num_beams > 0 && h->num_beams <= kTabMaxBeams && h->scan_finite &&
                       std::isfinite(h->max_range) && !std::getenv("MCL_NO_TABLE");
     if (!cand) return lf ? fail(h, MCL_ERR_INVALID, "the likelihood-field mode needs a finite scan of at most %d beams", kTabMaxBeams) : 0;
     if (lf) { int rc = refresh_likelihood_field(h); if (rc) return rc; }
+    auto debug_plan = [&](const char* what, const TabPlan& d) {
+        if (std::getenv("MCL_DEBUG_TABLE"))
+            std::fprintf(stderr, "[mcl table] %s: variant %d (batch of %d) -> ok %d reason %d best %d misfits %d w %d h %d cap %d; built: entries %d "
+                         "overflows %d windowless %d particles outside %d\n", what, d.variant, h->tab_batch, d.ok, d.reason, d.best, d.misfits,
+                         d.w, d.h, d.cap_entries, h->tab_hint->build[0], h->tab_hint->build[1], h->tab_hint->build[3], h->tab_hint->build[4]);
+    };
     if (h->tab_hint_pending && cudaEventQuery(h->ev_tab_hint) == cudaSuccess) {
         h->tab_hint_pending = false;
-        h->tab_ok = h->tab_hint->plan.ok != 0;
-        if (h->tab_hint->build[1] != 0) { h->tab_ok = false; h->tab_blocked = 64; }
-        if (h->tab_ok) h->stats_eps = h->tab_hint->plan.eps;
+        const TabPlan& hp = h->tab_hint->plan;
+        debug_plan("hint", hp);
+        h->tab_ok = hp.ok != 0;
+        const long long hint_batches = hp.batch ? (local + h->tab_batch - 1) / h->tab_batch : 1;
+        if (hp.ok && h->tab_hint->build[1] * 50ll > (hp.batch ? hint_batches : 0)) {
+            // the score table overflowed (the kernel scored those windows exactly): smaller batches, else another variant
+            h->tab_ok = false;
+            if (hp.batch && h->tab_batch == kTabBatch) h->tab_batch = kTabBatchSmall;
+            else h->tab_excluded |= 1 << hp.variant;
+        } else if (hp.best >= 0 && hp.best != hp.variant) {
+            // follow what the last plan saw: one window when the cloud fits one, 16-bit classes when they fit, ...
+            // (when this plan was not ok, tab_ok is false and the next pass plans synchronously)
+            h->tab_variant = hp.best;
+        }
     }
     if (h->tab_blocked > 0 && !lf) { --h->tab_blocked; return 0; }
     const size_t smem_total = (size_t)h->max_smem_optin - 1024;      // static shared memory of the kernel stays below 1 KB
+    long long nbatches = 0;
+    {
+        const long long most = (local + kTabBatchSmall - 1) / kTabBatchSmall;
+        if ((size_t)most > h->tab_bboxes_cap) {
+            if (h->tab_bboxes) cudaFree(h->tab_bboxes);
+            h->tab_bboxes = nullptr; h->tab_bboxes_cap = 0;
+            CK(cudaMalloc((void**)&h->tab_bboxes, sizeof(int4) * (size_t)most));
+            h->tab_bboxes_cap = (size_t)most;
+        }
+    }
     TabPlanIn in{};
     in.grid = h->grid;
     in.max_range = h->max_range; in.min_range = h->params.min_range; in.max_abs_theta = h->max_abs_theta;
@@ -625,19 +681,43 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     in.allow = 1;
     in.smem_total = (int)smem_total;
     in.smem_fixed = (int)table_fixed_smem(h->num_beams);
-    bbox_kernel<<<grid_for(h, local, 256), 256, 0, h->stream>>>(sa.x, sa.y, sa.px, sa.py, h->lo, h->hi, h->tab_box);
-    CKL(h);
-    table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan);
-    CKL(h);
+    const bool allow_batch = !lf && !std::getenv("MCL_NO_TABLE_BATCH");          // (the likelihood field keeps one window)
+    const double rc6 = (double)h->max_range * (double)h->grid.cells_per_meter + 6.0;
+    const long long k_budget = (long long)in.smem_total - in.smem_fixed - 64;       // for tab_batch_bytes
+    auto plan = [&]() -> int {
+        in.variant = h->tab_variant;
+        in.excluded = h->tab_excluded;
+        nbatches = (local + h->tab_batch - 1) / h->tab_batch;
+        in.num_batches = allow_batch ? nbatches : 0;
+        table_bbox_kernel<<<(int)nbatches, 256, 0, h->stream>>>(sa.x, sa.y, sa.px, sa.py, h->lo, h->hi, h->tab_batch, h->grid, rc6,
+                                                                k_budget, h->tab_box, allow_batch ? h->tab_bboxes : nullptr);
+        CKL(h);
+        table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan);
+        CKL(h);
+        return MCL_OK;
+    };
+    int rc = plan();
+    if (rc) return rc;
     if (!h->tab_ok) {
         // no usable hint (first pass after an init / import, or the last plan did not allow the table): plan synchronously
-        CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        h->tab_hint_pending = false;
-        h->tab_ok = h->tab_hint->plan.ok != 0;
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->tab_hint_pending = false;
+            const TabPlan& hp = h->tab_hint->plan;
+            h->tab_ok = hp.ok != 0;
+            debug_plan("plan", hp);
+            if (h->tab_ok || hp.reason != 3) break;                            // (3: the window does not fit)
+            if (hp.best >= 0) h->tab_variant = hp.best;                        // another variant is applicable
+            else if (allow_batch && h->tab_batch == kTabBatch) h->tab_batch = kTabBatchSmall;     // a sparse cloud: smaller batches
+            else break;
+            rc = plan();
+            if (rc) return rc;
+        }
         if (!h->tab_ok && !lf) return 0;      // (likelihood-field mode: the kernel then scores every ray exactly, from the field)
         h->stats_eps = h->tab_hint->plan.eps;
     }
+    const bool batch = h->tab_variant >= kTabBatch16, wide = (h->tab_variant & 1) != 0;
     TabArgs a{};
     a.x = sa.x; a.y = sa.y; a.th = sa.th; a.px = sa.px; a.py = sa.py; a.pth = sa.pth;
     a.score2 = sa.score2;
@@ -646,31 +726,48 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     a.grid = sa.grid;
     a.fast_cells = sa.fast_cells;
     a.lf_cells = lf ? h->map_lf : nullptr;
+    a.cls = h->map_cls; a.pack = h->map_pack; a.cpitch = h->cpitch;
     a.plan = h->tab_plan;
     a.gather_counter = sa.gather_counter;
     a.deferred_counter = sa.deferred_counter;
     a.build_info = h->tab_build;
-    a.num_peers = sa.num_peers;
-    for (int r = 0; r < kMaxPeers; ++r) a.peer_score[r] = sa.peer_score[r];
-    CK(cudaMemsetAsync(h->tab_build, 0, 2 * sizeof(int), h->stream));
+    a.bboxes = h->tab_bboxes;
+    a.batch = h->tab_batch;
+    CK(cudaMemsetAsync(h->tab_build, 0, 8 * sizeof(int), h->stream));
     const long long nunits = (local + 31) / 32;
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(nunits, h->sm_count));
+    // one CTA per SM; small clouds get as many CTAs as their (unit, 32-beam word) pairs can keep busy
+    const long long pairs = nunits * ((h->num_beams + 31) / 32);
+    const int blocks = batch ? (int)std::min<long long>(nbatches, h->sm_count)
+                             : (int)std::max<long long>(1, std::min<long long>((pairs + kTabWarps - 1) / kTabWarps, h->sm_count));
+    if (!batch) {   // the units of the last partial round are split by beams and ADD to their particles' scores: zero those
+        long long whole_units, items;
+        int split;
+        table_tail_split(nunits, (long long)blocks * kTabWarps, (h->num_beams + 31) / 32, whole_units, split, items);
+        if (whole_units < nunits)
+            CK(cudaMemsetAsync(a.score2 + a.lo + whole_units * 32, 0, sizeof(int32_t) * (size_t)(a.hi - a.lo - whole_units * 32),
+                               h->stream));
+    }
     auto launch = [&](auto kernel) -> int {
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
         kernel<<<blocks, kTabThreads, smem_total, h->stream>>>(a);
         CKL(h);
         return MCL_OK;
     };
-    int rc;
-    if (h->scan_interp) rc = h->count_gathers ? launch(score_table_kernel<true, true>) : launch(score_table_kernel<true, false>);
-    else rc = h->count_gathers ? launch(score_table_kernel<false, true>) : launch(score_table_kernel<false, false>);
+    auto pick = [&](auto interp, auto count) -> int {
+        constexpr bool I = decltype(interp)::value, C = decltype(count)::value;
+        if (batch) return wide ? launch(score_table_kernel<I, C, true, true>) : launch(score_table_kernel<I, C, true, false>);
+        return wide ? launch(score_table_kernel<I, C, false, true>) : launch(score_table_kernel<I, C, false, false>);
+    };
+    using T = std::true_type; using F = std::false_type;
+    if (h->scan_interp) rc = h->count_gathers ? pick(T{}, T{}) : pick(T{}, F{});
+    else rc = h->count_gathers ? pick(F{}, T{}) : pick(F{}, F{});
     if (rc) return rc;
     // the plan and the build summary follow the kernel to pinned memory: the hint for the next update
     CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->tab_hint->build, h->tab_build, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->tab_hint->build, h->tab_build, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->ev_tab_hint, h->stream));
     h->tab_hint_pending = true;
-    return 1;
+    return 1 + h->tab_variant;
 }
 
 int run_score(mcl_engine* h)
@@ -696,11 +793,12 @@ int run_score(mcl_engine* h)
     if (local > 0) {
         const int tr = run_score_table(h, a);
         if (tr < 0) return tr;
-        if (tr == 1) {
+        if (tr >= 1) {
             int rc = join_pushes(h);
             if (rc) return rc;
             h->stats.lanes_per_particle = 1;
-            h->stats.map_tile_used = 4;
+            h->stats.map_tile_used = tr >= 3 ? 5 : 4;
+            h->stats.table_variant = tr - 1;
             h->stats.sensor_path = 3;
             h->stats.fast_eps = h->stats_eps;
             h->stats.evals = local * (long long)h->num_beams;
@@ -1062,14 +1160,14 @@ void free_all(mcl_engine* h)
     F(h->opened); F(h->fallbacks); F(h->overruns); F(h->gather_counter); F(h->deferred_counter); F(h->masks); F(h->windows); F(h->map_beams); F(h->map_counts); F(h->map_flag);
     if (h->map_beams_host) cudaFreeHost(h->map_beams_host);
     if (h->map_flag_host) cudaFreeHost(h->map_flag_host);
-    F(h->ess_acc); F(h->bbox); F(h->est_out); F(h->map); F(h->map_fast); F(h->map_lf); F(h->dt_steps); F(h->beams); F(h->noise); F(h->staging);
+    F(h->ess_acc); F(h->bbox); F(h->est_out); F(h->map); F(h->map_fast); F(h->map_lf); F(h->map_cls); F(h->map_pack); F(h->dt_steps); F(h->beams); F(h->noise); F(h->staging);
     if (h->est_host) cudaFreeHost(h->est_host);
     if (h->beams_host) cudaFreeHost(h->beams_host);
     if (h->host_bbox) cudaFreeHost(h->host_bbox);
     if (h->host_bbox_init) cudaFreeHost(h->host_bbox_init);
     if (h->tab_hint) cudaFreeHost(h->tab_hint);
     if (h->ev_tab_hint) cudaEventDestroy(h->ev_tab_hint);
-    F(h->tab_plan); F(h->tab_build); F(h->tab_box);
+    F(h->tab_plan); F(h->tab_build); F(h->tab_box); F(h->tab_bboxes);
     if (h->host_counters) cudaFreeHost(h->host_counters);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1203,11 +1301,12 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMallocHost((void**)&h->host_bbox_init, 16));
     h->host_bbox_init[0] = h->host_bbox_init[1] = 0x7fffffff;
     h->host_bbox_init[2] = h->host_bbox_init[3] = (int)0x80000000;
-    CKB(cudaMalloc((void**)&h->tab_box, 16));
+    CKB(cudaMalloc((void**)&h->tab_box, 64));
+    CKB(cudaMemset(h->tab_box, 0, 64));
     CKB(cudaMemcpy(h->tab_box, h->host_bbox_init, 16, cudaMemcpyHostToDevice));
     CKB(cudaMalloc((void**)&h->tab_plan, sizeof(TabPlan)));
     CKB(cudaMemset(h->tab_plan, 0, sizeof(TabPlan)));
-    CKB(cudaMalloc((void**)&h->tab_build, 2 * sizeof(int)));
+    CKB(cudaMalloc((void**)&h->tab_build, 8 * sizeof(int)));
     CKB(cudaMallocHost((void**)&h->tab_hint, sizeof(mcl_engine::TabHint)));
     std::memset(h->tab_hint, 0, sizeof(mcl_engine::TabHint));
     CKB(cudaEventCreateWithFlags(&h->ev_tab_hint, cudaEventDisableTiming));
@@ -1351,16 +1450,24 @@ int mcl_set_map(mcl_engine* h, const int8_t* cells, int width, int height, float
     if (!cells || width <= 0 || height <= 0) return fail(h, MCL_ERR_INVALID, "bad map");
     CK(cudaSetDevice(h->device));
     const int pitch = (width + 15) & ~15;     // 16-byte rows: aligned word loads for the tile stager (and TMA-ready)
-    if (!h->map || h->grid.pitch != pitch || h->grid.height != height) {
+    const int cpitch = (width + 2 * kTabApron + 15) & ~15;
+    const size_t crows = (size_t)height + 2 * kTabApron;
+    if (!h->map || h->grid.pitch != pitch || h->grid.height != height || h->cpitch != cpitch) {
         if (h->map) {
             CK(cudaStreamSynchronize(h->stream));
             cudaFree(h->map); cudaFree(h->map_fast); cudaFree(h->map_lf); cudaFree(h->dt_steps);
+            cudaFree(h->map_cls); cudaFree(h->map_pack);
             h->map = h->map_fast = h->map_lf = nullptr; h->dt_steps = nullptr;
+            h->map_cls = nullptr; h->map_pack = nullptr;
         }
         CK(cudaMalloc((void**)&h->map, (size_t)pitch * height + 16));
         CK(cudaMalloc((void**)&h->map_fast, (size_t)pitch * height + 16));
         CK(cudaMalloc((void**)&h->map_lf, (size_t)pitch * height + 16));
+        CK(cudaMalloc((void**)&h->map_cls, (size_t)cpitch * crows));
+        CK(cudaMalloc((void**)&h->map_pack, sizeof(unsigned long long) * (size_t)cpitch * crows));
+        h->cpitch = cpitch;
     }
+    CK(cudaMemsetAsync(h->map_cls, 0, (size_t)cpitch * crows, h->stream));
     if (h->dt_steps && (h->grid.width != width || h->grid.height != height)) { cudaFree(h->dt_steps); h->dt_steps = nullptr; }
     CK(cudaMemsetAsync(h->map_lf, 0, (size_t)pitch * height + 16, h->stream));
     CK(cudaMemsetAsync(h->map, 0, (size_t)pitch * height + 16, h->stream));
@@ -1551,6 +1658,9 @@ int mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime
     CKL(h);
     h->pose_utime = h->parent_utime = utime;     // particle_filter.cpp:29-30
     h->tab_ok = false;
+    h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
+    h->tab_batch = kTabBatch;
+    h->tab_excluded = 0;
     h->have_particles = true;
     h->have_scores = false;
     h->last_estimate.x = x; h->last_estimate.y = y; h->last_estimate.theta = theta; h->last_estimate.utime = utime;
@@ -1579,6 +1689,9 @@ int mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed)
     CKL(h);
     h->pose_utime = h->parent_utime = utime;
     h->tab_ok = false;
+    h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
+    h->tab_batch = kTabBatch;
+    h->tab_excluded = 0;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;
@@ -1605,6 +1718,9 @@ int mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n)
     h->pose_utime = aos[0].pose.utime;
     h->parent_utime = aos[0].parent_pose.utime;
     h->tab_ok = false;
+    h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
+    h->tab_batch = kTabBatch;
+    h->tab_excluded = 0;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;

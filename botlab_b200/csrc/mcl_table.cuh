@@ -52,6 +52,8 @@ constexpr int kTabWarps = kTabThreads / 32;
 constexpr int kTabQueue = 192;               // per-warp queue of deferred (lane, beam) entries
 constexpr int kTabFixed = 129;               // T entries 0..128: the uniform classes
 constexpr int kTabMaxBeams = 2047;           // queue entries are (lane << 11) | beam
+constexpr int kTabBatch = 4096;              // batch mode: consecutive particles that share one window (4 serpentine blocks
+constexpr int kTabBatchSmall = 1024;         // of mcl_init_uniform), or 1024 when the cloud is too sparse for that to fit
 constexpr float kTabB2 = 0.59033447f;        // 4/pi * atan(1/2): the octant boundaries in u8 units (see tab_sector)
 constexpr float kTabS = 0.84697730f;         // 0.5 / kTabB2: u8 * S rounds to 0 inside +-B2, to +-1 beyond
 constexpr float kTabC8 = 1.27323954f;        // 8 / (2 pi)
@@ -65,9 +67,12 @@ struct __align__(16) TabBeam { float ratio, theta, rcx, rcy; };
 struct TabPlan {
     int ok;                      // 0: the table pass is not applicable -> every evaluation takes the exact path
     int x0, y0, w, h;            // window, global cells
-    int pitch_k;                 // K entries per row (2 bytes each); pitch_k / 2 is odd (rows spread over the banks)
+    int pitch_k;                 // K entries per row (2 bytes each, pitch_k / 2 odd; wide windows: 1 byte each, pitch_k / 4
+                                 // odd): rows spread over the banks
     int cap_entries;             // T capacity, the fixed ones included
     unsigned off_k, off_t;       // byte offsets of K and T in dynamic shared memory
+    int nseg;                    // wide windows: 64-cell segments per row (aligned in cell + bias_x)
+    int seg_off;                 // wide windows: byte offset of the segment bases within a row of K
     // normalised coordinate of a window-relative coordinate c:  n = (c + off) * inv_s,  off = kappa - 0.5,
     // s = w - 1.5 (x) / h - 1.5 (y).  bits(1 + n) * mul = ((floor(c + kappa) + bias) << 32) | fraction(c + kappa) 2^32
     double off, inv_sx, inv_sy;
@@ -82,6 +87,16 @@ struct TabPlan {
     float x2_lo_x, x2_lo_y;               // EDGE >= 1: normalised doubled endpoints at or above these are certainly >= 0
     int need_bytes;              // shared memory the window needs (K + fixed T + a minimum of entries)
     int reason;                  // why ok == 0 (diagnostic): 1 scan, 2 bbox, 3 window size, 4 eps, 5 disabled
+    // batch mode (global localisation: the cloud as a whole does not fit one window): every batch of kTabBatch
+    // consecutive particles gets a window of the SAME size (w, h) at its own origin (tab_batch_window), so everything
+    // above that depends on the size only is shared and x0, y0, ulo/uhi, hmin, x2_lo are rewritten per batch
+    int batch;                   // 1: this plan is a batch-mode plan
+    int wide;                    // 1: one-byte class tile + segment bases (windows too large for 16-bit classes)
+    int variant;                 // the variant this plan was made for (TabPlanIn::variant)
+    int best;                    // the best applicable variant (-1: none): the host follows it on the next update
+    int misfits;                 // batch mode: batches whose own window exceeds (w, h) -- they take the exact path
+    double rc6;                  // longest ray in cells + 6: the margin around a bounding box
+    double x2_min;               // global coordinate the doubled endpoint must exceed (EDGE >= 1)
 };
 
 struct TabPlanIn {
@@ -92,65 +107,237 @@ struct TabPlanIn {
     int scan_finite;
     int allow;
     int smem_total, smem_fixed;
+    int variant;                 // kTabSingle16 .. kTabBatch8: what the host is going to launch
+    int excluded;                // bit v: variant v is not to be used (its score table overflowed on this cloud)
+    long long num_batches;
 };
 
-// One thread: box -> window -> budget.  Resets the box for the next bbox_kernel.
+// Kernel variants, best first: one window for the whole slice or one per batch of particles; 16-bit classes (the class
+// is the index of the score-table entry) or 8-bit classes with per-segment entry bases (half the shared memory per
+// cell, six more instructions per evaluation).  A rebuild per batch costs less than the wide lookup.
+constexpr int kTabSingle16 = 0, kTabSingle8 = 1, kTabBatch16 = 2, kTabBatch8 = 3;
+
+__host__ __device__ inline long long tab_pitch_k(long long tw)
+{
+    long long p = (tw + 1) & ~1ll;
+    if (((p >> 1) & 1) == 0) p += 2;
+    return p;
+}
+__host__ __device__ inline long long tab_k_bytes(long long tw, long long th) { return (tab_pitch_k(tw) * 2 * th + 15) & ~15ll; }
+// wide windows: a row holds one byte per cell, then one 16-bit entry base per 64-cell segment of the row (segments are
+// aligned in (cell + bias_x), bias_x = 127 w - 191); rows of an odd number of words
+__host__ __device__ inline long long tab_nseg(long long tw)
+{
+    const long long bias = 127 * tw - 191;
+    return ((bias + tw - 1) >> 6) - (bias >> 6) + 1;
+}
+__host__ __device__ inline long long tab_seg_off(long long tw) { return (tw + 1) & ~1ll; }       // of the bases within a row
+__host__ __device__ inline long long tab_pitch_k8(long long tw)
+{
+    long long p = (tab_seg_off(tw) + 2 * tab_nseg(tw) + 3) & ~3ll;
+    if (((p >> 2) & 1) == 0) p += 4;
+    return p;
+}
+__host__ __device__ inline long long tab_k8_bytes(long long tw, long long th) { return (tab_pitch_k8(tw) * th + 15) & ~15ll; }
+// Batch mode sizes its windows so that T has room for one entry per 16 cells besides the fixed ones (free cells next to an
+// occupied one: 2 % of the synthetic maps' cells, up to 6.5 % of a window's); a batch that needs more takes the exact path.
+__host__ __device__ inline long long tab_batch_bytes(long long tw, long long th, bool wide)
+{
+    const long long e = tw * th / 16;
+    return (wide ? tab_k8_bytes(tw, th) : tab_k_bytes(tw, th)) + 8 * (kTabFixed + (e > 256 ? e : 256));
+}
+
+// Unclipped cell range of the window of a bounding box (ordered-int floats, bbox of poses and parents):
+// box +- (longest ray + 6 cells).  +6: every particle inside the box then passes make_tab_base's interior test, whose
+// reach carries 4 cells of margin plus 1.5 for the window's border.  Returns 0, or the reason it has none (2: box not
+// finite / empty, 3: out of the representable range).
+__device__ __forceinline__ int tab_box_cells(int b0, int b1, int b2, int b3, const DevGrid& g, double rc6, long long& ux0,
+                                             long long& uy0, long long& ux1, long long& uy1)
+{
+    auto unorder = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
+    const float mnx = unorder(b0), mny = unorder(b1), mxx = unorder(b2), mxy = unorder(b3);
+    if (!(isfinite(mnx) && isfinite(mny) && isfinite(mxx) && isfinite(mxy)) || mnx > mxx || mny > mxy) return 2;
+    const double cpm = (double)g.cells_per_meter;
+    const double cx0 = floor(((double)mnx - (double)g.origin_x) * cpm - rc6);
+    const double cy0 = floor(((double)mny - (double)g.origin_y) * cpm - rc6);
+    const double cx1 = ceil(((double)mxx - (double)g.origin_x) * cpm + rc6);
+    const double cy1 = ceil(((double)mxy - (double)g.origin_y) * cpm + rc6);
+    if (!(fabs(cx0) < 1.0e6 && fabs(cy0) < 1.0e6 && cx1 - cx0 < 8192.0 && cy1 - cy0 < 8192.0)) return 3;
+    ux0 = (long long)cx0; uy0 = (long long)cy0; ux1 = (long long)cx1; uy1 = (long long)cy1;
+    return 0;
+}
+
+// The plan fields that depend on where the window lies: window [x0, x0 + w) x [y0, y0 + h) serving the particles whose
+// rays stay inside the unclipped box [ux0, ux1] x [uy0, uy1].
+__device__ __forceinline__ void tab_window_fields(TabPlan& pl, long long x0, long long y0, long long ux0, long long uy0,
+                                                  long long ux1, long long uy1)
+{
+    pl.x0 = (int)x0; pl.y0 = (int)y0;
+    pl.ulo_x = (float)((double)ux0 + 1.5 + (double)pl.reach); pl.uhi_x = (float)((double)(ux1 + 1) - 1.5 - (double)pl.reach);
+    pl.ulo_y = (float)((double)uy0 + 1.5 + (double)pl.reach); pl.uhi_y = (float)((double)(uy1 + 1) - 1.5 - (double)pl.reach);
+    pl.hmin_x = (unsigned)((long long)pl.bias_x - x0);
+    pl.hmin_y = (unsigned)((long long)pl.bias_y - y0);
+    pl.x2_lo_x = (float)((pl.x2_min - (double)x0 + pl.off) * pl.inv_sx * (1.0 + 1e-6) + 1e-7);
+    pl.x2_lo_y = (float)((pl.x2_min - (double)y0 + pl.off) * pl.inv_sy * (1.0 + 1e-6) + 1e-7);
+}
+
+// Batch mode: places the plan's fixed-size window for the batch whose bounding box is bx.  The window is the batch's
+// unclipped box shifted (not shrunk) into [-4, W + 3] x [-4, H + 3]: it still covers every cell of the box within four
+// cells of the grid, and wherever rays can leave it its border lies four cells outside the grid (class 0).  false: the
+// batch needs a larger window than the plan's (its evaluations take the exact path).
+__device__ __forceinline__ bool tab_batch_window(TabPlan& pl, const int4 bx, const DevGrid& g)
+{
+    long long ux0, uy0, ux1, uy1;
+    if (tab_box_cells(bx.x, bx.y, bx.z, bx.w, g, pl.rc6, ux0, uy0, ux1, uy1) != 0) return false;
+    if (ux1 - ux0 + 1 > pl.w || uy1 - uy0 + 1 > pl.h) return false;
+    const long long hx = (long long)g.width + 3 - (pl.w - 1), hy = (long long)g.height + 3 - (pl.h - 1);
+    long long x0 = ux0 < hx ? ux0 : hx, y0 = uy0 < hy ? uy0 : hy;
+    if (x0 < -4) x0 = -4;
+    if (y0 < -4) y0 = -4;
+    tab_window_fields(pl, x0, y0, ux0, uy0, ux1, uy1);
+    return true;
+}
+
+// Bounding boxes: of the whole slice (box[0..3], ordered-int atomics) and of every batch of kTabBatch consecutive
+// particles, kTabBatch or kTabBatchSmall (bboxes[b]).  For 16-bit classes, box[4], box[5] = the largest window width
+// and height among the batches whose own window fits the shared-memory budget, box[6] = the number of batches that do
+// not (non-finite poses, or spread too far); box[7], box[8] = the same maxima over the fitting batches that are at
+// least as wide as tall, box[9] = the number of fitting batches that are taller than wide (the serpentine order of
+// mcl_init_uniform runs along x: only the batches at its row turns are tall, and one window size for both orientations
+// would have to be square).  box[10 .. 15] = the same for 8-bit classes.
+__global__ void __launch_bounds__(256) table_bbox_kernel(const float* x, const float* y, const float* px, const float* py,
+                                                         long long lo, long long hi, int batch, DevGrid grid, double rc6,
+                                                         long long k_budget, int* box, int4* bboxes)
+{
+    __shared__ int red[4][8];
+    const long long first = lo + (long long)blockIdx.x * batch;
+    const long long last = first + batch < hi ? first + batch : hi;
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+    for (long long i = first + threadIdx.x; i < last; i += blockDim.x) {
+        const int a = float_order(x[i]), b = float_order(y[i]), c = float_order(px[i]), d = float_order(py[i]);
+        mnx = min(mnx, min(a, c)); mxx = max(mxx, max(a, c));
+        mny = min(mny, min(b, d)); mxy = max(mxy, max(b, d));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mny;
+        red[2][threadIdx.x >> 5] = mxx; red[3][threadIdx.x >> 5] = mxy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            mnx = min(mnx, red[0][k]); mny = min(mny, red[1][k]); mxx = max(mxx, red[2][k]); mxy = max(mxy, red[3][k]);
+        }
+        atomicMin(box + 0, mnx); atomicMin(box + 1, mny);
+        atomicMax(box + 2, mxx); atomicMax(box + 3, mxy);
+        if (bboxes) {
+            bboxes[blockIdx.x] = make_int4(mnx, mny, mxx, mxy);
+            long long ux0, uy0, ux1, uy1;
+            const bool cells = tab_box_cells(mnx, mny, mxx, mxy, grid, rc6, ux0, uy0, ux1, uy1) == 0;
+            const int bw = (int)(ux1 - ux0 + 1), bh = (int)(uy1 - uy0 + 1);
+            for (int wide = 0; wide < 2; ++wide) {
+                int* bx = box + 4 + 6 * wide;
+                if (cells && tab_batch_bytes(bw, bh, wide != 0) <= k_budget) {
+                    atomicMax(bx + 0, bw); atomicMax(bx + 1, bh);
+                    if (bw >= bh) { atomicMax(bx + 3, bw); atomicMax(bx + 4, bh); }
+                    else atomicAdd(bx + 5, 1);
+                } else {
+                    atomicAdd(bx + 2, 1);
+                }
+            }
+        }
+    }
+}
+
+// One thread: boxes -> window(s) -> budget.  Re-arms the boxes for the next table_bbox_kernel.
 __global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
 {
     TabPlan pl;
     memset(&pl, 0, sizeof(pl));
-    auto unorder = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
-    const float mnx = unorder(box[0]), mny = unorder(box[1]), mxx = unorder(box[2]), mxy = unorder(box[3]);
+    const int b0 = box[0], b1 = box[1], b2 = box[2], b3 = box[3];
+    long long bdim[2][3];            // [wide]: window width, height, upper bound of the batches that will not fit it
     box[0] = 0x7fffffff; box[1] = 0x7fffffff; box[2] = (int)0x80000000; box[3] = (int)0x80000000;
+    {
+        const long long room_b = (long long)in.smem_total - in.smem_fixed - 64;
+        for (int wide = 0; wide < 2; ++wide) {
+            const int* bx = box + 4 + 6 * wide;
+            bdim[wide][0] = bx[0]; bdim[wide][1] = bx[1]; bdim[wide][2] = bx[2];
+            // both orientations in one window size if that fits, else the wide batches' size (the tall ones: exact path)
+            if (bx[0] >= 8 && bx[1] >= 8 && tab_batch_bytes(bx[0], bx[1], wide != 0) > room_b && bx[3] >= 8 && bx[4] >= 8) {
+                bdim[wide][0] = bx[3]; bdim[wide][1] = bx[4]; bdim[wide][2] = (long long)bx[2] + bx[5];
+            }
+        }
+    }
+    for (int i = 4; i < 16; ++i) box[i] = 0;
     const double cpm = (double)in.grid.cells_per_meter;
     const double Rc = (double)in.max_range * cpm;
     const double rho_max = fmax(fabs(in.ratio_lo), fabs(in.ratio_hi));
+    pl.rc6 = Rc + 6.0;
+    pl.variant = in.variant;
+    pl.best = -1;
     do {
         if (!in.allow) { pl.reason = 5; break; }
         if (!in.scan_finite || in.num_beams < 1 || in.num_beams > kTabMaxBeams || !isfinite(Rc) || !(cpm > 0.0) ||
             !((double)in.min_range * cpm >= 2.5) || !(in.max_abs_theta <= 6.3f) || !(in.ratio_lo >= -1.0) ||
             !(in.ratio_hi <= 2.0)) { pl.reason = 1; break; }
-        if (!(isfinite(mnx) && isfinite(mny) && isfinite(mxx) && isfinite(mxy)) || mnx > mxx || mny > mxy) { pl.reason = 2; break; }
-        // window = bounding box of poses and parents +- (longest ray + 6 cells), not clipped to the grid (cells outside
-        // read 0).  +6: every particle of the cloud then passes make_tab_base's interior test, whose reach carries
-        // 4 cells of margin plus 1.5 for the window's border.
-        const double reach = Rc + 6.0;
-        const double cx0 = floor(((double)mnx - (double)in.grid.origin_x) * cpm - reach);
-        const double cy0 = floor(((double)mny - (double)in.grid.origin_y) * cpm - reach);
-        const double cx1 = ceil(((double)mxx - (double)in.grid.origin_x) * cpm + reach);
-        const double cy1 = ceil(((double)mxy - (double)in.grid.origin_y) * cpm + reach);
-        if (!(fabs(cx0) < 1.0e6 && fabs(cy0) < 1.0e6 && cx1 - cx0 < 8192.0 && cy1 - cy0 < 8192.0)) { pl.reason = 3; break; }
-        const long long ux0 = (long long)cx0, uy0 = (long long)cy0, ux1 = (long long)cx1, uy1 = (long long)cy1;
-        // clipped to the grid plus four cells: everything beyond is class 0, and so are the clipped window's border cells,
-        // onto which the saturating coordinate arithmetic maps rays that leave it
+        // one window: the slice's box, not clipped to the grid for the particle tests (cells outside read 0) ...
+        long long ux0 = 0, uy0 = 0, ux1 = 0, uy1 = 0;
+        const int br = tab_box_cells(b0, b1, b2, b3, in.grid, pl.rc6, ux0, uy0, ux1, uy1);
+        if (br == 2) { pl.reason = 2; break; }
+        // ... and clipped to the grid plus four cells for the tile: everything beyond is class 0, and so are the clipped
+        // window's border cells, onto which the saturating coordinate arithmetic maps rays that leave it
         const long long x0 = ux0 > -4 ? ux0 : -4, y0 = uy0 > -4 ? uy0 : -4;
         const long long x1 = ux1 < in.grid.width + 3 ? ux1 : in.grid.width + 3, y1 = uy1 < in.grid.height + 3 ? uy1 : in.grid.height + 3;
-        const long long tw = x1 - x0 + 1, th = y1 - y0 + 1;
-        if (tw < 8 || th < 8) { pl.reason = 3; break; }       // (a cloud whose rays cannot reach the grid)
-        long long pitch_k = (tw + 1) & ~1ll;
-        if (((pitch_k >> 1) & 1) == 0) pitch_k += 2;
-        const long long k_bytes = (pitch_k * 2 * th + 15) & ~15ll;
-        const long long room = (long long)in.smem_total - in.smem_fixed - k_bytes - 64;
-        pl.need_bytes = (int)fmin(2.0e9, (double)(in.smem_fixed + k_bytes + 64 + 8 * (kTabFixed + 256)));
-        if (room < 8 * (kTabFixed + 256)) { pl.reason = 3; break; }
+        const long long sw = x1 - x0 + 1, sh = y1 - y0 + 1;
+        const long long room_base = (long long)in.smem_total - in.smem_fixed - 64;
+        const long long min_t = 8 * (kTabFixed + 256);
+        bool fit[4];
+        const bool single = br == 0 && sw >= 8 && sh >= 8;              // (sw < 8: a cloud whose rays cannot reach the grid)
+        fit[kTabSingle16] = single && room_base - tab_k_bytes(sw, sh) >= min_t;
+        fit[kTabSingle8] = single && room_base - tab_k8_bytes(sw, sh) >= min_t;
+        for (int wide = 0; wide < 2; ++wide)
+            fit[kTabBatch16 + wide] = in.num_batches > 0 && bdim[wide][0] >= 8 && bdim[wide][1] >= 8 &&
+                                      bdim[wide][2] * 50 <= in.num_batches &&
+                                      room_base - tab_batch_bytes(bdim[wide][0], bdim[wide][1], wide != 0) >= 0;
+        for (int v = 3; v >= 0; --v)
+            if (fit[v] && !((in.excluded >> v) & 1)) pl.best = v;
+        pl.need_bytes = br == 0 ? (int)fmin(2.0e9, (double)(in.smem_fixed + tab_k_bytes(sw, sh) + 64 + min_t)) : 0;
+        const int v = in.variant;
+        if (v < 0 || v > 3 || !fit[v] || ((in.excluded >> v) & 1)) { pl.reason = 3; break; }
+        const bool batch = v >= kTabBatch16, wide = (v & 1) != 0;
+        const long long tw = batch ? bdim[wide][0] : sw, th = batch ? bdim[wide][1] : sh;
+        pl.misfits = batch ? (int)bdim[wide][2] : 0;
+        const long long pitch_k = wide ? tab_pitch_k8(tw) : tab_pitch_k(tw);
+        const long long k_bytes = wide ? tab_k8_bytes(tw, th) : tab_k_bytes(tw, th);
+        const long long room = room_base - k_bytes;
         // error budget (cells).  Reference vs the real-valued model: as fast_plan (mcl_engine.cu).  Float model vs the
         // same: roundings of dS, rho and rc, the angle roundings and the measured SFU error; its coordinate roundings
         // (the normalised robot coordinate, the ratio FFMA, the endpoint FFMA, the +1.0) are below 2^-24 of the
         // window's extent each.
         const double u = 5.9604644775390625e-08;
         const double Cm = (double)(ux1 > uy1 ? ux1 : uy1) + 2.0;
-        if (Cm > 16000.0) { pl.reason = 3; break; }
+        if (br != 0 || Cm > 16000.0) { pl.reason = 3; pl.best = -1; break; }
         const double Xm = Cm / cpm + fmax(fabs((double)in.grid.origin_x), fabs((double)in.grid.origin_y));
         const double max_shift = 64.0;
         const double Ce = Cm + Rc;
         const double e_ref = cpm * u * Xm + 2.0 * u * Ce + 2.0 * u * Rc + Rc * (20.0 * u + 1.2e-7) + 1e-9;
+        // (angle: roundings of theta_r, of the folded beam angle and of their difference, + the SFU's error)
         const double e_apx = 6.0 * u * (double)(tw > th ? tw : th) + (1.0 + 2.0 * rho_max) * u * max_shift + 3.0 * u * Rc +
-                             Rc * ((3.14159265358979 * (3.0 * rho_max + 1.0) + 9.5) * u + (double)kFastTrigErr);
+                             Rc * ((3.14159265358979 * (3.0 * rho_max + 2.0) + 9.5) * u + (double)kFastTrigErr);
         const double eps = 1.25 * (e_ref + e_apx) + 1e-6;
         const double kappa = eps + 1e-5;
-        if (kappa > 1.0 / 16.0) { pl.reason = 4; break; }
+        if (kappa > 1.0 / 16.0) { pl.reason = 4; pl.best = -1; break; }
         pl.ok = 1;
-        pl.x0 = (int)x0; pl.y0 = (int)y0; pl.w = (int)tw; pl.h = (int)th; pl.pitch_k = (int)pitch_k;
+        pl.batch = batch ? 1 : 0;
+        pl.wide = wide ? 1 : 0;
+        pl.w = (int)tw; pl.h = (int)th; pl.pitch_k = (int)pitch_k;
+        pl.nseg = (int)tab_nseg(tw);
+        pl.seg_off = (int)tab_seg_off(tw);
         pl.cap_entries = (int)(room / 8);
         pl.off_k = (unsigned)in.smem_fixed;
         pl.off_t = (unsigned)(in.smem_fixed + k_bytes);
@@ -165,14 +352,9 @@ __global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
         pl.max_shift = (float)max_shift;
         pl.coord_hi = (float)(Cm - 1.0);
         pl.reach = (float)(Rc * (1.0 + 1e-6) + 4.0);
-        pl.ang_room = 9.5f - in.max_abs_theta;             // kFastTrigErr is measured for |angle| <= 9.5
-        pl.ulo_x = (float)((double)ux0 + 1.5 + (double)pl.reach); pl.uhi_x = (float)((double)(ux1 + 1) - 1.5 - (double)pl.reach);
-        pl.ulo_y = (float)((double)uy0 + 1.5 + (double)pl.reach); pl.uhi_y = (float)((double)(uy1 + 1) - 1.5 - (double)pl.reach);
-        pl.hmin_x = (unsigned)((long long)pl.bias_x - x0);
-        pl.hmin_y = (unsigned)((long long)pl.bias_y - y0);
-        const double x2_min = 3.0 * eps + 2.0 * kappa + 1e-3;         // global coordinate the doubled endpoint must exceed
-        pl.x2_lo_x = (float)((x2_min - (double)x0 + pl.off) * pl.inv_sx * (1.0 + 1e-6) + 1e-7);
-        pl.x2_lo_y = (float)((x2_min - (double)y0 + pl.off) * pl.inv_sy * (1.0 + 1e-6) + 1e-7);
+        pl.ang_room = 9.5f - fminf(in.max_abs_theta, 3.1415928f);      // kFastTrigErr is measured for |angle| <= 9.5
+        pl.x2_min = 3.0 * eps + 2.0 * kappa + 1e-3;        // global coordinate the doubled endpoint must exceed
+        tab_window_fields(pl, x0, y0, ux0, uy0, ux1, uy1); // (batch mode: rewritten for every batch)
     } while (false);
     *out = pl;
 }
@@ -233,6 +415,7 @@ struct TabConst {
     unsigned k0;            // shared address of T / 8: the K tile stores class + k0
     unsigned k129;          // k0 + kTabFixed
     unsigned lf;            // likelihood-field mode (gather counting only)
+    unsigned sdelta;        // WIDE: from the row term of a cell's address to the row's segment bases (minus the bias)
 };
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c)
@@ -245,7 +428,9 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c)
 // One certified evaluation of the table pass.  Returns true when certain; add = its score in half units (else 0).
 // EDGE (warp-uniform, from TabBase::edge): 1 adds the test that the doubled endpoint has no negative coordinate (the
 // sector is not certified otherwise), 2 also the test that the endpoint's global cell is >= 0.
-template <bool INTERP, bool COUNT, int EDGE>
+// WIDE: the class tile holds one byte per cell -- 0, 1, 2..128 as above, 129 + i = the i-th cell with a table entry of
+// its 64-cell row segment -- and a second lookup (one 16-bit base per segment) completes the entry's index.
+template <bool INTERP, bool COUNT, int EDGE, bool WIDE>
 __device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, float d8, const TabConst& tc,
                                          const TabPlan& pl, int& add, int& gathers)
 {
@@ -263,13 +448,22 @@ __device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, flo
     asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(fy), "=r"(hy) : "r"(__float_as_uint(byf)), "r"(tc.mul_y));
     bool cell_ok = min(fx, fy) >= tc.frac_thr;
     if (EDGE >= 2) cell_ok = cell_ok & (hx >= pl.hmin_x) & (hy >= pl.hmin_y);       // global cell >= 0 on both axes
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(kaddr) : "r"(hy), "r"(tc.pitch2), "r"(tc.kbase));
-    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(kaddr) : "r"(hx), "r"(kaddr));
+    unsigned krow;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(krow) : "r"(hy), "r"(tc.pitch2), "r"(tc.kbase));
+    if (WIDE) kaddr = krow + hx;
+    else asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(kaddr) : "r"(hx), "r"(krow));
     bool x2_pos = true;
     if (EDGE >= 1)      // the doubled endpoint must not have a negative coordinate (the reference truncates toward zero there)
         x2_pos = (__fmaf_rn(b.rcx, c, nx) >= pl.x2_lo_x) & (__fmaf_rn(b.rcy, s, ny) >= pl.x2_lo_y);
-    unsigned K;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(K) : "r"(kaddr));
+    unsigned K, sb = 0u;
+    if (WIDE) {
+        unsigned saddr;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(K) : "r"(kaddr));
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(saddr) : "r"(hx >> 6), "r"(krow + tc.sdelta));
+        asm("ld.shared.u16 %0, [%1];" : "=r"(sb) : "r"(saddr));
+    } else {
+        asm("ld.shared.u16 %0, [%1];" : "=r"(K) : "r"(kaddr));
+    }
     // sector: u8 = 8t - 2 round(4t) in [-1, 1] (t = a / 2pi) is the offset from the nearest axis, +-1 = 45 degrees;
     // n = 2 round(4t) + round(u8 * S) with S = 0.5 / B2, so the rounding flips exactly at the octant boundaries +-B2
     const float r8 = __fmaf_rn(a, kTabC8, 25165824.0f);                 // 1.5 * 2^24: ulp 2
@@ -277,13 +471,41 @@ __device__ __forceinline__ bool tab_eval(const TabBase& p, const TabBeam& b, flo
     const float wq = __fmaf_rn(u8, kTabS, __fsub_rn(r8, 12582912.0f));   // 1.5 * 2^23 + 2 round(4t): ulp 1
     // K carries the table's base (shared address / 8), so K * 8 + sector is the address of the score byte
     unsigned v, taddr;
-    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(taddr) : "r"(K), "r"(__float_as_uint(wq) & 7u));
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(taddr));
     const bool dir_ok = x2_pos & (fabsf(__fsub_rn(fabsf(u8), kTabB2)) > d8);
-    const bool certain = (K == tc.k0) | (cell_ok & ((K < tc.k129) | dir_ok));
+    bool certain;
+    if (WIDE) {
+        // entry = k0 + K for the uniform classes, base of the segment (which carries k0 - 129) + K for the others
+        const bool uni = K < (unsigned)kTabFixed;
+        const unsigned e = K + (uni ? tc.k0 : sb);
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(taddr) : "r"(e), "r"(__float_as_uint(wq) & 7u));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(taddr));
+        certain = (K == 0u) | (cell_ok & (uni | dir_ok));
+        if (COUNT) gathers += certain ? ((K - 2u < 127u) | (tc.lf != 0u) ? 1 : 3) : 0;
+    } else {
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(taddr) : "r"(K), "r"(__float_as_uint(wq) & 7u));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(taddr));
+        certain = (K == tc.k0) | (cell_ok & ((K < tc.k129) | dir_ok));
+        if (COUNT) gathers += certain ? ((K - tc.k0 - 2u < 127u) | (tc.lf != 0u) ? 1 : 3) : 0;
+    }
     add = certain ? (int)v : 0;
-    if (COUNT) gathers += certain ? ((K - tc.k0 - 2u < 127u) | (tc.lf != 0u) ? 1 : 3) : 0;
     return certain;
+}
+
+// How the kernel deals its work (shared with the host, which zeroes the scores of the split units): nunits units of 32
+// particles over `slots` warps; the units of the last, partial round are split into `split` beam ranges each.
+__host__ __device__ inline void table_tail_split(long long nunits, long long slots, int nwords, long long& whole_units,
+                                                 int& split, long long& items)
+{
+    const long long rem = nunits % slots;
+    whole_units = nunits - rem;
+    split = 1;
+    if (rem > 0) {
+        long long s = slots / rem;
+        if (s > nwords) s = nwords;
+        if (s > 1) split = (int)s;
+    }
+    if (split == 1) whole_units = nunits;
+    items = whole_units + (nunits - whole_units) * split;
 }
 
 struct TabArgs {
@@ -298,18 +520,24 @@ struct TabArgs {
     const TabPlan* plan;
     unsigned long long* gather_counter;
     unsigned long long* deferred_counter;
-    int* build_info;                // [0] table entries the window needs (max over CTAs), [1] CTAs that overflowed
-    int num_peers;
-    int32_t* peer_score[kMaxPeers];
+    int* build_info;                // [0] table entries the window needs (max over CTAs), [1] CTAs (batch mode: batches)
+                                    // that overflowed, [2] batch mode: the next batch to take, [3] batches without a
+                                    // window, [4] particles outside the table pass's domain (diagnostics)
+    const uint8_t* cls;             // class map (derive_class_map_kernel) ...
+    const unsigned long long* pack; // ... and the score-table entries of its class-255 cells
+    int cpitch;                     // bytes per row of the class map
+    const int4* bboxes;             // batch mode: bounding box of every batch (table_bbox_kernel)
+    int batch;                      // batch mode: particles per batch
 };
 
 // Cold-path state shared by the CTA (static shared memory): what the exact evaluations need.
 struct TabCold {
     DevGrid grid;
     const Beam* sbeams;
-    const uint16_t* ktile;      // class tile (null: not built -- read the mirror)
+    const uint16_t* ktile;      // class tile (null: not built -- read the mirror); wide windows: bytes
     int x0, y0, w, h, pitch_k;
     unsigned k0;
+    int wide;
     int lf;                     // likelihood-field mode: a ray scores 2 u(endpoint cell), no neighbour steps
     unsigned long long deferred, gathers;
 };
@@ -320,7 +548,8 @@ __device__ __forceinline__ int tab_cell_value(const TabCold* c, int gx, int gy)
 {
     const int tx = (int)((unsigned)gx - (unsigned)c->x0), ty = (int)((unsigned)gy - (unsigned)c->y0);
     if (c->ktile && (unsigned)tx < (unsigned)c->w && (unsigned)ty < (unsigned)c->h) {
-        const unsigned cls = (unsigned)c->ktile[ty * c->pitch_k + tx] - c->k0;
+        const unsigned cls = c->wide ? (unsigned)reinterpret_cast<const uint8_t*>(c->ktile)[ty * c->pitch_k + tx]
+                                     : (unsigned)c->ktile[ty * c->pitch_k + tx] - c->k0;
         return (cls - 2u < 127u) ? (int)cls - 1 : 0;
     }
     return max(grid_read(c->grid, gx, gy), 0);
@@ -368,56 +597,46 @@ __device__ __noinline__ void tab_drain_round(unsigned entry, bool active, float 
 }
 
 // Hands the set bits of the warp's mask words (m0..m3: beams 32 wbase .. 32 wbase + 127 of each lane's particle) to the
-// exact path.  Returns the new queue length (< 32).
+// exact path: the lanes append their (lane, beam) entries to the warp's queue in lane order (positions from a warp scan
+// of the pop-counts), the queue is drained 32 entries at a time, and whatever did not fit goes in the next pass -- so
+// every drain round has 32 active lanes whatever the number and distribution of uncertain beams (a particle outside
+// the table pass's domain has all of them set).  Returns the new queue length (< 32).
 template <bool INTERP, bool COUNT>
 __device__ __noinline__ int tab_defer_words(unsigned m0, unsigned m1, unsigned m2, unsigned m3, int wbase, int qn,
                                             float xa, float ya, float tha, float xb, float yb, float thb, TabCold* cold,
                                             uint16_t* q, int* wacc)
 {
     const int lane = threadIdx.x & 31;
-    const int c = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-    int incl = c;
+    for (;;) {
+        const int c = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        int incl = c;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (qn + total <= kTabQueue) {
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) break;
         int pos = qn + incl - c;
-        unsigned m = m0;
         int beam0 = wbase * 32;
+#pragma unroll
         for (int part = 0; part < 4; ++part) {
-            while (m) {
+            unsigned m = part == 0 ? m0 : (part == 1 ? m1 : (part == 2 ? m2 : m3));
+            while (m && pos < kTabQueue) {
                 const int k = __ffs(m) - 1;
                 m &= m - 1;
                 q[pos++] = (uint16_t)((lane << 11) | (beam0 + k));
             }
-            m = part == 0 ? m1 : (part == 1 ? m2 : m3);
+            if (part == 0) m0 = m; else if (part == 1) m1 = m; else if (part == 2) m2 = m; else m3 = m;
             beam0 += 32;
         }
-        qn += total;
+        qn = min(qn + total, kTabQueue);
         __syncwarp();
         while (qn >= 32) {
             qn -= 32;
             tab_drain_round<INTERP, COUNT>(q[qn + lane], true, xa, ya, tha, xb, yb, thb, cold, wacc);
         }
         __syncwarp();
-    } else {
-        // burst (lanes outside the table pass's domain): every lane with bits left evaluates its own next beam; the
-        // queue keeps what it held
-        unsigned m = m0;
-        int beam0 = wbase * 32;
-        for (int part = 0; part < 4; ++part) {
-            while (__any_sync(0xffffffffu, m != 0u)) {
-                const bool has = m != 0u;
-                const int k = has ? __ffs(m) - 1 : 0;
-                if (has) m &= m - 1;
-                tab_drain_round<INTERP, COUNT>((unsigned)((lane << 11) | (beam0 + k)), has, xa, ya, tha, xb, yb, thb, cold, wacc);
-            }
-            m = part == 0 ? m1 : (part == 1 ? m2 : m3);
-            beam0 += 32;
-        }
     }
     return qn;
 }
@@ -426,13 +645,178 @@ __device__ __noinline__ int tab_defer_words(unsigned m0, unsigned m1, unsigned m
 #define MCL_TAB_UNROLL 4
 #endif
 
-template <bool INTERP, bool COUNT>
+// Class of one window cell (see the head of this file): 0, 1, 2..128, or kTabNeedsEntry with the cell's eight
+// neighbours in n[] (sector order) when the cell gets a score-table entry.
+constexpr unsigned kTabNeedsEntry = 0xffffffffu;
+__device__ __forceinline__ unsigned tab_classify(const TabArgs& a, int gxc, int gyc, int n[8])
+{
+    const int W = a.grid.width, H = a.grid.height, gp = a.grid.pitch;
+    const int8_t* raw = a.grid.cells;
+    auto rawc = [&](int cx, int cy) -> int {
+        return ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) ? (int)__ldg(raw + (size_t)cy * gp + cx) : 0;
+    };
+    if (gxc <= -4 || gyc <= -4 || gxc >= W + 3 || gyc >= H + 3)
+        return 0u;         // the reference's (truncated) endpoint cell and its neighbours are all outside the grid
+    if (gxc < 0 || gyc < 0)
+        return 1u;         // truncation toward zero differs from the floor here: never certified (tab_eval, EDGE 2)
+    if (a.lf_cells) {
+        // likelihood field: every class is uniform (the ray scores the field value of its endpoint cell);
+        // class 0 = the field is 0 on the cell and on its eight neighbours (certain whatever the exact cell)
+        auto lfc = [&](int cx, int cy) -> int {
+            return ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) ? (int)__ldg(a.lf_cells + (size_t)cy * gp + cx) : 0;
+        };
+        const int u = lfc(gxc, gyc);
+        if (u > 0) return 1u + (unsigned)u;
+        int mx = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) mx = max(mx, lfc(gxc + dx, gyc + dy));
+        return mx > 0 ? 1u : 0u;
+    }
+    int f;
+    if (gxc < W && gyc < H) {
+        f = (int)__ldg(a.fast_cells + (size_t)gyc * gp + gxc);
+    } else {        // beyond the high edges: the cell reads 0; is anything positive within two cells?
+        bool any = false;
+        for (int dy = -2; dy <= 2; ++dy)
+            for (int dx = -2; dx <= 2; ++dx) any = any || rawc(gxc + dx, gyc + dy) > 0;
+        f = any ? 0 : -1;
+    }
+    if (f < 0) return 0u;
+    if (f > 0) return 1u + (unsigned)f;
+    // sector s steps (ux, uy): 0 (+1,0) 1 (+1,+1) 2 (0,+1) 3 (-1,+1) 4 (-1,0) 5 (-1,-1) 6 (0,-1) 7 (+1,-1)
+    n[0] = rawc(gxc + 1, gyc);     n[1] = rawc(gxc + 1, gyc + 1); n[2] = rawc(gxc, gyc + 1);
+    n[3] = rawc(gxc - 1, gyc + 1); n[4] = rawc(gxc - 1, gyc);     n[5] = rawc(gxc - 1, gyc - 1);
+    n[6] = rawc(gxc, gyc - 1);     n[7] = rawc(gxc + 1, gyc - 1);
+    int mx = 0;
+#pragma unroll
+    for (int sct = 0; sct < 8; ++sct) mx = max(mx, n[sct]);
+    return mx <= 0 ? 1u : kTabNeedsEntry;
+}
+
+// The score-table entry of a cell from its neighbours: per sector o1 > 0 ? o1 : max(o2, 0) (sensor_model.cpp:48-57).
+__device__ __forceinline__ unsigned long long tab_entry(const int n[8])
+{
+    unsigned long long pack = 0ull;
+#pragma unroll
+    for (int sct = 0; sct < 8; ++sct) {
+        const int o1 = n[(sct + 4) & 7], o2 = n[sct];
+        const int v = o1 > 0 ? o1 : max(o2, 0);
+        pack |= (unsigned long long)v << (8 * sct);
+    }
+    return pack;
+}
+
+// The CLASS MAP: tab_classify of every cell of the grid plus a four-cell apron (cell (gx, gy) at
+// cls[(gy + 4) * cpitch + gx + 4]; 255 = the cell gets a score-table entry, which is pack[same index]), kept current with
+// the mirror (refresh_fast_map) so that building a window is a copy plus the numbering of its entries.
+constexpr int kTabApron = 4;
+__global__ void derive_class_map_kernel(const TabArgs a, uint8_t* cls, unsigned long long* pack, int cpitch, int x0, int y0,
+                                        int w, int h)
+{
+    const int total = w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int gyc = y0 + i / w, gxc = x0 + i % w;
+        int n[8];
+        const unsigned K = tab_classify(a, gxc, gyc, n);
+        const size_t at = (size_t)(gyc + kTabApron) * cpitch + (gxc + kTabApron);
+        cls[at] = (uint8_t)(K == kTabNeedsEntry ? 255u : K);
+        if (K == kTabNeedsEntry) pack[at] = tab_entry(n);
+    }
+}
+
+// Builds the class tile K and the score table T of the window in pl (see the head of this file) from the class map.
+// All threads of the CTA; synchronises inside; the caller synchronises after it.  s_count: entries of T in use beyond
+// the fixed ones, s_overflow: T is full (the caller then scores the window's particles exactly).
+//   A  copy the window's classes (many independent loads in flight);
+//   B  one warp per 64-cell row segment numbers the cells that get an entry (ballots) and reserves the segment's run of
+//      entries; the entry remembers its cell;   WIDE: the tile keeps 129 + the number within the segment, the run's
+//      base goes to the row's segment bases; else the tile keeps the entry's index;
+//   C  the entries fetch their eight scores from the class map's pack array (independent loads again).
+template <bool WIDE>
+__device__ __forceinline__ void tab_build_window(const TabPlan& pl, const TabArgs& a, uint16_t* ktile,
+                                                 unsigned long long* ttab, unsigned k0, int* s_count, int* s_overflow)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* k8 = reinterpret_cast<uint8_t*>(ktile);
+    for (int i = tid; i < kTabFixed; i += kTabThreads)
+        ttab[i] = i >= 2 ? 0x0101010101010101ull * (unsigned long long)(2 * (i - 1)) : 0ull;
+    // A
+    const uint8_t* src = a.cls + (size_t)(pl.y0 + kTabApron) * a.cpitch + (pl.x0 + kTabApron);
+    for (int ty = warp; ty < pl.h; ty += kTabWarps) {
+        const uint8_t* row = src + (size_t)ty * a.cpitch;
+        const bool row_in = pl.y0 + ty < a.grid.height + kTabApron;         // (a batch window wider than the grid + apron)
+#pragma unroll 4
+        for (int tx = lane; tx < pl.w; tx += 32) {
+            const unsigned c = (row_in && pl.x0 + tx < a.grid.width + kTabApron) ? (unsigned)__ldg(row + tx) : 0u;
+            if (WIDE) k8[ty * pl.pitch_k + tx] = (uint8_t)c;
+            else ktile[ty * pl.pitch_k + tx] = (uint16_t)(c == 255u ? 0xffffu : c + k0);
+        }
+    }
+    __syncthreads();
+    // B
+    const int seg0 = (int)(pl.bias_x >> 6);
+    const int items = pl.h * pl.nseg;
+    for (int it = warp; it < items; it += kTabWarps) {
+        const int ty = it / pl.nseg, sg = it - ty * pl.nseg;
+        const int tx_lo = max(0, (seg0 + sg) * 64 - (int)pl.bias_x), tx_hi = min(pl.w, (seg0 + sg + 1) * 64 - (int)pl.bias_x);
+        const int tx0 = tx_lo + lane, tx1 = tx_lo + 32 + lane;
+        const bool n0 = tx0 < tx_hi && (WIDE ? (unsigned)k8[ty * pl.pitch_k + tx0] == 255u : (unsigned)ktile[ty * pl.pitch_k + tx0] == 0xffffu);
+        const bool n1 = tx1 < tx_hi && (WIDE ? (unsigned)k8[ty * pl.pitch_k + tx1] == 255u : (unsigned)ktile[ty * pl.pitch_k + tx1] == 0xffffu);
+        const unsigned need0 = __ballot_sync(0xffffffffu, n0), need1 = __ballot_sync(0xffffffffu, n1);
+        const int c0 = __popc(need0), c = c0 + __popc(need1);
+        int first = 0;
+        if (c > 0) {
+            if (lane == 0) first = kTabFixed + atomicAdd(s_count, c);
+            first = __shfl_sync(0xffffffffu, first, 0);
+        }
+        const bool room = first + c <= pl.cap_entries;
+        if (c > 0 && !room && lane == 0) *s_overflow = 1;
+        if (WIDE && lane == 0)
+            *reinterpret_cast<uint16_t*>(k8 + ty * pl.pitch_k + pl.seg_off + 2 * sg) = (uint16_t)(k0 + (unsigned)first - (unsigned)kTabFixed);
+        const unsigned below = (1u << lane) - 1u;
+        if (n0 || n1) {
+            const int tx = n0 ? tx0 : tx1;
+            // (a lane with both of its cells numbered handles the second below)
+            int id = n0 ? __popc(need0 & below) : c0 + __popc(need1 & below);
+            for (int rep = 0; rep < 2; ++rep) {
+                const int txr = rep == 0 ? tx : tx1;
+                if (rep == 1) { if (!(n0 && n1)) break; id = c0 + __popc(need1 & below); }
+                if (room) {
+                    ttab[first + id] = (unsigned long long)((unsigned)(pl.y0 + ty + kTabApron) * (unsigned)a.cpitch + (unsigned)(pl.x0 + txr + kTabApron));
+                    if (WIDE) k8[ty * pl.pitch_k + txr] = (uint8_t)(kTabFixed + id);
+                    else ktile[ty * pl.pitch_k + txr] = (uint16_t)((unsigned)(first + id) + k0);
+                } else {
+                    if (WIDE) k8[ty * pl.pitch_k + txr] = 1u;
+                    else ktile[ty * pl.pitch_k + txr] = (uint16_t)(1u + k0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // C  (not after an overflow: the caller scores the window exactly, and the entries past the last complete run
+    //    do not know their cells)
+    const int used = *s_overflow ? 0 : kTabFixed + *s_count;
+    for (int e = kTabFixed + tid; e < used; e += kTabThreads) {
+        const unsigned at = (unsigned)ttab[e];
+        ttab[e] = __ldg(a.pack + at);
+    }
+}
+
+// BATCH = false: one window for the whole slice; units of 32 particles are dealt over all warps of the grid.
+// BATCH = true:  CTAs take batches of a.batch consecutive particles from a counter (a.build_info[2]), place the
+//                plan's fixed-size window for each (tab_batch_window) and rebuild K and T; the batch's units are dealt
+//                over the CTA's warps.  A build is w h cell classifications for a.batch x beams evaluations (config 5:
+//                63 K cells for 1.46 M evaluations).
+// WIDE:          8-bit class tile + segment bases (tab_eval), for windows whose 16-bit tile does not fit.
+template <bool INTERP, bool COUNT, bool BATCH, bool WIDE>
 __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ TabPlan s_plan;
     __shared__ TabCold s_cold;
     __shared__ int s_count, s_overflow;
+    __shared__ long long s_batch;
+    __shared__ int s_batch_ok;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = a.num_beams;
@@ -450,14 +834,19 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     swacc[tid] = 0;
     __syncthreads();
     const TabPlan& pl = s_plan;
-    const bool table = pl.ok != 0;
+    const bool table = pl.ok != 0 && (pl.batch != 0) == BATCH && (pl.wide != 0) == WIDE;
     const float cpm = a.grid.cells_per_meter;
     for (int i = tid; i < nb; i += kTabThreads) {
         const Beam b = a.beams[i];
         sbeams[i] = b;
         TabBeam f;
         const float rc = __fmul_rn(b.range, cpm);
-        f.ratio = (float)b.ratio; f.theta = b.theta;
+        // the table pass folds the beam angle into [-pi, pi] (the same direction): its SFU arguments then stay within
+        // +-(2 pi + 0.2) whatever the particle's heading (lidar angles run to 2 pi; kFastTrigErr is measured to 9.5)
+        const double thd = (double)b.theta;
+        f.ratio = (float)b.ratio;
+        f.theta = (float)(thd > 3.14159265358979323846 ? thd - 6.28318530717958647692
+                                                       : (thd < -3.14159265358979323846 ? thd + 6.28318530717958647692 : thd));
         f.rcx = (float)((double)rc * pl.inv_sx); f.rcy = (float)((double)rc * pl.inv_sy);
         // |2|px| - |py|| = sqrt5 rc |sin(angle to the octant boundary)| must exceed T3: angular band, in u8 units
         const double xq = (double)pl.t3 / (2.2360679 * (double)rc * (1.0 - 1e-6));
@@ -466,129 +855,52 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
         sfast[i] = f;
     }
 
-    // ---- K tile and score table of this window ------------------------------------------------------------------
     uint16_t* ktile = reinterpret_cast<uint16_t*>(smem + pl.off_k);
     unsigned long long* ttab = reinterpret_cast<unsigned long long*>(smem + pl.off_t);
     const unsigned k0 = (unsigned)__cvta_generic_to_shared(ttab) >> 3;
-    if (table) {
-        const int W = a.grid.width, H = a.grid.height, gp = a.grid.pitch;
-        const int8_t* raw = a.grid.cells;
-        auto rawc = [&](int gxc, int gyc) -> int {
-            return ((unsigned)gxc < (unsigned)W && (unsigned)gyc < (unsigned)H) ? (int)__ldg(raw + (size_t)gyc * gp + gxc) : 0;
-        };
-        for (int i = tid; i < kTabFixed; i += kTabThreads)
-            ttab[i] = i >= 2 ? 0x0101010101010101ull * (unsigned long long)(2 * (i - 1)) : 0ull;
-        const int total = pl.w * pl.h;
-        for (int i = tid; i < total; i += kTabThreads) {
-            const int ty = i / pl.w, tx = i - ty * pl.w;
-            const int gxc = pl.x0 + tx, gyc = pl.y0 + ty;
-            unsigned K;
-            if (gxc <= -4 || gyc <= -4 || gxc >= W + 3 || gyc >= H + 3) {
-                K = 0u;        // the reference's (truncated) endpoint cell and its neighbours are all outside the grid
-            } else if (gxc < 0 || gyc < 0) {
-                K = 1u;        // truncation toward zero differs from the floor here: never certified (tab_eval, EDGE 2)
-            } else if (a.lf_cells) {
-                // likelihood field: every class is uniform (the ray scores the field value of its endpoint cell);
-                // class 0 = the field is 0 on the cell and on its eight neighbours (certain whatever the exact cell)
-                auto lfc = [&](int cx, int cy) -> int {
-                    return ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) ? (int)__ldg(a.lf_cells + (size_t)cy * gp + cx) : 0;
-                };
-                const int u = lfc(gxc, gyc);
-                if (u > 0) K = 1u + (unsigned)u;
-                else {
-                    int mx = 0;
-                    for (int dy = -1; dy <= 1; ++dy)
-                        for (int dx = -1; dx <= 1; ++dx) mx = max(mx, lfc(gxc + dx, gyc + dy));
-                    K = mx > 0 ? 1u : 0u;
-                }
-            } else {
-                int f;
-                if (gxc < W && gyc < H) {
-                    f = (int)__ldg(a.fast_cells + (size_t)gyc * gp + gxc);
-                } else {        // beyond the high edges: the cell reads 0; is anything positive within two cells?
-                    bool any = false;
-                    for (int dy = -2; dy <= 2; ++dy)
-                        for (int dx = -2; dx <= 2; ++dx) any = any || rawc(gxc + dx, gyc + dy) > 0;
-                    f = any ? 0 : -1;
-                }
-                if (f < 0) K = 0u;
-                else if (f > 0) K = 1u + (unsigned)f;
-                else {
-                    // sector s steps (ux, uy): 0 (+1,0) 1 (+1,+1) 2 (0,+1) 3 (-1,+1) 4 (-1,0) 5 (-1,-1) 6 (0,-1) 7 (+1,-1)
-                    int n[8];
-                    n[0] = rawc(gxc + 1, gyc);     n[1] = rawc(gxc + 1, gyc + 1); n[2] = rawc(gxc, gyc + 1);
-                    n[3] = rawc(gxc - 1, gyc + 1); n[4] = rawc(gxc - 1, gyc);     n[5] = rawc(gxc - 1, gyc - 1);
-                    n[6] = rawc(gxc, gyc - 1);     n[7] = rawc(gxc + 1, gyc - 1);
-                    int mx = 0;
-#pragma unroll
-                    for (int sct = 0; sct < 8; ++sct) mx = max(mx, n[sct]);
-                    if (mx <= 0) K = 1u;
-                    else {
-                        const int e = kTabFixed + atomicAdd(&s_count, 1);
-                        if (e < pl.cap_entries) {
-                            unsigned long long pack = 0ull;
-#pragma unroll
-                            for (int sct = 0; sct < 8; ++sct) {
-                                const int o1 = n[(sct + 4) & 7], o2 = n[sct];      // sensor_model.cpp:48-57
-                                const int v = o1 > 0 ? o1 : max(o2, 0);
-                                pack |= (unsigned long long)v << (8 * sct);
-                            }
-                            ttab[e] = pack;
-                            K = (unsigned)e;
-                        } else {
-                            K = 1u;
-                            s_overflow = 1;
-                        }
-                    }
-                }
-            }
-            ktile[ty * pl.pitch_k + tx] = (uint16_t)(K + k0);
-        }
-    }
-    __syncthreads();
-    const bool degrade = !table || s_overflow != 0;
-    if (tid == 0) {
-        if (table) {
-            atomicMax(a.build_info + 0, kTabFixed + s_count);
-            if (s_overflow) atomicAdd(a.build_info + 1, 1);
-        }
-        s_cold.grid = a.grid; s_cold.sbeams = sbeams; s_cold.deferred = 0ull; s_cold.gathers = 0ull;
-        s_cold.lf = a.lf_cells ? 1 : 0;
-        if (a.lf_cells) s_cold.grid.cells = a.lf_cells;         // the exact path reads the field outside the window
-        s_cold.ktile = degrade ? nullptr : ktile;
-        s_cold.x0 = pl.x0; s_cold.y0 = pl.y0; s_cold.w = pl.w; s_cold.h = pl.h; s_cold.pitch_k = pl.pitch_k;
-        s_cold.k0 = k0;
-    }
-    __syncthreads();
 
     TabConst tc;
     tc.mul_x = pl.mul_x; tc.mul_y = pl.mul_y; tc.frac_thr = pl.frac_thr;
-    tc.pitch2 = (unsigned)pl.pitch_k * 2u;
+    tc.pitch2 = (unsigned)pl.pitch_k * (WIDE ? 1u : 2u);
     const unsigned sk = (unsigned)__cvta_generic_to_shared(ktile);
-    tc.kbase = sk - pl.bias_y * tc.pitch2 - pl.bias_x * 2u;
+    tc.kbase = sk - pl.bias_y * tc.pitch2 - pl.bias_x * (WIDE ? 1u : 2u);
+    tc.sdelta = pl.bias_x + (unsigned)pl.seg_off - (pl.bias_x >> 6) * 2u;
     tc.k0 = k0;
     tc.k129 = k0 + (unsigned)kTabFixed;
     tc.lf = a.lf_cells ? 1u : 0u;
+    // (an IMAD takes one uniform-register operand: keep the row pitch in a vector register, or every cell address of
+    // the loop pays a move)
+    {
+        unsigned z;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(z));
+        tc.pitch2 += z >> 5;            // + 0, but no longer provably warp-uniform
+    }
     const double gx = (double)a.grid.origin_x, gy = (double)a.grid.origin_y, cpm_d = (double)cpm;
     const int nwords = (nb + 31) / 32;
     uint16_t* q = squeue + warp * kTabQueue;
     int* wacc = swacc + warp * 32;
     int gathers = 0;
 
-    // work unit = 32 consecutive particles = one warp; units are dealt round-robin over CTAs, then over warps
-    const long long nunits = (a.hi - a.lo + 31) / 32;
-    for (long long unit = (long long)blockIdx.x + (long long)gridDim.x * warp; unit < nunits;
-         unit += (long long)gridDim.x * kTabWarps) {
-        const long long p = a.lo + unit * 32 + lane;
-        const bool live = p < a.hi;
+    // One unit = the 32 particles [p0, p0 + 32) below p_end, beams of the 32-beam words [w0, w1); add_mode: the unit is
+    // one of several beam ranges of the same particles, whose partial sums add up in score2 (zeroed by the host).
+    // (particles are addressed relative to the slice, in 32 bits: the loop is short of registers)
+    auto score_unit = [&](unsigned i0, unsigned i_end, int w0, int w1, bool add_mode, bool degrade) {
+        const bool live = i0 + lane < i_end;
         float xa = 0.f, ya = 0.f, tha = 0.f, xb = 0.f, yb = 0.f, thb = 0.f;
-        if (live) { xa = a.x[p]; ya = a.y[p]; tha = a.th[p]; xb = a.px[p]; yb = a.py[p]; thb = a.pth[p]; }
+        if (live) {
+            const long long p = a.lo + (long long)(i0 + lane);
+            xa = a.x[p]; ya = a.y[p]; tha = a.th[p]; xb = a.px[p]; yb = a.py[p]; thb = a.pth[p];
+        }
         TabBase fb = make_tab_base<INTERP>(xa, ya, tha, xb, yb, thb, gx, gy, cpm_d, pl);
+        {
+            const unsigned bad = __ballot_sync(0xffffffffu, live && !fb.ok);
+            if (bad && lane == 0 && w0 == 0) atomicAdd(a.build_info + 4, __popc(bad));
+        }
         fb.ok = fb.ok && live && !degrade;
         const int edge = __reduce_max_sync(0xffffffffu, fb.ok ? fb.edge : 0);
         int acc = 0, qn = 0;
         unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;      // uncertain-beam bits of four consecutive 32-beam words
-        for (int w = 0; w < nwords; ++w) {
+        for (int w = w0; w < w1; ++w) {
             uint32_t m = 0;
             const int kend = min(32, nb - w * 32);
             if (fb.ok) {
@@ -600,7 +912,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
 MCL_UNROLL(MCL_TAB_UNROLL)
                     for (int k = 0; k < kend; ++k) {
                         int add;
-                        const bool certain = tab_eval<INTERP, COUNT, EDGE>(fb, bw[k], dw[k], tc, pl, add, gathers);
+                        const bool certain = tab_eval<INTERP, COUNT, EDGE, WIDE>(fb, bw[k], dw[k], tc, pl, add, gathers);
                         acc += add;
                         m |= certain ? 0u : bit;
                         bit += bit;
@@ -612,12 +924,12 @@ MCL_UNROLL(MCL_TAB_UNROLL)
             } else if (live) {
                 m = kend == 32 ? 0xffffffffu : ((1u << kend) - 1u);
             }
-            const int part = w & 3;
+            const int part = (w - w0) & 3;
             if (part == 0) m0 = m; else if (part == 1) m1 = m; else if (part == 2) m2 = m; else m3 = m;
-            if (part == 3 || w == nwords - 1) {
+            if (part == 3 || w == w1 - 1) {
                 // hand the uncertain beams of these (up to) four words to the exact path
                 if (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u))
-                    qn = tab_defer_words<INTERP, COUNT>(m0, m1, m2, m3, w & ~3, qn, xa, ya, tha, xb, yb, thb, &s_cold, q, wacc);
+                    qn = tab_defer_words<INTERP, COUNT>(m0, m1, m2, m3, w - part, qn, xa, ya, tha, xb, yb, thb, &s_cold, q, wacc);
                 m0 = m1 = m2 = m3 = 0u;
             }
         }
@@ -627,13 +939,93 @@ MCL_UNROLL(MCL_TAB_UNROLL)
         acc += wacc[lane];
         wacc[lane] = 0;
         if (live) {
-            if (a.num_peers > 0) {
-                for (int r = 0; r < a.num_peers; ++r) a.peer_score[r][p] = acc;     // final: to every rank
-            } else {
-                a.score2[p] = acc;
-            }
+            const long long p = a.lo + (long long)(i0 + lane);
+            if (add_mode) atomicAdd(a.score2 + p, acc);
+            else a.score2[p] = acc;
         }
         __syncwarp();
+    };
+
+    if (tid == 0) {
+        s_cold.grid = a.grid; s_cold.sbeams = sbeams; s_cold.deferred = 0ull; s_cold.gathers = 0ull;
+        s_cold.lf = a.lf_cells ? 1 : 0;
+        if (a.lf_cells) s_cold.grid.cells = a.lf_cells;         // the exact path reads the field outside the window
+        s_cold.ktile = nullptr;
+        s_cold.w = pl.w; s_cold.h = pl.h; s_cold.pitch_k = pl.pitch_k;
+        s_cold.k0 = k0;
+        s_cold.wide = WIDE ? 1 : 0;
+    }
+
+    if (!BATCH) {
+        // ---- K tile and score table of the slice's window --------------------------------------------------------
+        if (table) tab_build_window<WIDE>(pl, a, ktile, ttab, k0, &s_count, &s_overflow);
+        __syncthreads();
+        const bool degrade = !table || s_overflow != 0;
+        if (tid == 0) {
+            if (table) {
+                atomicMax(a.build_info + 0, kTabFixed + s_count);
+                if (s_overflow) atomicAdd(a.build_info + 1, 1);
+            }
+            s_cold.ktile = degrade ? nullptr : ktile;
+            s_cold.x0 = pl.x0; s_cold.y0 = pl.y0;
+        }
+        __syncthreads();
+
+        // work unit = 32 consecutive particles = one warp; units are dealt round-robin over CTAs, then over warps.  The
+        // last, partial round of units would leave most warps idle while a few finish a whole unit (with 2 M particles
+        // per GPU that is 6 % of the kernel): those units are split by beams into up to S parts, one per otherwise idle
+        // warp, which add their partial sums to score2 (zeroed by the host for exactly those particles:
+        // table_tail_split).
+        const long long nunits = (a.hi - a.lo + 31) / 32;
+        long long whole_units, items;
+        int split;
+        table_tail_split(nunits, (long long)gridDim.x * kTabWarps, nwords, whole_units, split, items);
+        for (long long item = (long long)blockIdx.x + (long long)gridDim.x * warp; item < items;
+             item += (long long)gridDim.x * kTabWarps) {
+            long long unit = item;
+            int w0 = 0, w1 = nwords;
+            if (item >= whole_units) {
+                const long long sub = item - whole_units;
+                unit = whole_units + sub / split;
+                const int part = (int)(sub - (sub / split) * split);
+                w0 = part * nwords / split; w1 = (part + 1) * nwords / split;
+            }
+            score_unit((unsigned)(unit * 32), (unsigned)(a.hi - a.lo), w0, w1, item >= whole_units, degrade);
+        }
+    } else {
+        const long long nbatches = (a.hi - a.lo + a.batch - 1) / a.batch;
+        int max_count = 0, overflows = 0;
+        for (;;) {
+            __syncthreads();                    // everyone is done with the previous batch's window (and s_batch)
+            if (tid == 0) {
+                const long long b = (long long)atomicAdd(a.build_info + 2, 1);
+                s_batch = b;
+                s_count = 0; s_overflow = 0;
+                s_batch_ok = (table && b < nbatches && tab_batch_window(s_plan, a.bboxes[b], a.grid)) ? 1 : 0;
+            }
+            __syncthreads();
+            const long long b = s_batch;
+            if (b >= nbatches) break;
+            const bool have = s_batch_ok != 0;
+            if (have) tab_build_window<WIDE>(pl, a, ktile, ttab, k0, &s_count, &s_overflow);
+            __syncthreads();
+            const bool degrade = !have || s_overflow != 0;
+            if (tid == 0) {
+                if (!have) atomicAdd(a.build_info + 3, 1);
+                if (have) { max_count = max(max_count, kTabFixed + s_count); overflows += s_overflow; }
+                s_cold.ktile = degrade ? nullptr : ktile;
+                s_cold.x0 = pl.x0; s_cold.y0 = pl.y0;
+            }
+            __syncthreads();
+            const unsigned first = (unsigned)(b * a.batch);
+            const unsigned last = (unsigned)((b + 1) * a.batch < a.hi - a.lo ? (b + 1) * a.batch : a.hi - a.lo);
+            for (unsigned i0 = first + warp * 32; i0 < last; i0 += kTabThreads)
+                score_unit(i0, last, 0, nwords, false, degrade);
+        }
+        if (tid == 0 && table) {
+            atomicMax(a.build_info + 0, max_count);
+            if (overflows) atomicAdd(a.build_info + 1, overflows);
+        }
     }
     __syncthreads();
     if (COUNT) {

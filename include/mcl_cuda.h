@@ -85,13 +85,15 @@ typedef struct {
     float   ms_resample, ms_action, ms_score, ms_normalize, ms_estimate, ms_total;  /* last mcl_update, CUDA events */
     int     lanes_per_particle;   /* mapping actually used by the last scoring pass */
     int     map_tile_used;        /* 1 = L2/global gathers, 2 = one shared-memory tile, 3 = one tile per batch of 1024 particles,
-                                     4 = one shared-memory class tile + score table (score-table pass) */
+                                     4 = one shared-memory class tile + score table (score-table pass), 5 = the same
+                                     rebuilt per batch of 4096 (or 1024) particles (dense global-localisation clouds) */
     int     kernel_launches;      /* kernels launched by the last mcl_update */
     int     collectives;          /* slice exchanges enqueued by the last mcl_update (0 on one GPU) */
     int     peer_push;            /* 1: pose slices travel by copy-engine peer writes (CUDA IPC), else NCCL all-gather */
     int     sensor_path;          /* path of the last scoring pass: 3 = score-table pass, 2 = certified float pass + exact
                                      re-evaluation (two kernels), 1 = exact only */
-    int     reserved[2];
+    int     table_variant;        /* score-table pass: 0 / 1 = one window, 16- / 8-bit classes; 2 / 3 = one window per batch */
+    int     reserved[1];
     int64_t deferred_evals;       /* evaluations of the last scoring pass the float pass could not certify (re-done exactly) */
     double  fast_eps;             /* error bound (cells) the certification used, 0 when the exact path ran alone */
 } mcl_stats;

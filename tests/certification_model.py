@@ -141,7 +141,9 @@ def fast_pass(grid, plan, particle, ranges, thetas, ratios, min_range, fast_cell
     sx = fma32(dsx * one, rho, sxb * one) if interp else sxb * one
     sy = fma32(dsy * one, rho, syb * one) if interp else syb * one
     thr = fma32(dth * one, rho, th0 * one) if interp else th0 * one
-    a = (thr - th).astype(F)
+    thd = th.astype(np.float64)                                # score_table_kernel folds the beam angle into [-pi, pi]
+    thf = np.where(thd > np.pi, thd - 2 * np.pi, np.where(thd < -np.pi, thd + 2 * np.pi, thd)).astype(F)
+    a = (thr - thf).astype(F)
     err = rng.uniform(-1.3e-6, 1.3e-6, (2, n))
     s = (np.sin(a.astype(np.float64)) + err[0]).astype(F)
     c = (np.cos(a.astype(np.float64)) + err[1]).astype(F)
@@ -245,7 +247,7 @@ class TabPlan:
         ce = cm_ + rc_max
         e_ref = cpm * U * xm + 2 * U * ce + 2 * U * rc_max + rc_max * (20 * U + 1.2e-7) + 1e-9
         e_apx = 6 * U * max(tw, th_) + (1 + 2 * rho_max) * U * shift + 3 * U * rc_max + \
-            rc_max * ((3.14159265358979 * (3 * rho_max + 1) + 9.5) * U + TRIG_ERR)
+            rc_max * ((3.14159265358979 * (3 * rho_max + 2) + 9.5) * U + TRIG_ERR)
         self.eps = eps = 1.25 * (e_ref + e_apx) + 1e-6
         self.kappa = kappa = eps + 1e-5
         if kappa > 1.0 / 16.0:
@@ -262,7 +264,7 @@ class TabPlan:
         self.rho_lo, self.rho_hi, self.rho_abs = F(rho_lo), F(rho_hi), F(rho_max * (1 + 1e-6))
         self.max_shift, self.coord_hi = F(shift), F(cm_ - 1.0)
         self.reach = F(rc_max * (1 + 1e-6) + 4.0)
-        self.ang_room = F(9.5) - F(max_abs_theta)
+        self.ang_room = F(9.5) - min(F(max_abs_theta), F(3.1415928))     # the beam angles are folded into [-pi, pi]
         self.ulo_x, self.uhi_x = F(ux0 + 1.5 + float(self.reach)), F(ux1 + 1 - 1.5 - float(self.reach))
         self.ulo_y, self.uhi_y = F(uy0 + 1.5 + float(self.reach)), F(uy1 + 1 - 1.5 - float(self.reach))
         self.hmin_x, self.hmin_y = self.bias_x - x0, self.bias_y - y0
@@ -348,7 +350,9 @@ def table_pass(grid, plan, K, T, particle, ranges, thetas, ratios, min_range, rn
     sxm = fma32(dsxn * onev, rho, sxn * onev) if interp else sxn * onev
     sym = fma32(dsyn * onev, rho, syn * onev) if interp else syn * onev
     thr = fma32(dth * onev, rho, th0 * onev) if interp else th0 * onev
-    a = (thr - th).astype(F)
+    thd = th.astype(np.float64)                                # score_table_kernel folds the beam angle into [-pi, pi]
+    thf = np.where(thd > np.pi, thd - 2 * np.pi, np.where(thd < -np.pi, thd + 2 * np.pi, thd)).astype(F)
+    a = (thr - thf).astype(F)
     err = rng.uniform(-1.3e-6, 1.3e-6, (2, n))
     s = (np.sin(a.astype(np.float64)) + err[0]).astype(F)
     c = (np.cos(a.astype(np.float64)) + err[1]).astype(F)

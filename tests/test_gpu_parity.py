@@ -66,7 +66,7 @@ def test_sensor_golden(name, variant, lanes, tile, real_map, sensor_golden):
     assert np.array_equal(s, want)                                        # engine == oracle, bit for bit
     st = e.stats()
     assert st["evals"] == evals and st["gathers"] == gathers              # algorithmic work agrees with the oracle
-    assert st["map_tile_used"] == (2 if tile == 2 else st["map_tile_used"])
+    assert st["map_tile_used"] in ((2, 4) if tile == 2 else (st["map_tile_used"],))    # 4: the score-table pass's own tile
     e.close()
 
 
@@ -647,52 +647,81 @@ def test_init_uniform_is_stratified_and_ordered():
     assert span.max() < 0.1 * ext
 
 
-@pytest.mark.parametrize("side,n", [(2000, 1_500_000), (1000, 700_001)])
-def test_batch_windows_equal_exact_and_oracle(side, n):
+@pytest.mark.parametrize("side,n,dense,max_range,stride",
+                         [(2000, 1_500_000, False, 8.0, 97), (1000, 700_001, False, 8.0, 97), (1000, 4_000_000, True, 5.0, 97),
+                          (600, 2_000_003, True, 5.0, 97), (1000, 16_000_000, True, 8.0, 397)])
+def test_batch_windows_equal_exact_and_oracle(side, n, dense, max_range, stride):
     """A uniformly initialised cloud over a map far larger than one shared-memory tile is scored behind per-batch
-    windows (stats: map_tile_used == 3).  Scores must equal the exact-only path's, the L2-gather path's, and the
-    oracle's on a sub-sample, before and after a full update."""
+    windows (stats: map_tile_used == 5 for the score-table pass, whose CTAs rebuild their class tile and score table
+    per batch, 3 for the older kernel families; the score-table pass needs a DENSE cloud -- config 5 has four particles
+    per cell -- because its class tile and score table must hold the window of a whole batch of 1024 or 4096
+    consecutive particles, and leaves sparse clouds to the older kernels).  The dense cases cover 16-bit class tiles
+    (5 m rays) and 8-bit ones (8 m rays).  Scores must equal the exact-only path's, the L2-gather path's, and the
+    oracle's on a sub-sample, before and after two full updates."""
     grid = synth.make_map(side, seed=side + 7)
     rng = np.random.default_rng(n)
     truth = synth.find_free_pose(grid, rng)
-    r, th, t = synth.make_scan(grid, truth, seed=3)
+    r, th, t = synth.make_scan(grid, truth, seed=3, max_range=max_range)
     engines = {name: make_engine(n, grid, **kw) for name, kw in
-               {"two_pass": {}, "exact": {"sensor_path": 1}, "l2": {"map_tile": 1}}.items()}
+               {"table": {}, "two_pass": {"sensor_path": 2}, "exact": {"sensor_path": 1}, "l2": {"map_tile": 1}}.items()}
     scores = {}
     for name, e in engines.items():
         e.init_uniform(utime=int(t[0]) - 100_000, seed=11)
         scores[name] = e.score(r, th, t)
     st = {k: e.stats() for k, e in engines.items()}
+    assert (st["table"]["map_tile_used"], st["table"]["sensor_path"]) == ((5, 3) if dense else (3, 2)), st["table"]
+    assert st["table"]["deferred_evals"] < 0.1 * st["table"]["evals"]
+    assert np.array_equal(scores["table"], scores["two_pass"])
     assert st["two_pass"]["map_tile_used"] == 3 and st["two_pass"]["sensor_path"] == 2
     assert st["exact"]["map_tile_used"] == 3 and st["exact"]["sensor_path"] == 1
     assert st["l2"]["map_tile_used"] == 1
     assert np.array_equal(scores["two_pass"], scores["exact"]) and np.array_equal(scores["two_pass"], scores["l2"])
-    sub = engines["two_pass"].export_particles(stride=97)
+    sub = engines["two_pass"].export_particles(stride=stride)
     want, _, _ = port.likelihood(port_grid(grid), sub, r, th, t)
-    assert np.array_equal(scores["two_pass"][::97], want)
+    assert np.array_equal(scores["two_pass"][::stride], want)
+    if dense:
+        assert st["table"]["table_variant"] == (3 if max_range > 6 else 2)
     # one full update (resample -> action -> score ...) keeps the order, hence the mode, and the paths agree
     am = engine.ActionModel()
     am.update(0.0, 0.0, 0.0, int(t[0]) - 100_000)
     assert am.update(0.02, 0.01, 0.01, int(t[-1]))
     clouds = {}
-    for name in ("two_pass", "exact"):
+    for name in ("table", "two_pass", "exact"):
         e = engines[name]
         e.update(am, int(t[-1]), r, th, t, 0.37 / n)
+        e.update(am, int(t[-1]) + 100_000, r, th, t + 100_000, 0.61 / n)
         clouds[name] = e.export_particles()
-        assert e.stats()["map_tile_used"] == 3
-    for k in ("pose", "parent_pose"):
-        for f in ("x", "y", "theta"):
-            assert np.array_equal(clouds["two_pass"][k][f], clouds["exact"][k][f])
-    assert np.array_equal(clouds["two_pass"]["weight"], clouds["exact"]["weight"])
+        assert e.stats()["map_tile_used"] in ((5,) if name == "table" and dense else (1, 3))
+    for name in ("table", "two_pass"):
+        for k in ("pose", "parent_pose"):
+            for f in ("x", "y", "theta"):
+                assert np.array_equal(clouds[name][k][f], clouds["exact"][k][f])
+        assert np.array_equal(clouds[name]["weight"], clouds["exact"]["weight"])
+    if dense:
+        # the cloud collapses (here: a tight cloud is imported): the score-table pass goes back to ONE window, at the
+        # latest on the pass after the one whose plan saw that the cloud fits one; scores stay the oracle's
+        tight = synth.make_particles(n, truth, seed=5, parent_utime=int(t[0]) - 100_000, pose_utime=int(t[-1]))
+        want, _, _ = port.likelihood(port_grid(grid), tight[::997], r, th, t)
+        e = engines["table"]
+        e.import_particles(tight)
+        for _ in range(3):
+            assert np.array_equal(e.score(r, th, t)[::997], want)
+        assert e.stats()["map_tile_used"] == 4 and e.stats()["sensor_path"] == 3
+        # ... and spreads out again
+        e.init_uniform(utime=int(t[0]) - 100_000, seed=11)
+        assert np.array_equal(e.score(r, th, t), scores["exact"]) and e.stats()["map_tile_used"] == 5
     for e in engines.values():
         e.close()
 
 
-def test_config5_shape_full_size():
-    """BASELINE configs[4] at one GPU's share of its shape: 8 M uniformly initialised particles on the 4000 x 4000 grid
-    (what each of eight GPUs holds of the 64 M), scored behind per-batch windows.  A sub-sample of the scores (every
-    10 007th particle) equals the ORACLE's, before and after a full update; the exact-only path agrees everywhere."""
-    n, side = 8_000_000, 4000
+@pytest.mark.parametrize("n,paths,stride", [(8_000_000, (0, 2, 1), 10_007), (64_000_000, (0, 1), 100_003)])
+def test_config5_shape_full_size(n, paths, stride):
+    """BASELINE configs[4] on the 4000 x 4000 grid, uniformly initialised particles scored behind per-batch windows:
+    8 M particles (one GPU's share of the count, spread over the whole map: half a particle per cell, too sparse for
+    the score-table pass, so path 0 resolves to the certified float pass + exact pass) and all 64 M (four per cell: path 0
+    is the score-table pass with one window per batch).  A sub-sample of the scores equals the ORACLE's, before and
+    after a full update; the exact pass alone (path 1) agrees everywhere."""
+    side = 4000
     grid = synth.make_map(side, seed=synth.MAP_SEED + 5)
     rng = np.random.default_rng(55)
     truth = synth.find_free_pose(grid, rng)
@@ -701,29 +730,33 @@ def test_config5_shape_full_size():
     am = engine.ActionModel()
     am.update(0.0, 0.0, 0.0, int(t[0]) - 100_000)
     assert am.update(0.02, 0.01, 0.01, int(t[-1]))
+    dense = n >= 32_000_000
     out = {}
-    for path in (0, 1):
+    for path in paths:
         e = make_engine(n, grid, sensor_path=path)
         e.init_uniform(utime=int(t[0]) - 100_000, seed=11)
         s0 = e.score(r, th, t)
         st = e.stats()
-        assert st["map_tile_used"] == 3 and st["sensor_path"] == (2 if path == 0 else 1), st
-        sub0 = e.export_particles(stride=10_007)
+        want_tile = 5 if (path == 0 and dense) else 3
+        assert st["map_tile_used"] == want_tile and st["sensor_path"] == {0: 3 if dense else 2, 2: 2, 1: 1}[path], st
+        sub0 = e.export_particles(stride=stride)
         est = e.update(am, int(t[-1]), r, th, t, 0.37 / n)
-        assert e.stats()["map_tile_used"] == 3
+        assert e.stats()["map_tile_used"] == want_tile
         s1 = e.score(r, th, t)
-        sub1 = e.export_particles(stride=10_007)
+        sub1 = e.export_particles(stride=stride)
         out[path] = (s0, sub0, s1, sub1, (est.x, est.y, est.theta), e.stats()["weight_sum"])
         e.close()
-    a, b = out[0], out[1]
+    a = out[0]
     want0, _, _ = port.likelihood(pg, a[1], r, th, t)
     want1, _, _ = port.likelihood(pg, a[3], r, th, t)
-    assert np.array_equal(a[0][::10_007], want0) and np.array_equal(a[2][::10_007], want1)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[4] == b[4] and a[5] == b[5]
-    for k in ("pose", "parent_pose"):
-        for f in ("x", "y", "theta"):
-            assert np.array_equal(a[3][k][f], b[3][k][f])
-    assert np.array_equal(a[3]["weight"], b[3]["weight"])
+    assert np.array_equal(a[0][::stride], want0) and np.array_equal(a[2][::stride], want1)
+    for path in paths[1:]:
+        b = out[path]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[4] == b[4] and a[5] == b[5]
+        for k in ("pose", "parent_pose"):
+            for f in ("x", "y", "theta"):
+                assert np.array_equal(a[3][k][f], b[3][k][f])
+        assert np.array_equal(a[3]["weight"], b[3]["weight"])
 
 
 # ------------------------------------------------------------------------------- map update on the device mirror
@@ -787,7 +820,8 @@ def test_map_update_edge_cases(real_map):
 @pytest.mark.parametrize("placement", ["interior", "bench"])
 def test_config4_full_size_two_pass_equals_exact(placement):
     """BASELINE configs[3] at full size (16 M particles x 360 beams, 2000 x 2000 grid): the default sensor path (the
-    score-table pass where the window fits: bench.py's own workload; else the two-pass path), the two-pass path and the
+    score-table pass: with 16-bit classes on bench.py's own workload, whose window the map's corner clips, with 8-bit
+    classes for a robot in the map's interior, whose 8 m rays need a 355 x 355 window), the two-pass path and the
     literal restatement give the same 16 M scores, hence the same weight sum, estimate and resampled cloud -- and a
     sub-sample of those scores (every 10 007th particle) equals the ORACLE's, so the three cannot be wrong together."""
     n, side = synth.CONFIGS["config4"]
@@ -809,7 +843,8 @@ def test_config4_full_size_two_pass_equals_exact(placement):
         e.init_at_pose(*truth, utime=int(t[0]) - 100_000, seed=21)
         est = e.update(am, int(t[-1]), r, th, t, 0.8401877171547095 / n)
         st = e.stats()
-        assert st["sensor_path"] == {0: (3 if placement == "bench" else 2), 2: 2, 1: 1}[path]
+        assert st["sensor_path"] == {0: 3, 2: 2, 1: 1}[path]
+        assert path != 0 or (st["map_tile_used"], st["table_variant"]) == (4, 0 if placement == "bench" else 1), st
         scores = e.score(r, th, t)                   # same cloud, same scan: the stage alone, all 16 M scores
         sub = e.export_particles(stride=10_007)
         am2 = engine.ActionModel()
