@@ -727,11 +727,11 @@ __global__ void derive_class_map_kernel(const TabArgs a, uint8_t* cls, unsigned 
 // Builds the class tile K and the score table T of the window in pl (see the head of this file) from the class map.
 // All threads of the CTA; synchronises inside; the caller synchronises after it.  s_count: entries of T in use beyond
 // the fixed ones, s_overflow: T is full (the caller then scores the window's particles exactly).
-//   A  copy the window's classes (many independent loads in flight);
-//   B  one warp per 64-cell row segment numbers the cells that get an entry (ballots) and reserves the segment's run of
-//      entries; the entry remembers its cell;   WIDE: the tile keeps 129 + the number within the segment, the run's
-//      base goes to the row's segment bases; else the tile keeps the entry's index;
-//   C  the entries fetch their eight scores from the class map's pack array (independent loads again).
+//   One warp per row, 64-cell segment by segment (four segments' loads in flight): the lanes fetch the classes of
+//   their two cells, ballots number the cells that get an entry and lane 0 reserves the segment's run of entries; an
+//   entry remembers its cell.  WIDE: the tile keeps 129 + the number within the segment and the run's base goes to
+//   the row's segment bases; else the tile keeps the entry's index.  Then the entries fetch their eight scores from
+//   the class map's pack array (independent loads).
 template <bool WIDE>
 __device__ __forceinline__ void tab_build_window(const TabPlan& pl, const TabArgs& a, uint16_t* ktile,
                                                  unsigned long long* ttab, unsigned k0, int* s_count, int* s_overflow)
@@ -740,61 +740,65 @@ __device__ __forceinline__ void tab_build_window(const TabPlan& pl, const TabArg
     uint8_t* k8 = reinterpret_cast<uint8_t*>(ktile);
     for (int i = tid; i < kTabFixed; i += kTabThreads)
         ttab[i] = i >= 2 ? 0x0101010101010101ull * (unsigned long long)(2 * (i - 1)) : 0ull;
-    // A
-    const uint8_t* src = a.cls + (size_t)(pl.y0 + kTabApron) * a.cpitch + (pl.x0 + kTabApron);
-    for (int ty = warp; ty < pl.h; ty += kTabWarps) {
-        const uint8_t* row = src + (size_t)ty * a.cpitch;
-        const bool row_in = pl.y0 + ty < a.grid.height + kTabApron;         // (a batch window wider than the grid + apron)
-#pragma unroll 4
-        for (int tx = lane; tx < pl.w; tx += 32) {
-            const unsigned c = (row_in && pl.x0 + tx < a.grid.width + kTabApron) ? (unsigned)__ldg(row + tx) : 0u;
-            if (WIDE) k8[ty * pl.pitch_k + tx] = (uint8_t)c;
-            else ktile[ty * pl.pitch_k + tx] = (uint16_t)(c == 255u ? 0xffffu : c + k0);
-        }
-    }
-    __syncthreads();
-    // B
-    const int seg0 = (int)(pl.bias_x >> 6);
-    const int items = pl.h * pl.nseg;
-    for (int it = warp; it < items; it += kTabWarps) {
-        const int ty = it / pl.nseg, sg = it - ty * pl.nseg;
-        const int tx_lo = max(0, (seg0 + sg) * 64 - (int)pl.bias_x), tx_hi = min(pl.w, (seg0 + sg + 1) * 64 - (int)pl.bias_x);
-        const int tx0 = tx_lo + lane, tx1 = tx_lo + 32 + lane;
-        const bool n0 = tx0 < tx_hi && (WIDE ? (unsigned)k8[ty * pl.pitch_k + tx0] == 255u : (unsigned)ktile[ty * pl.pitch_k + tx0] == 0xffffu);
-        const bool n1 = tx1 < tx_hi && (WIDE ? (unsigned)k8[ty * pl.pitch_k + tx1] == 255u : (unsigned)ktile[ty * pl.pitch_k + tx1] == 0xffffu);
-        const unsigned need0 = __ballot_sync(0xffffffffu, n0), need1 = __ballot_sync(0xffffffffu, n1);
-        const int c0 = __popc(need0), c = c0 + __popc(need1);
-        int first = 0;
-        if (c > 0) {
-            if (lane == 0) first = kTabFixed + atomicAdd(s_count, c);
-            first = __shfl_sync(0xffffffffu, first, 0);
-        }
-        const bool room = first + c <= pl.cap_entries;
-        if (c > 0 && !room && lane == 0) *s_overflow = 1;
-        if (WIDE && lane == 0)
-            *reinterpret_cast<uint16_t*>(k8 + ty * pl.pitch_k + pl.seg_off + 2 * sg) = (uint16_t)(k0 + (unsigned)first - (unsigned)kTabFixed);
-        const unsigned below = (1u << lane) - 1u;
-        if (n0 || n1) {
-            const int tx = n0 ? tx0 : tx1;
-            // (a lane with both of its cells numbered handles the second below)
-            int id = n0 ? __popc(need0 & below) : c0 + __popc(need1 & below);
-            for (int rep = 0; rep < 2; ++rep) {
-                const int txr = rep == 0 ? tx : tx1;
-                if (rep == 1) { if (!(n0 && n1)) break; id = c0 + __popc(need1 & below); }
-                if (room) {
-                    ttab[first + id] = (unsigned long long)((unsigned)(pl.y0 + ty + kTabApron) * (unsigned)a.cpitch + (unsigned)(pl.x0 + txr + kTabApron));
-                    if (WIDE) k8[ty * pl.pitch_k + txr] = (uint8_t)(kTabFixed + id);
-                    else ktile[ty * pl.pitch_k + txr] = (uint16_t)((unsigned)(first + id) + k0);
-                } else {
-                    if (WIDE) k8[ty * pl.pitch_k + txr] = 1u;
-                    else ktile[ty * pl.pitch_k + txr] = (uint16_t)(1u + k0);
+    const int w = pl.w, h = pl.h, pitch = pl.pitch_k, cap = pl.cap_entries, nseg = pl.nseg, seg_off = pl.seg_off;
+    const int x0 = pl.x0, y0 = pl.y0, cpitch = a.cpitch;
+    const int bx = (int)(pl.bias_x & 63u);                       // segment s starts at tile column 64 s - bx
+    const int wlim = min(w, a.grid.width + kTabApron - x0);      // (a batch window wider than the grid + apron)
+    const int hlim = a.grid.height + kTabApron - y0;
+    const uint8_t* src = a.cls + (size_t)(y0 + kTabApron) * cpitch + (x0 + kTabApron);
+    const unsigned below = (1u << lane) - 1u;
+    for (int ty = warp; ty < h; ty += kTabWarps) {
+        const uint8_t* row = src + (size_t)ty * cpitch;
+        const bool row_in = ty < hlim;
+        const unsigned at_row = (unsigned)(y0 + ty + kTabApron) * (unsigned)cpitch + (unsigned)(x0 + kTabApron);
+        for (int sg0 = 0; sg0 < nseg; sg0 += 4) {
+            unsigned c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int tx = (sg0 + (j >> 1)) * 64 - bx + (j & 1) * 32 + lane;
+                c[j] = (row_in && tx >= 0 && tx < wlim) ? (unsigned)__ldg(row + tx) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sg = sg0 + j;
+                if (sg >= nseg) break;
+                const int tx0 = sg * 64 - bx + lane, tx1 = tx0 + 32;
+                const bool n0 = c[2 * j] == 255u, n1 = c[2 * j + 1] == 255u;
+                const unsigned need0 = __ballot_sync(0xffffffffu, n0), need1 = __ballot_sync(0xffffffffu, n1);
+                const int c0 = __popc(need0), cnt = c0 + __popc(need1);
+                int first = 0;
+                bool room = true;
+                if (cnt > 0) {
+                    if (lane == 0) first = kTabFixed + atomicAdd(s_count, cnt);
+                    first = __shfl_sync(0xffffffffu, first, 0);
+                    room = first + cnt <= cap;
+                    if (!room && lane == 0) *s_overflow = 1;
+                }
+                if (WIDE && lane == 0)
+                    *reinterpret_cast<uint16_t*>(k8 + ty * pitch + seg_off + 2 * sg) = (uint16_t)(k0 + (unsigned)first - (unsigned)kTabFixed);
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int tx = hlf ? tx1 : tx0;
+                    if (tx < 0 || tx >= w) continue;
+                    unsigned K = c[2 * j + hlf];
+                    if (K == 255u) {
+                        const int id = hlf ? c0 + __popc(need1 & below) : __popc(need0 & below);
+                        if (room) {
+                            ttab[first + id] = (unsigned long long)(at_row + (unsigned)tx);
+                            K = WIDE ? (unsigned)(kTabFixed + id) : (unsigned)(first + id);
+                        } else {
+                            K = 1u;
+                        }
+                    }
+                    if (WIDE) k8[ty * pitch + tx] = (uint8_t)K;
+                    else ktile[ty * pitch + tx] = (uint16_t)(K + k0);
                 }
             }
         }
     }
     __syncthreads();
-    // C  (not after an overflow: the caller scores the window exactly, and the entries past the last complete run
-    //    do not know their cells)
+    // (not after an overflow: the caller scores the window exactly, and the entries past the last complete run do not
+    // know their cells)
     const int used = *s_overflow ? 0 : kTabFixed + *s_count;
     for (int e = kTabFixed + tid; e < used; e += kTabThreads) {
         const unsigned at = (unsigned)ttab[e];
