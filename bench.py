@@ -421,6 +421,12 @@ def roofline(st, gathers, local_n, grid, score_s, clock_info, gather_peak):
     fig = kernel_figures()
     kern = {3: "score_table_kernel", 2: "score_fast_kernel+score_deferred_kernel"}.get(st["sensor_path"], "score_kernel")
     f = fig.get(kern, {})
+    if st["sensor_path"] == 3:
+        # four variants of the kernel (one window / one per batch of particles, 16- / 8-bit classes), each with its capture
+        variant = {0: "one window, 16-bit classes", 1: "one window, 8-bit classes", 2: "window per batch, 16-bit classes",
+                   3: "window per batch, 8-bit classes"}[st["table_variant"]]
+        f = fig.get(f"score_table_kernel/v{st['table_variant']}", f)
+        kern = f"score_table_kernel<{variant}>"
     sm_mhz = clock_info.get("sm_mhz") or 1965.0
     sms = 148
     evals = st["evals"]

@@ -109,7 +109,7 @@ struct mcl_engine {
     int tab_blocked = 0;                // updates to keep off the table pass after an overflow
     int tab_variant = 0;                // kTabSingle16 .. kTabBatch8 (mcl_table.cuh): what the next pass launches
     int tab_excluded = 0;               // variants whose score table overflowed on this cloud
-    int tab_batch = kTabBatch;          // kTabBatch, or kTabBatchSmall for sparse clouds
+    int tab_batch = kTabBatch;          // kTabBatch = 4096, halved down to kTabBatchSmall = 1024 until the windows fit
     int4* tab_bboxes = nullptr;         // bounding box per batch
     size_t tab_bboxes_cap = 0;
     bool scan_finite = true;
@@ -652,7 +652,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
         if (hp.ok && h->tab_hint->build[1] * 50ll > (hp.batch ? hint_batches : 0)) {
             // the score table overflowed (the kernel scored those windows exactly): smaller batches, else another variant
             h->tab_ok = false;
-            if (hp.batch && h->tab_batch == kTabBatch) h->tab_batch = kTabBatchSmall;
+            if (hp.batch && h->tab_batch > kTabBatchSmall) h->tab_batch >>= 1;
             else h->tab_excluded |= 1 << hp.variant;
         } else if (hp.best >= 0 && hp.best != hp.variant) {
             // follow what the last plan saw: one window when the cloud fits one, 16-bit classes when they fit, ...
@@ -700,7 +700,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     if (rc) return rc;
     if (!h->tab_ok) {
         // no usable hint (first pass after an init / import, or the last plan did not allow the table): plan synchronously
-        for (int attempt = 0; attempt < 4; ++attempt) {
+        for (int attempt = 0; attempt < 6; ++attempt) {
             CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             h->tab_hint_pending = false;
@@ -709,7 +709,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
             debug_plan("plan", hp);
             if (h->tab_ok || hp.reason != 3) break;                            // (3: the window does not fit)
             if (hp.best >= 0) h->tab_variant = hp.best;                        // another variant is applicable
-            else if (allow_batch && h->tab_batch == kTabBatch) h->tab_batch = kTabBatchSmall;     // a sparse cloud: smaller batches
+            else if (allow_batch && h->tab_batch > kTabBatchSmall) h->tab_batch >>= 1;     // 4096 -> 2048 -> 1024: smaller windows
             else break;
             rc = plan();
             if (rc) return rc;

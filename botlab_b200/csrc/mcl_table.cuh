@@ -53,7 +53,7 @@ constexpr int kTabQueue = 192;               // per-warp queue of deferred (lane
 constexpr int kTabFixed = 129;               // T entries 0..128: the uniform classes
 constexpr int kTabMaxBeams = 2047;           // queue entries are (lane << 11) | beam
 constexpr int kTabBatch = 4096;              // batch mode: consecutive particles that share one window (4 serpentine blocks
-constexpr int kTabBatchSmall = 1024;         // of mcl_init_uniform), or 1024 when the cloud is too sparse for that to fit
+constexpr int kTabBatchSmall = 1024;         // of mcl_init_uniform), halved down to 1024 until the windows fit
 constexpr float kTabB2 = 0.59033447f;        // 4/pi * atan(1/2): the octant boundaries in u8 units (see tab_sector)
 constexpr float kTabS = 0.84697730f;         // 0.5 / kTabB2: u8 * S rounds to 0 inside +-B2, to +-1 beyond
 constexpr float kTabC8 = 1.27323954f;        // 8 / (2 pi)
