@@ -258,9 +258,7 @@ int xbarrier(mcl_engine* h, int slot)
     if (h->world == 1) return MCL_OK;
     if (!h->xpeer) return fail(h, MCL_ERR_COMM, "exchange blocks are not mapped");
     const int epoch = ++h->xepoch[slot];
-    xsignal_kernel<<<1, 32, 0, h->stream>>>(h->xp, h->xl.flags, slot, epoch);
-    CKL(h);
-    xwait_kernel<<<1, 32, 0, h->stream>>>(h->xblock, h->xl.flags, h->xl.err, slot, epoch, h->world);
+    xbarrier_kernel<<<1, 32, 0, h->stream>>>(h->xp, h->xl.flags, h->xl.err, slot, epoch);
     CKL(h);
     ++h->collectives;
     return MCL_OK;
@@ -293,7 +291,7 @@ int seq_total(mcl_engine* h, int wbuf)
         xseq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_excl,
                                                             (const double*)(h->xblock + h->xl.tot), h->fb_count, h->xp, o);
         CKL(h);
-        xseq_group_maps_kernel<<<(int)((group_hi - group_lo + 127) / 128), 128, 0, h->stream>>>(
+        xseq_group_maps_kernel<<<(int)((group_hi - group_lo + 3) / 4), 128, 0, h->stream>>>(
             h->ebias, h->q0, h->q1, n1, group_lo, group_hi, h->xp, h->xl.g0, h->xl.g1, h->xl.ge);
         CKL(h);
     }
@@ -302,7 +300,7 @@ int seq_total(mcl_engine* h, int wbuf)
     if (rc) return rc;
     prof_mark(h, "seq:barrierB");
     {
-        const size_t walk_smem = (size_t)n2 * 20;                    // g0, g1 (8 B each) + gebias (4 B) per group
+        const size_t walk_smem = xseq_walk_smem(n2);                 // group maps + the pre-staged chunk maps and raw chunks
         const int staged = walk_smem + 4096 <= (size_t)h->max_smem_optin ? 1 : 0;
         if (staged) CK(cudaFuncSetAttribute(xseq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
         xseq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(

@@ -68,6 +68,28 @@ __global__ void xsignal_kernel(const XPeers xp, size_t flags_off, int slot, int 
     }
 }
 
+// signal + wait in one launch (lane r tells rank r, then waits for rank r)
+__global__ void xbarrier_kernel(const XPeers xp, size_t flags_off, size_t err_off, int slot, int epoch)
+{
+    const int r = threadIdx.x;
+    if (r < xp.world) {
+        __threadfence_system();
+        volatile int* out = reinterpret_cast<volatile int*>(xp.base[r] + flags_off) + slot * kMaxPeers + xp.rank;
+        *out = epoch;
+        __threadfence_system();
+        unsigned char* base = xp.base[xp.rank];
+        volatile int* f = reinterpret_cast<volatile int*>(base + flags_off) + slot * kMaxPeers + r;
+        const long long t0 = clock64();
+        while (*f < epoch) {
+            if (clock64() - t0 > 20000000000ll) {       // ~10 s: a peer died; do not hang the GPU
+                *reinterpret_cast<volatile int*>(base + err_off) = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
 __global__ void xwait_kernel(unsigned char* base, size_t flags_off, size_t err_off, int slot, int epoch, int world)
 {
     const int r = threadIdx.x;
@@ -223,27 +245,43 @@ __global__ void __launch_bounds__(128) xseq_chunk_maps_kernel(const double* w, l
 }
 
 // ---- S4: level-2 maps of the slice's groups [group_lo, group_hi), pushed to every rank ---------------------------------------
-__global__ void xseq_group_maps_kernel(const int* ebias, const long long* q0, const long long* q1, long long n1,
-                                       long long group_lo, long long group_hi, const XPeers xp, size_t g0_off,
-                                       size_t g1_off, size_t ge_off)
+// One warp per group: every lane composes two consecutive chunk maps, a shuffle tree composes the 32 results in order
+// (composition is associative, not commutative).
+__global__ void __launch_bounds__(128) xseq_group_maps_kernel(const int* ebias, const long long* q0, const long long* q1,
+                                                              long long n1, long long group_lo, long long group_hi,
+                                                              const XPeers xp, size_t g0_off, size_t g1_off, size_t ge_off)
 {
-    const long long j = group_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long j = group_lo + blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= group_hi) return;
     const long long first = j * kL2;
     const long long last = first + kL2 < n1 ? first + kL2 : n1;
+    const long long ka = first + 2 * lane, kb = ka + 1;
     const int e = ebias[first];
-    bool ok = e != 0;
-    long long a0 = 0, a1 = 0;
-    for (long long k = first; k < last && ok; ++k) {
-        if (ebias[k] != e) { ok = false; break; }
-        const long long f0 = q0[k], f1 = q1[k];
-        a0 += ((a0 & 1) ? f1 : f0);
-        a1 += (((a1 + 1) & 1) ? f1 : f0);
+    long long a0 = 0, a1 = 0;                               // identity map for the chunks past the end
+    bool same = true;
+    if (ka < last) { same = ebias[ka] == e; a0 = q0[ka]; a1 = q1[ka]; }
+    if (kb < last) {
+        same = same && ebias[kb] == e;
+        long long r0, r1;
+        seq_compose(a0, a1, q0[kb], q1[kb], r0, r1);
+        a0 = r0; a1 = r1;
     }
-    for (int r = 0; r < xp.world; ++r) {
-        reinterpret_cast<long long*>(xp.base[r] + g0_off)[j] = a0;
-        reinterpret_cast<long long*>(xp.base[r] + g1_off)[j] = a1;
-        reinterpret_cast<int*>(xp.base[r] + ge_off)[j] = ok ? e : 0;
+    const bool ok = e != 0 && __all_sync(0xffffffffu, same);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const long long b0 = __shfl_down_sync(0xffffffffu, a0, off), b1 = __shfl_down_sync(0xffffffffu, a1, off);
+        if ((lane & (2 * off - 1)) == 0) {
+            long long r0, r1;
+            seq_compose(a0, a1, b0, b1, r0, r1);
+            a0 = r0; a1 = r1;
+        }
+    }
+    a0 = __shfl_sync(0xffffffffu, a0, 0); a1 = __shfl_sync(0xffffffffu, a1, 0);        // lane 0 holds the group's map
+    if (lane < xp.world) {
+        reinterpret_cast<long long*>(xp.base[lane] + g0_off)[j] = a0;
+        reinterpret_cast<long long*>(xp.base[lane] + g1_off)[j] = a1;
+        reinterpret_cast<int*>(xp.base[lane] + ge_off)[j] = ok ? e : 0;
     }
 }
 
@@ -290,6 +328,29 @@ __device__ __forceinline__ int seq_apply_prefix(double& c, int cnt, int e_l, lon
 // weights of such a chunk come from the rank's own slice, from the side buffer its owner filled, or from the owner's
 // weights over NVLink.  Produces the exact entry sum of every group (cin2), of every chunk of the groups that had to
 // be opened (cin1, flagged in opened[j]), the exact total and the number of chunks added element by element.
+constexpr int kWalkOpen = 16;        // groups whose chunk maps are staged ahead of the walk
+constexpr int kWalkFb = 16;          // chunks whose raw weights are staged ahead of the walk
+__host__ __device__ inline size_t xseq_walk_smem(long long n2)
+{
+    return (size_t)n2 * 20 + (size_t)kWalkOpen * kL2 * 20 + (size_t)kWalkFb * kL1 * 8;
+}
+
+// Where the raw weights of chunk k live for this rank: its own slice, the side buffer its owner filled (S3 knew the
+// chunk would be added element by element), or the owner's weights over NVLink.  bounded: not zero padded past n.
+__device__ __forceinline__ const double* xseq_raw_chunk(const XPeers& xp, size_t w_off, size_t fbraw_off, long long k, int e,
+                                                        long long f0, bool& bounded)
+{
+    const long long efirst = k * kL1;
+    const int owner = xowner(xp, efirst);
+    bounded = true;
+    if (owner == xp.rank) return reinterpret_cast<const double*>(xp.base[xp.rank] + w_off) + efirst;
+    if (e == 0 && f0 >= 0) {
+        bounded = false;
+        return reinterpret_cast<const double*>(xp.base[xp.rank] + fbraw_off) + ((size_t)owner * kFbSlots + (size_t)f0) * kL1;
+    }
+    return reinterpret_cast<const double*>(xp.base[owner] + w_off) + efirst;
+}
+
 __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long n1, long long n2, const int* ebias,
                                                        const long long* q0, const long long* q1, const int* gebias,
                                                        const long long* g0, const long long* g1, double* cin2, double* cin1,
@@ -299,12 +360,61 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
     __shared__ double fb_chunk[kL1];
     __shared__ long long sc0[kL2], sc1[kL2];      // level-1 maps of the group being opened
     __shared__ int sce[kL2];
+    __shared__ int s_nopen, s_nfb;
+    __shared__ long long s_open_j[kWalkOpen], s_fb_k[kWalkFb];
+    __shared__ int s_fb_e[kWalkFb];
+    __shared__ long long s_fb_f0[kWalkFb];
     extern __shared__ __align__(16) unsigned char walk_smem[];
     long long* sg0 = reinterpret_cast<long long*>(walk_smem);
     long long* sg1 = sg0 + (staged ? n2 : 0);
-    int* sge = reinterpret_cast<int*>(sg1 + (staged ? n2 : 0));
+    long long* so0 = sg1 + (staged ? n2 : 0);                 // [kWalkOpen][kL2]
+    long long* so1 = so0 + (staged ? kWalkOpen * kL2 : 0);
+    double* sfb = reinterpret_cast<double*>(so1 + (staged ? kWalkOpen * kL2 : 0));      // [kWalkFb][kL1]
+    int* sge = reinterpret_cast<int*>(sfb + (staged ? kWalkFb * kL1 : 0));
+    int* soe = sge + (staged ? n2 : 0);                       // [kWalkOpen][kL2]
+    int nopen = 0, nfb = 0;
     if (staged) {
+        // Everything the walk will read, staged by the whole CTA so that its single warp never waits for global memory:
+        // the group maps; the chunk maps of the groups that do not apply as a whole (S4 marked them); the raw weights
+        // of their chunks that are added element by element (S3 marked those).
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (threadIdx.x == 0) { s_nopen = 0; s_nfb = 0; }
         for (long long j = threadIdx.x; j < n2; j += blockDim.x) { sg0[j] = g0[j]; sg1[j] = g1[j]; sge[j] = gebias[j]; }
+        __syncthreads();
+        for (long long j = wrp; j < n2; j += nwarps) {
+            if (sge[j] != 0) continue;
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&s_nopen, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot >= kWalkOpen) continue;
+            if (lane == 0) s_open_j[slot] = j;
+            const long long kfirst = j * kL2;
+            for (int i = lane; i < kL2; i += 32) {
+                const bool in = kfirst + i < n1;
+                so0[slot * kL2 + i] = in ? q0[kfirst + i] : 0;
+                so1[slot * kL2 + i] = in ? q1[kfirst + i] : 0;
+                soe[slot * kL2 + i] = in ? ebias[kfirst + i] : -1;
+            }
+        }
+        __syncthreads();
+        nopen = min(s_nopen, kWalkOpen);
+        for (int t = threadIdx.x; t < nopen * kL2; t += blockDim.x) {
+            if (soe[t] == 0) {
+                const int fs = atomicAdd(&s_nfb, 1);
+                if (fs < kWalkFb) {
+                    s_fb_k[fs] = s_open_j[t / kL2] * kL2 + (t % kL2);
+                    s_fb_e[fs] = 0; s_fb_f0[fs] = so0[t];
+                }
+            }
+        }
+        __syncthreads();
+        nfb = min(s_nfb, kWalkFb);
+        for (int fs = wrp; fs < nfb; fs += nwarps) {
+            bool bounded;
+            const long long k = s_fb_k[fs];
+            const double* src = xseq_raw_chunk(xp, w_off, fbraw_off, k, s_fb_e[fs], s_fb_f0[fs], bounded);
+            for (int i = lane; i < kL1; i += 32) sfb[fs * kL1 + i] = (!bounded || k * kL1 + i < n) ? src[i] : 0.0;
+        }
         __syncthreads();
     }
     if (threadIdx.x >= 32) return;
@@ -326,9 +436,18 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
         if (lane == 0) { cin2[j] = c; opened[j] = 1; }
         const long long kfirst = j * kL2;
         const int kcnt = (int)((kfirst + kL2 < n1 ? kfirst + kL2 : n1) - kfirst);
-        for (int i = lane; i < kL2; i += 32) {
-            const bool in = i < kcnt;
-            sce[i] = in ? ebias[kfirst + i] : 0; sc0[i] = in ? q0[kfirst + i] : 0; sc1[i] = in ? q1[kfirst + i] : 0;
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < nopen && s_open_j[lane < nopen ? lane : 0] == j);
+        if (hit) {
+            const int slot = __ffs(hit) - 1;
+            for (int i = lane; i < kL2; i += 32) {
+                const bool in = i < kcnt;
+                sce[i] = in ? soe[slot * kL2 + i] : 0; sc0[i] = in ? so0[slot * kL2 + i] : 0; sc1[i] = in ? so1[slot * kL2 + i] : 0;
+            }
+        } else {
+            for (int i = lane; i < kL2; i += 32) {
+                const bool in = i < kcnt;
+                sce[i] = in ? ebias[kfirst + i] : 0; sc0[i] = in ? q0[kfirst + i] : 0; sc1[i] = in ? q1[kfirst + i] : 0;
+            }
         }
         __syncwarp();
         int kd = 0;
@@ -345,25 +464,24 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
             const long long k = kfirst + kd;
             if (lane == 0) cin1[k] = c;
             ++fallbacks;
-            const long long efirst = k * kL1;
-            const int owner = xowner(xp, efirst);
-            const int e = sce[kd];
-            const long long f0 = sc0[kd];
-            const double* src;
-            bool bounded = true;
-            if (owner == xp.rank) src = reinterpret_cast<const double*>(xp.base[xp.rank] + w_off) + efirst;
-            else if (e == 0 && f0 >= 0) {
-                src = reinterpret_cast<const double*>(xp.base[xp.rank] + fbraw_off) + ((size_t)owner * kFbSlots + (size_t)f0) * kL1;
-                bounded = false;            // the side buffer is zero padded past n
-            } else src = reinterpret_cast<const double*>(xp.base[owner] + w_off) + efirst;
-            double v_l[kL1 / 32];
+            const unsigned fhit = __ballot_sync(0xffffffffu, lane < nfb && s_fb_k[lane < nfb ? lane : 0] == k);
+            if (fhit) {
+                const double* src = sfb + (__ffs(fhit) - 1) * kL1;
 #pragma unroll
-            for (int q = 0; q < kL1 / 32; ++q) {                      // all loads in flight before the adds
-                const long long gi = efirst + q * 32 + lane;
-                v_l[q] = (!bounded || gi < n) ? src[q * 32 + lane] : 0.0;
+                for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = src[q * 32 + lane];
+            } else {
+                bool bounded;
+                const double* src = xseq_raw_chunk(xp, w_off, fbraw_off, k, sce[kd], sc0[kd], bounded);
+                const long long efirst = k * kL1;
+                double v_l[kL1 / 32];
+#pragma unroll
+                for (int q = 0; q < kL1 / 32; ++q) {                      // all loads in flight before the adds
+                    const long long gi = efirst + q * 32 + lane;
+                    v_l[q] = (!bounded || gi < n) ? src[q * 32 + lane] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
             }
-#pragma unroll
-            for (int q = 0; q < kL1 / 32; ++q) fb_chunk[q * 32 + lane] = v_l[q];
             __syncwarp();
 #pragma unroll 16
             for (int i = 0; i < kL1; ++i) c = __dadd_rn(c, fb_chunk[i]);
