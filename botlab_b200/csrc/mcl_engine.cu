@@ -31,6 +31,9 @@ struct PoseSoA {
 
 }  // namespace
 
+// What a blocking call reads back (read_back()): counters[0..5] = overruns, gathers, fall-back chunks, (double) weight sum,
+// (double) sum w^2, deferred evaluations; counters[6] = barrier time-out flag; est = the pose estimate.
+struct Readback { unsigned long long counters[7]; float est[4]; };
 struct mcl_engine {
     mcl_params params;
     int device = 0;
@@ -149,7 +152,8 @@ struct mcl_engine {
     size_t staging_bytes = 0;
     int* host_bbox = nullptr;          // pinned 4 ints
     int* host_bbox_init = nullptr;     // pinned: the empty box
-    unsigned long long* host_counters = nullptr;   // pinned: overruns, gathers, fallbacks, (double) total, ess
+    Readback* readback_dev = nullptr;             // see read_back()
+    Readback* readback_host = nullptr;            // pinned
 
     // stats
     mcl_stats stats{};
@@ -1071,40 +1075,54 @@ int run_resample_indices(mcl_engine* h, double r, int wbuf, long long children =
     return MCL_OK;
 }
 
-int read_counters(mcl_engine* h)
+// What a blocking call reads back, gathered on the device so that it is ONE copy (each tiny D2H copy costs the host
+// several microseconds): counters[0..5] = overruns, gathers, fall-back chunks, (double) weight sum, (double) sum w^2,
+// deferred evaluations; counters[6] = barrier time-out flag; est = the pose estimate.
+__global__ void readback_kernel(const unsigned long long* overruns, const unsigned long long* gathers,
+                                const long long* fallbacks, const double* total, const double* ess,
+                                const unsigned long long* deferred, const int* err, const float* est, Readback* out)
 {
-    CK(cudaMemcpyAsync(&h->host_counters[0], h->overruns, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[1], h->gather_counter, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[2], h->fallbacks, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[3], h->total, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[4], h->ess_acc, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[5], h->deferred_counter, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&h->host_counters[6], h->xblock + h->xl.err, 4, cudaMemcpyDeviceToHost, h->stream));
+    Readback r;
+    r.counters[0] = *overruns; r.counters[1] = *gathers; r.counters[2] = (unsigned long long)*fallbacks;
+    r.counters[3] = (unsigned long long)__double_as_longlong(*total);
+    r.counters[4] = (unsigned long long)__double_as_longlong(*ess);
+    r.counters[5] = *deferred; r.counters[6] = (unsigned long long)(unsigned)*err;
+    for (int i = 0; i < 4; ++i) r.est[i] = est[i];
+    *out = r;
+}
+
+int read_back(mcl_engine* h, bool counters, bool estimate, int64_t utime)
+{
+    readback_kernel<<<1, 1, 0, h->stream>>>(h->overruns, h->gather_counter, (const long long*)h->fallbacks, h->total, h->ess_acc,
+                                            h->deferred_counter, (const int*)(h->xblock + h->xl.err), h->est_out, h->readback_dev);
+    CKL(h);
+    CK(cudaMemcpyAsync(h->readback_host, h->readback_dev, sizeof(Readback), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if ((int)(h->host_counters[6] & 0xffffffffu) != 0)
+    const Readback& r = *h->readback_host;
+    if ((int)(r.counters[6] & 0xffffffffu) != 0)
         return fail(h, MCL_ERR_COMM, "a cross-rank barrier timed out (a peer rank stopped)");
-    h->stats.deferred_evals = (int64_t)h->host_counters[5];
-    h->stats.resample_overruns = (int64_t)h->host_counters[0];
-    h->stats.gathers = h->count_gathers ? (int64_t)h->host_counters[1] : -1;
-    h->stats.seq_fallback_chunks = (int64_t)h->host_counters[2];
-    double d;
-    std::memcpy(&d, &h->host_counters[3], 8);
-    h->stats.weight_sum = d;
-    std::memcpy(&d, &h->host_counters[4], 8);
-    h->stats.effective_sample_size = d > 0 ? 1.0 / d : 0.0;
+    if (counters) {
+        h->stats.deferred_evals = (int64_t)r.counters[5];
+        h->stats.resample_overruns = (int64_t)r.counters[0];
+        h->stats.gathers = h->count_gathers ? (int64_t)r.counters[1] : -1;
+        h->stats.seq_fallback_chunks = (int64_t)r.counters[2];
+        double d;
+        std::memcpy(&d, &r.counters[3], 8);
+        h->stats.weight_sum = d;
+        std::memcpy(&d, &r.counters[4], 8);
+        h->stats.effective_sample_size = d > 0 ? 1.0 / d : 0.0;
+    }
+    if (estimate) {
+        h->last_estimate.x = r.est[0];
+        h->last_estimate.y = r.est[1];
+        h->last_estimate.theta = r.est[2];
+        h->last_estimate.utime = utime;
+    }
     return MCL_OK;
 }
 
-int fetch_estimate(mcl_engine* h, int64_t utime)
-{
-    CK(cudaMemcpyAsync(h->est_host, h->est_out, sizeof(float) * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->last_estimate.x = h->est_host[0];
-    h->last_estimate.y = h->est_host[1];
-    h->last_estimate.theta = h->est_host[2];
-    h->last_estimate.utime = utime;
-    return MCL_OK;
-}
+int read_counters(mcl_engine* h) { return read_back(h, true, false, 0); }
+int fetch_estimate(mcl_engine* h, int64_t utime) { return read_back(h, false, true, utime); }
 
 // The five stages of ParticleFilter::updateFilter on the engine's stream, no host synchronisation unless the tile
 // heuristic needs the cloud's bounding box.
@@ -1166,7 +1184,8 @@ void free_all(mcl_engine* h)
     if (h->tab_hint) cudaFreeHost(h->tab_hint);
     if (h->ev_tab_hint) cudaEventDestroy(h->ev_tab_hint);
     F(h->tab_plan); F(h->tab_build); F(h->tab_box); F(h->tab_bboxes);
-    if (h->host_counters) cudaFreeHost(h->host_counters);
+    if (h->readback_host) cudaFreeHost(h->readback_host);
+    if (h->readback_dev) cudaFree(h->readback_dev);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
@@ -1308,7 +1327,8 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMallocHost((void**)&h->tab_hint, sizeof(mcl_engine::TabHint)));
     std::memset(h->tab_hint, 0, sizeof(mcl_engine::TabHint));
     CKB(cudaEventCreateWithFlags(&h->ev_tab_hint, cudaEventDisableTiming));
-    CKB(cudaMallocHost((void**)&h->host_counters, 64));
+    CKB(cudaMallocHost((void**)&h->readback_host, 128));
+    CKB(cudaMalloc((void**)&h->readback_dev, 128));
 #undef CKB
     h->stats.num_particles = h->n;
     h->stats.local_particles = h->n;
@@ -1944,9 +1964,7 @@ int mcl_update(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, con
         if (rc) return rc;
         rc = enqueue_update(h, a, odometry_utime, r, nd);
         if (rc) return rc;
-        rc = fetch_estimate(h, odometry_utime);
-        if (rc) return rc;
-        rc = read_counters(h);
+        rc = read_back(h, true, true, odometry_utime);
         if (rc) return rc;
         prof_collect(h);
         float ms = 0;
