@@ -319,7 +319,7 @@ def measure(hx, args, config, steps, warmup, particles=0, uniform=False, want_ro
 
     valid = int((r0 > np.float32(0.15)).sum())
     h2d = valid * 16 + 64            # prepared beams (16 B each) + scalars
-    d2h = 16 + 56                    # pose estimate + counters
+    d2h = 80                         # one readback struct: counters + pose estimate
 
     # ---- e2e arm: blocking C-ABI calls with host scan buffers ---------------------------------------------------
     for _ in range(warmup):
@@ -389,7 +389,8 @@ def measure(hx, args, config, steps, warmup, particles=0, uniform=False, want_ro
                                     if 28 * n > 126e6 else
                                     "particle state smaller than L2 (it is rewritten by every update; no flush between steps)",
                        "lanes_per_particle": st["lanes_per_particle"], "map_tile_used": st["map_tile_used"],
-                       "sensor_path": st["sensor_path"], "deferred_fraction": st["deferred_evals"] / max(st["evals"], 1),
+                       "sensor_path": st["sensor_path"], "table_variant": st["table_variant"], "culled_beams": st["culled_beams"],
+                       "deferred_fraction": st["deferred_evals"] / max(st["evals"], 1),
                        "certification_eps_cells": st["fast_eps"], "particles_per_gpu": local_n},
             "e2e": {"value": evals_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
@@ -430,6 +431,9 @@ def roofline(st, gathers, local_n, grid, score_s, clock_info, gather_peak):
     sm_mhz = clock_info.get("sm_mhz") or 1965.0
     sms = 148
     evals = st["evals"]
+    if st["sensor_path"] == 3 and st.get("culled_beams", 0) > 0 and local_n > 0:
+        # beams culled for the whole slice are not executed: the instruction figure applies to the evaluations that are
+        evals = evals * (1.0 - st["culled_beams"] / (evals / local_n))
     peak_issue = 4 * sms * sm_mhz * 1e6
     peak, peak_kind = measured_peaks()
     hbm_bytes = 36 * local_n + grid.width * grid.height
@@ -497,6 +501,17 @@ def run_engine(args):
                                              "sample": f"{cpu_updates} updateFilter calls at full size ({cn} particles, "
                                                        f"{sec:.1f} s of CPU)"}
                 extra.append(entry)
+            # config 4 again with the robot in the map's interior: the seeded pose lies 2.5 m from the map's corner, which
+            # clips the sensor kernel's window; here the whole 8 m reach is inside the map (8-bit class tile), and the
+            # rays that end in open space are culled (they score 0 for every particle)
+            INTERIOR_POSE[0] = True
+            try:
+                res, _ = measure(hx, args, "config4", 5, 3, want_roofline=False)
+            finally:
+                INTERIOR_POSE[0] = args.pose == "interior"
+            extra.append({"config": res["config"], "details": res["details"], "value": res["value"], "unit": UNIT,
+                          "ms_per_step": res["ms_per_step"], "steps": 5, "warmup": 3, "e2e": res["e2e"],
+                          "stage_ms": res["stage_ms"], "gpu_launches": res["gpu_launches"]})
         elif world == 8:
             res, _ = measure(hx, args, "config5", 3, 3, want_roofline=False)
             if rank == 0:

@@ -33,7 +33,7 @@ struct PoseSoA {
 
 // What a blocking call reads back (read_back()): counters[0..5] = overruns, gathers, fall-back chunks, (double) weight sum,
 // (double) sum w^2, deferred evaluations; counters[6] = barrier time-out flag; est = the pose estimate.
-struct Readback { unsigned long long counters[7]; float est[4]; };
+struct Readback { unsigned long long counters[7]; float est[4]; int culled; int pad; };
 struct mcl_engine {
     mcl_params params;
     int device = 0;
@@ -112,6 +112,8 @@ struct mcl_engine {
     int tab_blocked = 0;                // updates to keep off the table pass after an overflow
     int tab_variant = 0;                // kTabSingle16 .. kTabBatch8 (mcl_table.cuh): what the next pass launches
     int tab_excluded = 0;               // variants whose score table overflowed on this cloud
+    uint8_t* tab_cull = nullptr;        // per beam: 1 = the table pass skips it (table_cull_kernel)
+    int cull_interval = 1, cull_wait = 0;   // the culling pass runs every cull_interval-th update while it finds nothing
     int tab_batch = kTabBatch;          // kTabBatch = 4096, halved down to kTabBatchSmall = 1024 until the windows fit
     int4* tab_bboxes = nullptr;         // bounding box per batch
     size_t tab_bboxes_cap = 0;
@@ -661,6 +663,8 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
             // (when this plan was not ok, tab_ok is false and the next pass plans synchronously)
             h->tab_variant = hp.best;
         }
+        // a culling pass that finds nothing is tried less and less often (every 2nd ... 16th update); a hit resets that
+        if (h->tab_hint->build[6]) h->cull_interval = h->tab_hint->build[5] > 0 ? 1 : std::min(16, h->cull_interval * 2);
     }
     if (h->tab_blocked > 0 && !lf) { --h->tab_blocked; return 0; }
     const size_t smem_total = (size_t)h->max_smem_optin - 1024;      // static shared memory of the kernel stays below 1 KB
@@ -681,6 +685,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     in.num_beams = h->num_beams;
     in.scan_finite = h->scan_finite ? 1 : 0;
     in.allow = 1;
+    in.cull = (!lf && !std::getenv("MCL_NO_CULL")) ? 1 : 0;
     in.smem_total = (int)smem_total;
     in.smem_fixed = (int)table_fixed_smem(h->num_beams);
     const bool allow_batch = !lf && !std::getenv("MCL_NO_TABLE_BATCH");          // (the likelihood field keeps one window)
@@ -691,8 +696,9 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
         in.excluded = h->tab_excluded;
         nbatches = (local + h->tab_batch - 1) / h->tab_batch;
         in.num_batches = allow_batch ? nbatches : 0;
-        table_bbox_kernel<<<(int)nbatches, 256, 0, h->stream>>>(sa.x, sa.y, sa.px, sa.py, h->lo, h->hi, h->tab_batch, h->grid, rc6,
-                                                                k_budget, h->tab_box, allow_batch ? h->tab_bboxes : nullptr);
+        table_bbox_kernel<<<(int)nbatches, 256, 0, h->stream>>>(sa.x, sa.y, sa.th, sa.px, sa.py, sa.pth, h->lo, h->hi, h->tab_batch,
+                                                                h->grid, rc6, k_budget, h->tab_box,
+                                                                allow_batch ? h->tab_bboxes : nullptr);
         CKL(h);
         table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan);
         CKL(h);
@@ -735,7 +741,17 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     a.build_info = h->tab_build;
     a.bboxes = h->tab_bboxes;
     a.batch = h->tab_batch;
+    a.cull = nullptr;
+    if (!batch && in.cull && ++h->cull_wait >= h->cull_interval) {
+        h->cull_wait = 0;
+        a.cull = h->tab_cull;
+    }
     CK(cudaMemsetAsync(h->tab_build, 0, 8 * sizeof(int), h->stream));
+    if (a.cull) {
+        table_cull_kernel<<<h->num_beams, 256, 0, h->stream>>>(h->tab_plan, sa.beams, h->num_beams, h->grid, h->map_cls, h->cpitch,
+                                                               h->tab_cull, h->tab_build + 5);
+        CKL(h);
+    }
     const long long nunits = (local + 31) / 32;
     // one CTA per SM; small clouds get as many CTAs as their (unit, 32-beam word) pairs can keep busy
     const long long pairs = nunits * ((h->num_beams + 31) / 32);
@@ -1080,7 +1096,8 @@ int run_resample_indices(mcl_engine* h, double r, int wbuf, long long children =
 // deferred evaluations; counters[6] = barrier time-out flag; est = the pose estimate.
 __global__ void readback_kernel(const unsigned long long* overruns, const unsigned long long* gathers,
                                 const long long* fallbacks, const double* total, const double* ess,
-                                const unsigned long long* deferred, const int* err, const float* est, Readback* out)
+                                const unsigned long long* deferred, const int* err, const float* est, const int* tab_build,
+                                Readback* out)
 {
     Readback r;
     r.counters[0] = *overruns; r.counters[1] = *gathers; r.counters[2] = (unsigned long long)*fallbacks;
@@ -1088,13 +1105,15 @@ __global__ void readback_kernel(const unsigned long long* overruns, const unsign
     r.counters[4] = (unsigned long long)__double_as_longlong(*ess);
     r.counters[5] = *deferred; r.counters[6] = (unsigned long long)(unsigned)*err;
     for (int i = 0; i < 4; ++i) r.est[i] = est[i];
+    r.culled = tab_build[5]; r.pad = 0;
     *out = r;
 }
 
 int read_back(mcl_engine* h, bool counters, bool estimate, int64_t utime)
 {
     readback_kernel<<<1, 1, 0, h->stream>>>(h->overruns, h->gather_counter, (const long long*)h->fallbacks, h->total, h->ess_acc,
-                                            h->deferred_counter, (const int*)(h->xblock + h->xl.err), h->est_out, h->readback_dev);
+                                            h->deferred_counter, (const int*)(h->xblock + h->xl.err), h->est_out, h->tab_build,
+                                            h->readback_dev);
     CKL(h);
     CK(cudaMemcpyAsync(h->readback_host, h->readback_dev, sizeof(Readback), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1106,6 +1125,7 @@ int read_back(mcl_engine* h, bool counters, bool estimate, int64_t utime)
         h->stats.resample_overruns = (int64_t)r.counters[0];
         h->stats.gathers = h->count_gathers ? (int64_t)r.counters[1] : -1;
         h->stats.seq_fallback_chunks = (int64_t)r.counters[2];
+        h->stats.culled_beams = h->stats.sensor_path == 3 ? r.culled : 0;
         double d;
         std::memcpy(&d, &r.counters[3], 8);
         h->stats.weight_sum = d;
@@ -1183,7 +1203,7 @@ void free_all(mcl_engine* h)
     if (h->host_bbox_init) cudaFreeHost(h->host_bbox_init);
     if (h->tab_hint) cudaFreeHost(h->tab_hint);
     if (h->ev_tab_hint) cudaEventDestroy(h->ev_tab_hint);
-    F(h->tab_plan); F(h->tab_build); F(h->tab_box); F(h->tab_bboxes);
+    F(h->tab_plan); F(h->tab_build); F(h->tab_box); F(h->tab_bboxes); F(h->tab_cull);
     if (h->readback_host) cudaFreeHost(h->readback_host);
     if (h->readback_dev) cudaFree(h->readback_dev);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -1318,8 +1338,14 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMallocHost((void**)&h->host_bbox_init, 16));
     h->host_bbox_init[0] = h->host_bbox_init[1] = 0x7fffffff;
     h->host_bbox_init[2] = h->host_bbox_init[3] = (int)0x80000000;
-    CKB(cudaMalloc((void**)&h->tab_box, 64));
-    CKB(cudaMemset(h->tab_box, 0, 64));
+    CKB(cudaMalloc((void**)&h->tab_box, 96));
+    CKB(cudaMemset(h->tab_box, 0, 96));
+    {
+        const int arm[2] = {0x7fffffff, (int)0x80000000};          // heading range (table_bbox_kernel)
+        CKB(cudaMemcpy(h->tab_box + 16, arm, 8, cudaMemcpyHostToDevice));
+    }
+    CKB(cudaMalloc((void**)&h->tab_cull, kTabMaxBeams + 1));
+    CKB(cudaMemset(h->tab_cull, 0, kTabMaxBeams + 1));
     CKB(cudaMemcpy(h->tab_box, h->host_bbox_init, 16, cudaMemcpyHostToDevice));
     CKB(cudaMalloc((void**)&h->tab_plan, sizeof(TabPlan)));
     CKB(cudaMemset(h->tab_plan, 0, sizeof(TabPlan)));
@@ -1679,6 +1705,7 @@ int mcl_init_at_pose(mcl_engine* h, float x, float y, float theta, int64_t utime
     h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
     h->tab_batch = kTabBatch;
     h->tab_excluded = 0;
+    h->cull_interval = 1; h->cull_wait = 0;
     h->have_particles = true;
     h->have_scores = false;
     h->last_estimate.x = x; h->last_estimate.y = y; h->last_estimate.theta = theta; h->last_estimate.utime = utime;
@@ -1710,6 +1737,7 @@ int mcl_init_uniform(mcl_engine* h, int64_t utime, uint64_t seed)
     h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
     h->tab_batch = kTabBatch;
     h->tab_excluded = 0;
+    h->cull_interval = 1; h->cull_wait = 0;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;
@@ -1739,6 +1767,7 @@ int mcl_import_particles(mcl_engine* h, const mcl_particle_t* aos, int64_t n)
     h->tab_hint_pending = false;        // (a plan of the previous cloud says nothing about this one)
     h->tab_batch = kTabBatch;
     h->tab_excluded = 0;
+    h->cull_interval = 1; h->cull_wait = 0;
     h->have_particles = true;
     h->have_scores = false;
     return MCL_OK;

@@ -52,6 +52,7 @@ constexpr int kTabWarps = kTabThreads / 32;
 constexpr int kTabQueue = 192;               // per-warp queue of deferred (lane, beam) entries
 constexpr int kTabFixed = 129;               // T entries 0..128: the uniform classes
 constexpr int kTabMaxBeams = 2047;           // queue entries are (lane << 11) | beam
+constexpr int kTabApron = 4;                 // the class map covers the grid plus this many cells on every side
 constexpr int kTabBatch = 4096;              // batch mode: consecutive particles that share one window (4 serpentine blocks
 constexpr int kTabBatchSmall = 1024;         // of mcl_init_uniform), halved down to 1024 until the windows fit
 constexpr float kTabB2 = 0.59033447f;        // 4/pi * atan(1/2): the octant boundaries in u8 units (see tab_sector)
@@ -95,6 +96,10 @@ struct TabPlan {
     int variant;                 // the variant this plan was made for (TabPlanIn::variant)
     int best;                    // the best applicable variant (-1: none): the host follows it on the next update
     int misfits;                 // batch mode: batches whose own window exceeds (w, h) -- they take the exact path
+    // beam culling (one-window variants): where the robot can be (global cell coordinates) and which headings it can
+    // have during the sweep, over every particle of the slice; table_cull_kernel turns that into a region per beam
+    int cull_ok;
+    double cull_x0, cull_x1, cull_y0, cull_y1, cull_a0, cull_a1;
     double rc6;                  // longest ray in cells + 6: the margin around a bounding box
     double x2_min;               // global coordinate the doubled endpoint must exceed (EDGE >= 1)
 };
@@ -109,6 +114,7 @@ struct TabPlanIn {
     int smem_total, smem_fixed;
     int variant;                 // kTabSingle16 .. kTabBatch8: what the host is going to launch
     int excluded;                // bit v: variant v is not to be used (its score table overflowed on this cloud)
+    int cull;                    // beam culling allowed
     long long num_batches;
 };
 
@@ -205,36 +211,57 @@ __device__ __forceinline__ bool tab_batch_window(TabPlan& pl, const int4 bx, con
 // least as wide as tall, box[9] = the number of fitting batches that are taller than wide (the serpentine order of
 // mcl_init_uniform runs along x: only the batches at its row turns are tall, and one window size for both orientations
 // would have to be square).  box[10 .. 15] = the same for 8-bit classes.
-__global__ void __launch_bounds__(256) table_bbox_kernel(const float* x, const float* y, const float* px, const float* py,
-                                                         long long lo, long long hi, int batch, DevGrid grid, double rc6,
-                                                         long long k_budget, int* box, int4* bboxes)
+// box[16], box[17] = the range of headings (ordered-int floats, relative to the parent heading of the slice's first
+// particle, which goes to box[19]) the particles pass through between parent and pose; box[18] != 0: some heading is not
+// finite or not wrapped.  (Beam culling, table_cull_kernel.)
+__global__ void __launch_bounds__(256) table_bbox_kernel(const float* x, const float* y, const float* th, const float* px,
+                                                         const float* py, const float* pth, long long lo, long long hi,
+                                                         int batch, DevGrid grid, double rc6, long long k_budget, int* box,
+                                                         int4* bboxes)
 {
-    __shared__ int red[4][8];
+    __shared__ int red[6][8];
     const long long first = lo + (long long)blockIdx.x * batch;
     const long long last = first + batch < hi ? first + batch : hi;
     int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+    int mna = 0x7fffffff, mxa = (int)0x80000000;
+    bool bad_heading = false;
+    const float th_ref = pth[lo];
     for (long long i = first + threadIdx.x; i < last; i += blockDim.x) {
         const int a = float_order(x[i]), b = float_order(y[i]), c = float_order(px[i]), d = float_order(py[i]);
         mnx = min(mnx, min(a, c)); mxx = max(mxx, max(a, c));
         mny = min(mny, min(b, d)); mxy = max(mxy, max(b, d));
+        // the heading runs from the parent's to the pose's along the shorter way round (interpolation.hpp:41)
+        const float ta = th[i], tb = pth[i];
+        if (!(fabsf(ta) <= 3.15f && fabsf(tb) <= 3.15f && fabsf(th_ref) <= 3.15f)) bad_heading = true;
+        const double db = fold_pi(__dsub_rn((double)tb, (double)th_ref));
+        const double da = db + fold_pi(__dsub_rn((double)ta, (double)tb));
+        const float lo_f = __double2float_rd(fmin(db, da)), hi_f = __double2float_ru(fmax(db, da));
+        mna = min(mna, float_order(lo_f)); mxa = max(mxa, float_order(hi_f));
     }
     for (int off = 16; off > 0; off >>= 1) {
         mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
         mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, off));
         mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
         mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+        mna = min(mna, __shfl_xor_sync(0xffffffffu, mna, off));
+        mxa = max(mxa, __shfl_xor_sync(0xffffffffu, mxa, off));
     }
+    if (__any_sync(0xffffffffu, bad_heading) && (threadIdx.x & 31) == 0) atomicOr(box + 18, 1);
     if ((threadIdx.x & 31) == 0) {
         red[0][threadIdx.x >> 5] = mnx; red[1][threadIdx.x >> 5] = mny;
         red[2][threadIdx.x >> 5] = mxx; red[3][threadIdx.x >> 5] = mxy;
+        red[4][threadIdx.x >> 5] = mna; red[5][threadIdx.x >> 5] = mxa;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < 8; ++k) {
             mnx = min(mnx, red[0][k]); mny = min(mny, red[1][k]); mxx = max(mxx, red[2][k]); mxy = max(mxy, red[3][k]);
+            mna = min(mna, red[4][k]); mxa = max(mxa, red[5][k]);
         }
         atomicMin(box + 0, mnx); atomicMin(box + 1, mny);
         atomicMax(box + 2, mxx); atomicMax(box + 3, mxy);
+        atomicMin(box + 16, mna); atomicMax(box + 17, mxa);
+        if (blockIdx.x == 0) box[19] = __float_as_int(th_ref);
         if (bboxes) {
             bboxes[blockIdx.x] = make_int4(mnx, mny, mxx, mxy);
             long long ux0, uy0, ux1, uy1;
@@ -261,6 +288,9 @@ __global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
     memset(&pl, 0, sizeof(pl));
     const int b0 = box[0], b1 = box[1], b2 = box[2], b3 = box[3];
     long long bdim[2][3];            // [wide]: window width, height, upper bound of the batches that will not fit it
+    const int ha0 = box[16], ha1 = box[17], hbad = box[18];
+    const float th_ref = __int_as_float(box[19]);
+    box[16] = 0x7fffffff; box[17] = (int)0x80000000; box[18] = 0;
     box[0] = 0x7fffffff; box[1] = 0x7fffffff; box[2] = (int)0x80000000; box[3] = (int)0x80000000;
     {
         const long long room_b = (long long)in.smem_total - in.smem_fixed - 64;
@@ -355,8 +385,84 @@ __global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
         pl.ang_room = 9.5f - fminf(in.max_abs_theta, 3.1415928f);      // kFastTrigErr is measured for |angle| <= 9.5
         pl.x2_min = 3.0 * eps + 2.0 * kappa + 1e-3;        // global coordinate the doubled endpoint must exceed
         tab_window_fields(pl, x0, y0, ux0, uy0, ux1, uy1); // (batch mode: rewritten for every batch)
+        // beam culling: one window, interpolation ratios within [0, 1] (the ray origin then lies between parent and
+        // pose), wrapped finite headings spanning less than 2.5 rad
+        auto unorder = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
+        const float a0 = unorder(ha0), a1 = unorder(ha1);
+        if (!batch && in.cull && !hbad && in.ratio_lo >= 0.0 && in.ratio_hi <= 1.0 && isfinite(a0) && isfinite(a1) && a0 <= a1 &&
+            a1 - a0 < 2.5f) {
+            pl.cull_ok = 1;
+            pl.cull_x0 = ((double)unorder(b0) - (double)in.grid.origin_x) * cpm; pl.cull_x1 = ((double)unorder(b2) - (double)in.grid.origin_x) * cpm;
+            pl.cull_y0 = ((double)unorder(b1) - (double)in.grid.origin_y) * cpm; pl.cull_y1 = ((double)unorder(b3) - (double)in.grid.origin_y) * cpm;
+            pl.cull_a0 = (double)th_ref + (double)a0; pl.cull_a1 = (double)th_ref + (double)a1;
+        }
     } while (false);
     *out = pl;
+}
+
+// BEAM CULLING.  A beam whose endpoint cell is class 0 for EVERY particle of the slice scores 0 for every particle (no
+// positive cell within two cells of the endpoint cell, hence none among the reference's three reads), so the table pass
+// need not evaluate it at all -- typically the rays that ended in open space at the sensor's maximum range.  One CTA
+// per beam bounds where its endpoints can lie.  The ray origin S lies in the bounding box of poses and parents (centre
+// C, half extents hx, hy), the heading in [a0, a1], so with am the middle direction of the beam, hw the half width of
+// its directions, and (u, v) the coordinates along / across am relative to C:
+//     u in [rc cos hw - bu, rc + bu],   |v| <= rc sin hw + bv,     bu = hx |cos am| + hy |sin am|, bv = hx |sin am| + hy |cos am|
+// (an annular sector swept by the box, bounded by an oriented rectangle).  + 4.5 cells: 3 for the roundings of either
+// model and the reference's truncation, 1.5 because a cell is tested at its corner.  The beam is culled when every cell
+// whose corner lies in that rectangle is class 0 in the class map (cells beyond the map's apron are: they lie four or
+// more cells outside the grid; cells with a negative coordinate inside the apron are class 1, so truncation toward zero
+// never matters).  flags[b] = 1: culled.  count[0] += culled beams, count[1] = 1 (the pass ran).
+__global__ void __launch_bounds__(256) table_cull_kernel(const TabPlan* plan, const Beam* beams, int num_beams, DevGrid grid,
+                                                         const uint8_t* cls, int cpitch, uint8_t* flags, int* count)
+{
+    const int b = blockIdx.x;
+    if (b >= num_beams) return;
+    const TabPlan& pl = *plan;
+    if (b == 0 && threadIdx.x == 0) count[1] = 1;
+    if (!pl.ok || !pl.cull_ok) {
+        if (threadIdx.x == 0) flags[b] = 0;
+        return;
+    }
+    const Beam bm = beams[b];
+    const double rc = (double)__fmul_rn(bm.range, grid.cells_per_meter);
+    const double am = 0.5 * (pl.cull_a0 + pl.cull_a1) - (double)bm.theta, hw = 0.5 * (pl.cull_a1 - pl.cull_a0) * (1.0 + 1e-6) + 1e-6;
+    double sn, cs;
+    sincos(am, &sn, &cs);
+    const double cx = 0.5 * (pl.cull_x0 + pl.cull_x1), cy = 0.5 * (pl.cull_y0 + pl.cull_y1);
+    const double hx = 0.5 * (pl.cull_x1 - pl.cull_x0), hy = 0.5 * (pl.cull_y1 - pl.cull_y0);
+    const double bu = hx * fabs(cs) + hy * fabs(sn), bv = hx * fabs(sn) + hy * fabs(cs);
+    const double m = 4.5;
+    const double u0 = rc * cos(hw) * (1.0 - 1e-6) - bu - m, u1 = rc * (1.0 + 1e-6) + bu + m, vm = rc * sin(hw) * (1.0 + 1e-6) + bv + m;
+    // axis-aligned bounds of the oriented rectangle
+    const double ex = fmax(fabs(u0), fabs(u1)) * fabs(cs) + vm * fabs(sn), ey = fmax(fabs(u0), fabs(u1)) * fabs(sn) + vm * fabs(cs);
+    const double fx0 = floor(cx - ex), fx1 = ceil(cx + ex), fy0 = floor(cy - ey), fy1 = ceil(cy + ey);
+    bool nonzero = !(fabs(fx0) < 1.0e6 && fabs(fy0) < 1.0e6 && fabs(fx1) < 1.0e6 && fabs(fy1) < 1.0e6);
+    if (!nonzero) {
+        const int x0 = max((int)fx0, -kTabApron), x1 = min((int)fx1, grid.width + kTabApron - 1);
+        const int y0 = max((int)fy0, -kTabApron), y1 = min((int)fy1, grid.height + kTabApron - 1);
+        const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+        if (w > 0 && h > 0) {
+            if ((long long)w * h > 262144) nonzero = true;         // (not worth scanning: a wide heading range)
+            else {
+                const float fcs = (float)cs, fsn = (float)sn, fu0 = (float)u0 - 0.01f, fu1 = (float)u1 + 0.01f, fvm = (float)vm + 0.01f;
+                const float ox = (float)((double)x0 - cx), oy = (float)((double)y0 - cy);
+                unsigned acc = 0u;
+                for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+                    const int ry = i / w, rx = i - ry * w;
+                    const float dx = ox + (float)rx, dy = oy + (float)ry;
+                    const float u = dx * fcs + dy * fsn, v = dy * fcs - dx * fsn;
+                    if (u >= fu0 && u <= fu1 && fabsf(v) <= fvm)
+                        acc |= (unsigned)__ldg(cls + (size_t)(y0 + ry + kTabApron) * cpitch + (x0 + rx + kTabApron));
+                }
+                nonzero = acc != 0u;
+            }
+        }
+    }
+    const int any = __syncthreads_or(nonzero ? 1 : 0);
+    if (threadIdx.x == 0) {
+        flags[b] = any ? 0 : 1;
+        if (!any) atomicAdd(count, 1);
+    }
 }
 
 // Per-particle constants of the table pass: robot coordinate at rho = 0 in window-normalised units, its change over
@@ -522,12 +628,14 @@ struct TabArgs {
     unsigned long long* deferred_counter;
     int* build_info;                // [0] table entries the window needs (max over CTAs), [1] CTAs (batch mode: batches)
                                     // that overflowed, [2] batch mode: the next batch to take, [3] batches without a
-                                    // window, [4] particles outside the table pass's domain (diagnostics)
+                                    // window, [4] particles outside the table pass's domain (diagnostics), [5] beams
+                                    // culled, [6] the culling pass ran
     const uint8_t* cls;             // class map (derive_class_map_kernel) ...
     const unsigned long long* pack; // ... and the score-table entries of its class-255 cells
     int cpitch;                     // bytes per row of the class map
     const int4* bboxes;             // batch mode: bounding box of every batch (table_bbox_kernel)
     int batch;                      // batch mode: particles per batch
+    const uint8_t* cull;            // one-window variants: beams the table pass skips (table_cull_kernel), else null
 };
 
 // Cold-path state shared by the CTA (static shared memory): what the exact evaluations need.
@@ -709,7 +817,6 @@ __device__ __forceinline__ unsigned long long tab_entry(const int n[8])
 // The CLASS MAP: tab_classify of every cell of the grid plus a four-cell apron (cell (gx, gy) at
 // cls[(gy + 4) * cpitch + gx + 4]; 255 = the cell gets a score-table entry, which is pack[same index]), kept current with
 // the mirror (refresh_fast_map) so that building a window is a copy plus the numbering of its entries.
-constexpr int kTabApron = 4;
 __global__ void derive_class_map_kernel(const TabArgs a, uint8_t* cls, unsigned long long* pack, int cpitch, int x0, int y0,
                                         int w, int h)
 {
@@ -820,11 +927,11 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     __shared__ TabCold s_cold;
     __shared__ int s_count, s_overflow;
     __shared__ long long s_batch;
-    __shared__ int s_batch_ok;
+    __shared__ int s_batch_ok, s_nb;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nb = a.num_beams;
-    const int nb4 = (nb + 3) & ~3;
+    const int nb_all = a.num_beams;
+    const int nb4 = (nb_all + 3) & ~3;
     TabBeam* sfast = reinterpret_cast<TabBeam*>(smem);
     Beam* sbeams = reinterpret_cast<Beam*>(smem + (size_t)nb4 * sizeof(TabBeam));
     float* sd8 = reinterpret_cast<float*>(smem + (size_t)nb4 * (sizeof(TabBeam) + sizeof(Beam)));
@@ -840,8 +947,29 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     const TabPlan& pl = s_plan;
     const bool table = pl.ok != 0 && (pl.batch != 0) == BATCH && (pl.wide != 0) == WIDE;
     const float cpm = a.grid.cells_per_meter;
-    for (int i = tid; i < nb; i += kTabThreads) {
-        const Beam b = a.beams[i];
+    // The beams the table pass evaluates, compacted: those table_cull_kernel found to score 0 for every particle of the
+    // slice are left out (their position in the compacted list is kept in the queue words for a moment).
+    const bool culling = !BATCH && table && pl.cull_ok && a.cull != nullptr;
+    if (warp == 0) {
+        int base = 0;
+        for (int i0 = 0; i0 < nb_all; i0 += 32) {
+            const int i = i0 + lane;
+            const bool keep = i < nb_all && !(culling && a.cull[i]);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (i < nb_all) squeue[i] = (uint16_t)(keep ? base + __popc(m & ((1u << lane) - 1u)) : 0xffffu);
+            base += __popc(m);
+        }
+        if (lane == 0) s_nb = base;
+    }
+    __syncthreads();
+    const int nb = s_nb;
+    uint16_t my_slot[2];                                     // (kTabMaxBeams <= 2 * kTabThreads)
+    for (int k = 0; k < 2; ++k) my_slot[k] = tid + k * kTabThreads < nb_all ? squeue[tid + k * kTabThreads] : (uint16_t)0xffffu;
+    __syncthreads();                                         // the queue words are free again
+    for (int k = 0; k < 2; ++k) {
+        if (my_slot[k] == 0xffffu) continue;
+        const int i = my_slot[k];
+        const Beam b = a.beams[tid + k * kTabThreads];
         sbeams[i] = b;
         TabBeam f;
         const float rc = __fmul_rn(b.range, cpm);
@@ -888,7 +1016,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
     // One unit = the 32 particles [p0, p0 + 32) below p_end, beams of the 32-beam words [w0, w1); add_mode: the unit is
     // one of several beam ranges of the same particles, whose partial sums add up in score2 (zeroed by the host).
     // (particles are addressed relative to the slice, in 32 bits: the loop is short of registers)
-    auto score_unit = [&](unsigned i0, unsigned i_end, int w0, int w1, bool add_mode, bool degrade) {
+    auto score_unit = [&](unsigned i0, unsigned i_end, int w0, int w1, bool add_mode, bool degrade, bool first_part) {
         const bool live = i0 + lane < i_end;
         float xa = 0.f, ya = 0.f, tha = 0.f, xb = 0.f, yb = 0.f, thb = 0.f;
         if (live) {
@@ -898,7 +1026,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) score_table_kernel(const TabAr
         TabBase fb = make_tab_base<INTERP>(xa, ya, tha, xb, yb, thb, gx, gy, cpm_d, pl);
         {
             const unsigned bad = __ballot_sync(0xffffffffu, live && !fb.ok);
-            if (bad && lane == 0 && w0 == 0) atomicAdd(a.build_info + 4, __popc(bad));
+            if (bad && lane == 0 && first_part) atomicAdd(a.build_info + 4, __popc(bad));
         }
         fb.ok = fb.ok && live && !degrade;
         const int edge = __reduce_max_sync(0xffffffffu, fb.ok ? fb.edge : 0);
@@ -942,6 +1070,7 @@ MCL_UNROLL(MCL_TAB_UNROLL)
         __syncwarp();
         acc += wacc[lane];
         wacc[lane] = 0;
+        if (COUNT && live && first_part) gathers += 3 * (nb_all - nb);      // a culled beam reads three cells in the reference
         if (live) {
             const long long p = a.lo + (long long)(i0 + lane);
             if (add_mode) atomicAdd(a.score2 + p, acc);
@@ -983,18 +1112,19 @@ MCL_UNROLL(MCL_TAB_UNROLL)
         const long long nunits = (a.hi - a.lo + 31) / 32;
         long long whole_units, items;
         int split;
-        table_tail_split(nunits, (long long)gridDim.x * kTabWarps, nwords, whole_units, split, items);
+        // (the split is the host's: it depends on the scan's beam count, not on how many beams survive the culling)
+        table_tail_split(nunits, (long long)gridDim.x * kTabWarps, (nb_all + 31) / 32, whole_units, split, items);
         for (long long item = (long long)blockIdx.x + (long long)gridDim.x * warp; item < items;
              item += (long long)gridDim.x * kTabWarps) {
             long long unit = item;
-            int w0 = 0, w1 = nwords;
+            int w0 = 0, w1 = nwords, part = 0;
             if (item >= whole_units) {
                 const long long sub = item - whole_units;
                 unit = whole_units + sub / split;
-                const int part = (int)(sub - (sub / split) * split);
+                part = (int)(sub - (sub / split) * split);
                 w0 = part * nwords / split; w1 = (part + 1) * nwords / split;
             }
-            score_unit((unsigned)(unit * 32), (unsigned)(a.hi - a.lo), w0, w1, item >= whole_units, degrade);
+            score_unit((unsigned)(unit * 32), (unsigned)(a.hi - a.lo), w0, w1, item >= whole_units, degrade, part == 0);
         }
     } else {
         const long long nbatches = (a.hi - a.lo + a.batch - 1) / a.batch;
@@ -1024,7 +1154,7 @@ MCL_UNROLL(MCL_TAB_UNROLL)
             const unsigned first = (unsigned)(b * a.batch);
             const unsigned last = (unsigned)((b + 1) * a.batch < a.hi - a.lo ? (b + 1) * a.batch : a.hi - a.lo);
             for (unsigned i0 = first + warp * 32; i0 < last; i0 += kTabThreads)
-                score_unit(i0, last, 0, nwords, false, degrade);
+                score_unit(i0, last, 0, nwords, false, degrade, true);
         }
         if (tid == 0 && table) {
             atomicMax(a.build_info + 0, max_count);

@@ -52,7 +52,7 @@ class Stats(C.Structure):
                 ("ms_score", C.c_float), ("ms_normalize", C.c_float), ("ms_estimate", C.c_float),
                 ("ms_total", C.c_float), ("lanes_per_particle", C.c_int), ("map_tile_used", C.c_int),
                 ("kernel_launches", C.c_int), ("collectives", C.c_int), ("peer_push", C.c_int), ("sensor_path", C.c_int), ("table_variant", C.c_int),
-                ("reserved", C.c_int * 1),
+                ("culled_beams", C.c_int),
                 ("deferred_evals", C.c_int64), ("fast_eps", C.c_double)]
 
     def as_dict(self):

@@ -93,7 +93,8 @@ typedef struct {
     int     sensor_path;          /* path of the last scoring pass: 3 = score-table pass, 2 = certified float pass + exact
                                      re-evaluation (two kernels), 1 = exact only */
     int     table_variant;        /* score-table pass: 0 / 1 = one window, 16- / 8-bit classes; 2 / 3 = one window per batch */
-    int     reserved[1];
+    int     culled_beams;         /* score-table pass: beams of the last scan that score 0 for every particle of the slice
+                                     (their endpoints can only lie in open space) and were not evaluated */
     int64_t deferred_evals;       /* evaluations of the last scoring pass the float pass could not certify (re-done exactly) */
     double  fast_eps;             /* error bound (cells) the certification used, 0 when the exact path ran alone */
 } mcl_stats;

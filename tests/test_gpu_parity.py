@@ -950,6 +950,43 @@ def test_map_update_reference_golden(real_map):
     e.close()
 
 
+@pytest.mark.parametrize("theta,sigma_theta,expect_cull", [(0.4, 0.05, True), (3.13, 0.05, True), (-1.2, 0.9, False)])
+def test_beam_culling_is_exact(theta, sigma_theta, expect_cull, monkeypatch):
+    """The score-table pass leaves out the beams whose endpoints can only lie in class-0 cells (nothing positive within
+    two cells) for every particle of the slice: they score 0 in the reference.  Scores with and without the culling
+    equal the oracle's, map-read counts included; a robot in open space culls beams, a heading spread beyond 2.5 rad
+    switches the culling off, headings around +-pi do not confuse the heading range."""
+    grid = synth.make_map(700, seed=31)
+    rng = np.random.default_rng(31)
+    best, pose = -1, None
+    for _ in range(40):                                      # the candidate with the most max-range (no-hit) rays
+        x, y, _t = synth.find_free_pose(grid, rng, clearance=30)
+        r, th, t = synth.make_scan(grid, (x, y, theta), seed=7)
+        if (r > 7.9).sum() > best:
+            best, pose = int((r > 7.9).sum()), (x, y, theta)
+    r, th, t = synth.make_scan(grid, pose, seed=7)
+    cloud = synth.make_particles(40_000, pose, seed=3, sigma_xy=0.10, sigma_theta=sigma_theta,
+                                 parent_utime=int(t[0]) - 100_000, pose_utime=int(t[-1]))
+    want, gathers, evals = port.likelihood(port_grid(grid), cloud, r, th, t)
+    out = {}
+    for cull in (True, False):
+        if cull:
+            monkeypatch.delenv("MCL_NO_CULL", raising=False)
+        else:
+            monkeypatch.setenv("MCL_NO_CULL", "1")
+        e = make_engine(len(cloud), grid)
+        e.import_particles(cloud)
+        e.set_gather_counting(True)
+        s = e.score(r, th, t)
+        st = e.stats()
+        assert st["sensor_path"] == 3 and np.array_equal(s, want)
+        assert st["evals"] == evals and st["gathers"] == gathers
+        out[cull] = st["culled_beams"]
+        e.close()
+    assert out[False] == 0
+    assert (out[True] > 0) == expect_cull, (out, best)
+
+
 @pytest.mark.parametrize("path", [0, 2])
 def test_scoring_follows_device_map_updates(path):
     """The fast passes read a derived copy of the map (empty-neighbourhood look-ahead), the score-table pass builds its
