@@ -1146,7 +1146,11 @@ int fetch_estimate(mcl_engine* h, int64_t utime) { return read_back(h, false, tr
 
 // The five stages of ParticleFilter::updateFilter on the engine's stream, no host synchronisation unless the tile
 // heuristic needs the cloud's bounding box.
-int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r, const float* noise_dev)
+// scan (optional): host scan buffers to prepare and upload between the action step and the sensor stage, so that the
+// host's share of it (compaction, interpolation ratios) runs while the GPU resamples and moves the cloud.
+struct HostScan { const float* ranges; const float* thetas; const int64_t* times; int nb; long long t_begin, t_end; };
+int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r, const float* noise_dev,
+                   const HostScan* scan = nullptr)
 {
     h->launches = 0;
     h->collectives = 0;
@@ -1159,6 +1163,10 @@ int enqueue_update(mcl_engine* h, const mcl_action_t* a, int64_t utime, double r
     rc = run_action(h, a, utime, noise_dev, true);
     if (rc) return rc;
     prof_mark(h, "action");
+    if (scan) {
+        rc = prepare_scan(h, scan->ranges, scan->thetas, scan->times, scan->nb, scan->t_begin, scan->t_end);
+        if (rc) return rc;
+    }
     cudaEventRecord(h->ev[2], h->stream);
     rc = run_score(h);
     if (rc) return rc;
@@ -1988,10 +1996,10 @@ int mcl_update(mcl_engine* h, const mcl_action_t* a, int64_t odometry_utime, con
         if (rc) return rc;
         // the scan's interpolation ratios depend on the utimes the action step is about to assign
         const long long t_end = h->params.legacy_equal_utime ? h->pose_utime : odometry_utime;
-        CK(cudaStreamSynchronize(h->stream));
-        rc = prepare_scan(h, ranges, thetas, times, nb, h->pose_utime, t_end);
-        if (rc) return rc;
-        rc = enqueue_update(h, a, odometry_utime, r, nd);
+        if (nb < 0 || (nb > 0 && (!ranges || !thetas || !times))) return fail(h, MCL_ERR_INVALID, "bad scan arrays");
+        CK(cudaStreamSynchronize(h->stream));       // (the scan staging buffer may still be in flight)
+        const HostScan scan{ranges, thetas, times, nb, h->pose_utime, t_end};
+        rc = enqueue_update(h, a, odometry_utime, r, nd, &scan);
         if (rc) return rc;
         rc = read_back(h, true, true, odometry_utime);
         if (rc) return rc;
