@@ -4,8 +4,10 @@ tag=${1:-r02aa}
 mkdir -p gpurun_out
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29618 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/${tag}_bench_config4_8gpu.json 2> gpurun_out/${tag}_bench_8gpu.err
 tail -2 gpurun_out/${tag}_bench_8gpu.err
+if [ -n "$MCL_WANT_PROFILE" ]; then
 MCL_PROFILE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29619 bench.py --gpus 8 --steps 10 --warmup 3 --no-extra > gpurun_out/${tag}_prof_8gpu.json 2> gpurun_out/${tag}_prof_8gpu.err
 grep -A20 "MCL_PROFILE rank 0" gpurun_out/${tag}_prof_8gpu.err | head -22
+fi
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus 4 --steps 20 --warmup 5 --no-extra > gpurun_out/${tag}_bench_config4_4gpu.json 2> gpurun_out/${tag}_bench_4gpu.err
 for f in gpurun_out/${tag}_bench_*.json; do python - "$f" <<'PY'
 import json,sys
