@@ -385,3 +385,70 @@ def table_pass(grid, plan, K, T, particle, ranges, thetas, ratios, min_range, rn
     dir_ok = x2_pos & (np.abs((np.abs(u8) - TAB_B2).astype(F)) > d8)
     certain = (Kv == 0) | (cell_ok & ((Kv < TAB_FIXED) | dir_ok))
     return np.where(certain, v, 0), certain, edge
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Beam culling of the score-table pass (mcl_table.cuh: table_bbox_kernel's heading range, table_plan_kernel's cull
+# fields, table_cull_kernel): a beam is left out when every class-map cell its endpoints can fall into is class 0.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Window:
+    def __init__(self, x0, y0, w, h):
+        self.x0, self.y0, self.w, self.h = x0, y0, w, h
+
+
+def class_zero_map(grid, apron=4):
+    """Boolean map over the grid plus the apron: True where the class map holds class 0 (index [gy + apron, gx + apron])."""
+    K, _, _ = build_score_table(grid, _Window(-apron, -apron, grid.width + 2 * apron, grid.height + 2 * apron))
+    return K == 0
+
+
+def _fold(d):
+    return np.where(np.abs(d) > np.pi, d - np.sign(d) * 2 * np.pi, d)
+
+
+def cull_flags(grid, cloud, ranges, thetas, ratios, min_range, margin=4.5, hw_scale=1.0, apron=4):
+    """Per valid beam: True = culled.  margin / hw_scale exist so that a test can show the rule is not vacuous."""
+    valid = ranges > F(min_range)
+    r, th = ranges[valid], thetas[valid]
+    flags = np.zeros(len(r), bool)
+    rho = ratios[valid]
+    ta, tb = cloud["pose"]["theta"], cloud["parent_pose"]["theta"]
+    if not (rho.min() >= 0.0 and rho.max() <= 1.0 and (np.abs(ta) <= F(3.15)).all() and (np.abs(tb) <= F(3.15)).all()):
+        return flags
+    th_ref = np.float64(tb[0])
+    db = _fold(tb.astype(np.float64) - th_ref)
+    da = db + _fold(ta.astype(np.float64) - tb.astype(np.float64))
+    a0 = np.nextafter(F(min(db.min(), da.min())), F(-np.inf))          # rounded outward, as __double2float_rd / _ru
+    a1 = np.nextafter(F(max(db.max(), da.max())), F(np.inf))
+    if not (np.isfinite(a0) and np.isfinite(a1) and a1 - a0 < F(2.5)):
+        return flags
+    cpm = np.float64(F(grid.cells_per_meter))
+    ox, oy = np.float64(F(grid.origin_x)), np.float64(F(grid.origin_y))
+    xs = np.concatenate([cloud["pose"]["x"], cloud["parent_pose"]["x"]]).astype(np.float64)
+    ys = np.concatenate([cloud["pose"]["y"], cloud["parent_pose"]["y"]]).astype(np.float64)
+    bx0, bx1, by0, by1 = (xs.min() - ox) * cpm, (xs.max() - ox) * cpm, (ys.min() - oy) * cpm, (ys.max() - oy) * cpm
+    ca0, ca1 = th_ref + np.float64(a0), th_ref + np.float64(a1)
+    zero = class_zero_map(grid, apron)
+    H, W = grid.height, grid.width
+    cx, cy, hx, hy = 0.5 * (bx0 + bx1), 0.5 * (by0 + by1), 0.5 * (bx1 - bx0), 0.5 * (by1 - by0)
+    for b in range(len(r)):
+        rc = np.float64(F(r[b]) * F(grid.cells_per_meter))
+        am = 0.5 * (ca0 + ca1) - np.float64(th[b])
+        hw = (0.5 * (ca1 - ca0) * (1 + 1e-6) + 1e-6) * hw_scale
+        cs, sn = np.cos(am), np.sin(am)
+        bu, bv = hx * abs(cs) + hy * abs(sn), hx * abs(sn) + hy * abs(cs)
+        u0, u1 = rc * np.cos(hw) * (1 - 1e-6) - bu - margin, rc * (1 + 1e-6) + bu + margin
+        vm = rc * np.sin(hw) * (1 + 1e-6) + bv + margin
+        ex = max(abs(u0), abs(u1)) * abs(cs) + vm * abs(sn)
+        ey = max(abs(u0), abs(u1)) * abs(sn) + vm * abs(cs)
+        x0, x1 = max(int(np.floor(cx - ex)), -apron), min(int(np.ceil(cx + ex)), W + apron - 1)
+        y0, y1 = max(int(np.floor(cy - ey)), -apron), min(int(np.ceil(cy + ey)), H + apron - 1)
+        if x1 < x0 or y1 < y0:
+            flags[b] = True                                   # wholly beyond the apron: class 0 everywhere
+            continue
+        gy, gx = np.meshgrid(np.arange(y0, y1 + 1), np.arange(x0, x1 + 1), indexing="ij")
+        dx, dy = gx - cx, gy - cy
+        u, v = dx * cs + dy * sn, dy * cs - dx * sn
+        inside = (u >= u0 - 0.01) & (u <= u1 + 0.01) & (np.abs(v) <= vm + 0.01)
+        flags[b] = bool(zero[gy + apron, gx + apron][inside].all())
+    return flags

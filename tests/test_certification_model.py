@@ -212,3 +212,53 @@ def test_table_check_is_sensitive():
         plan.t3 = np.float32(0.0)
     res = _table_case(3, perturb=blind)
     assert res is not None and res[0] > 0
+
+
+# ------------------------------------------------------------------------------------------------ beam culling (CPU)
+def _cull_case(case):
+    """A tracking cloud in the open part of a map (so that some rays end in open space), several geometries."""
+    rng = np.random.default_rng(8100 + case)
+    mpc = [0.05, 0.05, 0.025, 0.05][case % 4]
+    side = [500, 700, 600, 400][case % 4]
+    grid = synth.make_map(side, seed=40 + case, meters_per_cell=mpc)
+    theta = [0.3, 3.12, -1.6, -3.1][case % 4]
+    best, pose = -1, None
+    for _ in range(25):
+        x, y, _t = synth.find_free_pose(grid, rng, clearance=24)
+        r, th, t = synth.make_scan(grid, (x, y, theta), seed=case, max_range=[8.0, 8.0, 5.0, 12.0][case % 4])
+        far = int((r > 0.95 * r.max()).sum())
+        if far > best:
+            best, pose = far, (x, y, theta)
+    r, th, t = synth.make_scan(grid, pose, seed=case, max_range=[8.0, 8.0, 5.0, 12.0][case % 4])
+    cloud = synth.make_particles(120, pose, seed=case, sigma_xy=0.08, sigma_theta=0.04, parent_utime=int(t[0]) - 100_000,
+                                 pose_utime=int(t[-1]))
+    return grid, cloud, r, th, t
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_culled_beams_score_zero_for_every_particle(case):
+    """The culling rule of the score-table pass, restated in numpy (certification_model.cull_flags): every beam it culls
+    scores exactly 0 in the ORACLE for every particle of the cloud, and in open space it does cull beams."""
+    grid, cloud, r, th, t = _cull_case(case)
+    t0, t1 = int(cloud["parent_pose"]["utime"][0]), int(cloud["pose"]["utime"][0])
+    ratios = (t - t0).astype(np.float64) / float(t1 - t0)
+    flags = cm.cull_flags(grid, cloud, r, th, ratios, MIN_RANGE)
+    pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
+    per_ray = np.stack([port.ray_scores(pg, cloud[i], r, th, t) for i in range(len(cloud))])       # [particles, beams]
+    assert per_ray.shape[1] == len(flags)
+    assert (per_ray[:, flags] == 0).all()
+    assert flags.sum() > 0, "no beam culled: the case does not exercise the rule"
+
+
+def test_the_culling_check_is_sensitive():
+    """Negative control: a rule that ignores the heading spread and the margins culls beams that do score somewhere."""
+    wrong = 0
+    for case in range(4):
+        grid, cloud, r, th, t = _cull_case(case)
+        t0, t1 = int(cloud["parent_pose"]["utime"][0]), int(cloud["pose"]["utime"][0])
+        ratios = (t - t0).astype(np.float64) / float(t1 - t0)
+        flags = cm.cull_flags(grid, cloud, r, th, ratios, MIN_RANGE, margin=-6.0, hw_scale=0.02)
+        pg = port.Grid(grid.cells, grid.origin_x, grid.origin_y, grid.cells_per_meter)
+        per_ray = np.stack([port.ray_scores(pg, cloud[i], r, th, t) for i in range(len(cloud))])
+        wrong += int((per_ray[:, flags] != 0).any(axis=0).sum())
+    assert wrong > 0
