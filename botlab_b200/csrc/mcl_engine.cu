@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #ifdef MCL_WITH_NCCL
@@ -106,6 +107,7 @@ struct mcl_engine {
     int* tab_build = nullptr;           // [0] table entries needed, [1] CTAs whose table overflowed
     struct TabHint { TabPlan plan; int build[8]; };
     TabHint* tab_hint = nullptr;        // pinned
+    TabHint* tab_hint_dev = nullptr;    // device: tab_plan and tab_build point into it
     cudaEvent_t ev_tab_hint = nullptr;
     bool tab_hint_pending = false;
     bool tab_ok = false;                // the last plan the host has seen allows the table pass
@@ -113,6 +115,7 @@ struct mcl_engine {
     int tab_variant = 0;                // kTabSingle16 .. kTabBatch8 (mcl_table.cuh): what the next pass launches
     int tab_excluded = 0;               // variants whose score table overflowed on this cloud
     uint8_t* tab_cull = nullptr;        // per beam: 1 = the table pass skips it (table_cull_kernel)
+    std::unordered_map<const void*, int> smem_attr;     // kernels whose dynamic shared-memory limit has been raised, to what
     int cull_interval = 1, cull_wait = 0;   // the culling pass runs every cull_interval-th update while it finds nothing
     int tab_batch = kTabBatch;          // kTabBatch = 4096, halved down to kTabBatchSmall = 1024 until the windows fit
     int4* tab_bboxes = nullptr;         // bounding box per batch
@@ -204,6 +207,19 @@ void prof_collect(mcl_engine* h)          // after a stream synchronisation
     h->prof_n = 0;
 }
 
+int fail(mcl_engine* h, int code, const char* fmt, ...);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size (the call costs the host microseconds)
+template <class K>
+int raise_smem(mcl_engine* h, K kernel, size_t bytes)
+{
+    auto it = h->smem_attr.find((const void*)kernel);
+    if (it != h->smem_attr.end() && it->second >= (int)bytes) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(h, MCL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    h->smem_attr[(const void*)kernel] = (int)bytes;
+    return 0;
+}
+
 int fail(mcl_engine* h, int code, const char* fmt, ...)
 {
     char buf[512];
@@ -272,7 +288,7 @@ int xbarrier(mcl_engine* h, int slot)
 
 // ---- exact sequential running sum of the weights (buffer wbuf of the exchange block), sharded over the ranks ----------------
 // Leaves the exact total in h->total and the exact entry sum of every group in h->cin2 on every rank.
-int seq_total(mcl_engine* h, int wbuf)
+int seq_total(mcl_engine* h, int wbuf, double* zero_after = nullptr)
 {
     const long long n = h->n, n1 = h->n1, n2 = h->n2;
     const double* w = h->weight[wbuf];
@@ -285,13 +301,12 @@ int seq_total(mcl_engine* h, int wbuf)
         xseq_chunk_sums_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_sums);
         CKL(h);
     }
-    xseq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tile_lo, tile_hi, h->tile_excl, h->xp, h->xl.tot);
+    xseq_tile_scan_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sums, tile_lo, tile_hi, h->tile_excl, h->xp, h->xl.tot, h->fb_count);
     CKL(h);
     prof_mark(h, "seq:S1+S2");
     int rc = xbarrier(h, 0);
     if (rc) return rc;
     prof_mark(h, "seq:barrierA");
-    CK(cudaMemsetAsync(h->fb_count, 0, sizeof(int), h->stream));
     if (tiles > 0) {
         XSeqOut o{h->xl.q0, h->xl.q1, h->xl.eb, h->xl.fbraw};
         xseq_chunk_maps_kernel<<<tiles, 128, 0, h->stream>>>(w, n, n1, tile_lo, h->sums, h->tile_excl,
@@ -308,10 +323,10 @@ int seq_total(mcl_engine* h, int wbuf)
     {
         const size_t walk_smem = xseq_walk_smem(n2);                 // group maps + the pre-staged chunk maps and raw chunks
         const int staged = walk_smem + 4096 <= (size_t)h->max_smem_optin ? 1 : 0;
-        if (staged) CK(cudaFuncSetAttribute(xseq_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+        if (staged) { int rc2 = raise_smem(h, xseq_walk_kernel, walk_smem); if (rc2) return rc2; }
         xseq_walk_kernel<<<1, staged ? 1024 : 32, staged ? walk_smem : 0, h->stream>>>(
             n, n1, n2, h->ebias, h->q0, h->q1, h->gebias, h->g0, h->g1, h->cin2, h->cin1, h->opened, h->total,
-            h->fallbacks, staged, h->xp, h->xl.w[wbuf], h->xl.fbraw);
+            h->fallbacks, staged, h->xp, h->xl.w[wbuf], h->xl.fbraw, zero_after);
         CKL(h);
     }
     prof_mark(h, "seq:walk");
@@ -700,7 +715,8 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
                                                                 h->grid, rc6, k_budget, h->tab_box,
                                                                 allow_batch ? h->tab_bboxes : nullptr);
         CKL(h);
-        table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan);
+        table_plan_kernel<<<1, 1, 0, h->stream>>>(in, h->tab_box, h->tab_plan, h->tab_build, h->deferred_counter,
+                                                  h->count_gathers ? h->gather_counter : nullptr);
         CKL(h);
         return MCL_OK;
     };
@@ -746,7 +762,6 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
         h->cull_wait = 0;
         a.cull = h->tab_cull;
     }
-    CK(cudaMemsetAsync(h->tab_build, 0, 8 * sizeof(int), h->stream));
     if (a.cull) {
         table_cull_kernel<<<h->num_beams, 256, 0, h->stream>>>(h->tab_plan, sa.beams, h->num_beams, h->grid, h->map_cls, h->cpitch,
                                                                h->tab_cull, h->tab_build + 5);
@@ -766,7 +781,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
                                h->stream));
     }
     auto launch = [&](auto kernel) -> int {
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
+        { int rc2 = raise_smem(h, kernel, smem_total); if (rc2) return rc2; }
         kernel<<<blocks, kTabThreads, smem_total, h->stream>>>(a);
         CKL(h);
         return MCL_OK;
@@ -781,8 +796,7 @@ int run_score_table(mcl_engine* h, ScoreArgs& sa)
     else rc = h->count_gathers ? pick(F{}, T{}) : pick(F{}, F{});
     if (rc) return rc;
     // the plan and the build summary follow the kernel to pinned memory: the hint for the next update
-    CK(cudaMemcpyAsync(&h->tab_hint->plan, h->tab_plan, sizeof(TabPlan), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->tab_hint->build, h->tab_build, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->tab_hint, h->tab_hint_dev, sizeof(mcl_engine::TabHint), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->ev_tab_hint, h->stream));
     h->tab_hint_pending = true;
     return 1 + h->tab_variant;
@@ -805,11 +819,8 @@ int run_score(mcl_engine* h)
     a.grid = h->grid;
     a.gather_counter = h->gather_counter;
     a.deferred_counter = h->deferred_counter;
-    if (h->count_gathers) CK(cudaMemsetAsync(h->gather_counter, 0, sizeof(unsigned long long), h->stream));
-    CK(cudaMemsetAsync(h->deferred_counter, 0, sizeof(unsigned long long), h->stream));
-
     if (local > 0) {
-        const int tr = run_score_table(h, a);
+        const int tr = run_score_table(h, a);       // (its plan kernel zeroes the counters)
         if (tr < 0) return tr;
         if (tr >= 1) {
             int rc = join_pushes(h);
@@ -824,6 +835,8 @@ int run_score(mcl_engine* h)
             return MCL_OK;
         }
     }
+    if (h->count_gathers) CK(cudaMemsetAsync(h->gather_counter, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->deferred_counter, 0, sizeof(unsigned long long), h->stream));
 
     // lanes per particle: enough particle groups to fill the machine (148 SMs x 8 CTAs x (256/G) slots)
     int G = h->params.lanes_per_particle;
@@ -975,9 +988,8 @@ int run_normalize(mcl_engine* h)
         CKL(h);
     }
     prof_mark(h, "normalise:floor");
-    int rc = seq_total(h, h->wcur);
+    int rc = seq_total(h, h->wcur, h->ess_acc);          // (the walk also zeroes the sum of squares the divide accumulates)
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->ess_acc, 0, sizeof(double), h->stream));
     if (local > 0) {
         xdivide_kernel<<<g, 256, 0, h->stream>>>(w, lo, hi, h->total, h->ess_acc);
         CKL(h);
@@ -1071,7 +1083,7 @@ int run_resample_indices(mcl_engine* h, double r, int wbuf, long long children =
     const long long n = h->n, n1 = h->n1, n2 = h->n2;
     if (children < 0) { children = n; clo = h->lo; chi = h->hi; idx_out = h->idx; }
     const long long local = chi - clo;
-    xresample_range_kernel<<<1, 32, 0, h->stream>>>(h->cin2, n2, children, r, clo, chi, h->xrange);
+    xresample_range_kernel<<<1, 32, 0, h->stream>>>(h->cin2, n2, children, r, clo, chi, h->xrange, h->overruns);
     CKL(h);
     const long long groups_cap = (h->world == 1 || children != n) ? n2
                                : std::min<long long>(n2, 2 * ((local + kSliceAlign - 1) / kSliceAlign) + 64);
@@ -1082,7 +1094,6 @@ int run_resample_indices(mcl_engine* h, double r, int wbuf, long long children =
     xseq_materialize_kernel<<<(int)std::min<long long>(tiles_cap, (long long)h->sm_count * 32), 128, 0, h->stream>>>(
         n, n1, h->cin1, h->cum, h->xrange, h->xp, h->xl.w[wbuf]);
     CKL(h);
-    CK(cudaMemsetAsync(h->overruns, 0, sizeof(unsigned long long), h->stream));
     if (local > 0) {
         xresample_search_kernel<<<grid_for(h, (local + kSearchRun - 1) / kSearchRun, 128), 128, 0, h->stream>>>(
             h->cum, n, children, r, clo, chi, h->xrange, idx_out, h->overruns);
@@ -1211,7 +1222,7 @@ void free_all(mcl_engine* h)
     if (h->host_bbox_init) cudaFreeHost(h->host_bbox_init);
     if (h->tab_hint) cudaFreeHost(h->tab_hint);
     if (h->ev_tab_hint) cudaEventDestroy(h->ev_tab_hint);
-    F(h->tab_plan); F(h->tab_build); F(h->tab_box); F(h->tab_bboxes); F(h->tab_cull);
+    F(h->tab_hint_dev); F(h->tab_box); F(h->tab_bboxes); F(h->tab_cull);
     if (h->readback_host) cudaFreeHost(h->readback_host);
     if (h->readback_dev) cudaFree(h->readback_dev);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -1355,9 +1366,11 @@ int mcl_create(const mcl_params* params, int64_t num_particles, int device, mcl_
     CKB(cudaMalloc((void**)&h->tab_cull, kTabMaxBeams + 1));
     CKB(cudaMemset(h->tab_cull, 0, kTabMaxBeams + 1));
     CKB(cudaMemcpy(h->tab_box, h->host_bbox_init, 16, cudaMemcpyHostToDevice));
-    CKB(cudaMalloc((void**)&h->tab_plan, sizeof(TabPlan)));
-    CKB(cudaMemset(h->tab_plan, 0, sizeof(TabPlan)));
-    CKB(cudaMalloc((void**)&h->tab_build, 8 * sizeof(int)));
+    // the plan and the build summary share one buffer (same layout as the pinned TabHint): one copy brings both back
+    CKB(cudaMalloc((void**)&h->tab_hint_dev, sizeof(mcl_engine::TabHint)));
+    CKB(cudaMemset(h->tab_hint_dev, 0, sizeof(mcl_engine::TabHint)));
+    h->tab_plan = &h->tab_hint_dev->plan;
+    h->tab_build = h->tab_hint_dev->build;
     CKB(cudaMallocHost((void**)&h->tab_hint, sizeof(mcl_engine::TabHint)));
     std::memset(h->tab_hint, 0, sizeof(mcl_engine::TabHint));
     CKB(cudaEventCreateWithFlags(&h->ev_tab_hint, cudaEventDisableTiming));

@@ -129,12 +129,13 @@ __global__ void __launch_bounds__(128) xseq_chunk_sums_kernel(const double* w, l
 }
 
 // ---- S2: exclusive scan of the slice's tile totals (slice-relative) + the slice total to every rank ----------------------
+// (also re-arms fb_count, the side-buffer slot counter S3 is about to use)
 __global__ void __launch_bounds__(1024) xseq_tile_scan_kernel(const double* tile_sums, long long tile_lo, long long tile_hi,
-                                                              double* tile_excl, const XPeers xp, size_t tot_off)
+                                                              double* tile_excl, const XPeers xp, size_t tot_off, int* fb_count)
 {
     __shared__ double warp_tot[32];
     __shared__ double carry_s;
-    if (threadIdx.x == 0) carry_s = 0.0;
+    if (threadIdx.x == 0) { carry_s = 0.0; *fb_count = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (long long base = tile_lo; base < tile_hi; base += 1024) {
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
                                                        const long long* q0, const long long* q1, const int* gebias,
                                                        const long long* g0, const long long* g1, double* cin2, double* cin1,
                                                        int* opened, double* total, long long* fallback_chunks, int staged,
-                                                       const XPeers xp, size_t w_off, size_t fbraw_off)
+                                                       const XPeers xp, size_t w_off, size_t fbraw_off, double* zero_after)
 {
     __shared__ double fb_chunk[kL1];
     __shared__ long long sc0[kL2], sc1[kL2];      // level-1 maps of the group being opened
@@ -494,16 +495,19 @@ __global__ void __launch_bounds__(1024) xseq_walk_kernel(long long n, long long 
     if (lane == 0) {
         *total = c;
         *fallback_chunks = fallbacks;
+        if (zero_after) *zero_after = 0.0;          // (the normaliser's sum of squares, accumulated by the divide that follows)
     }
 }
 
 // ---- resampling: which groups do this rank's children draw from? ---------------------------------------------------------
 // Child m compares U_m = r + m/N with the running sum; its parent lies in the last group whose ENTRY sum is below U_m.
 // range[0], range[1] = first and last such group over the rank's children [lo, hi).
+// (also re-arms the search's overrun counter)
 __global__ void xresample_range_kernel(const double* cin2, long long n2, long long children, double r, long long lo,
-                                       long long hi, long long* range)
+                                       long long hi, long long* range, unsigned long long* overruns)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    *overruns = 0ull;
     const double m_inv = __ddiv_rn(1.0, (double)children);
     auto last_below = [&](double u) {
         long long a = 0, b = n2;                 // first j with !(cin2[j] < u)

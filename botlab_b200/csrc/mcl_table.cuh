@@ -282,8 +282,13 @@ __global__ void __launch_bounds__(256) table_bbox_kernel(const float* x, const f
 }
 
 // One thread: boxes -> window(s) -> budget.  Re-arms the boxes for the next table_bbox_kernel.
-__global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out)
+// Also re-arms what the score kernel accumulates into: the build summary and the deferred / gather counters.
+__global__ void table_plan_kernel(const TabPlanIn in, int* box, TabPlan* out, int* build, unsigned long long* deferred,
+                                  unsigned long long* gathers)
 {
+    for (int i = 0; i < 8; ++i) build[i] = 0;
+    *deferred = 0ull;
+    if (gathers) *gathers = 0ull;
     TabPlan pl;
     memset(&pl, 0, sizeof(pl));
     const int b0 = box[0], b1 = box[1], b2 = box[2], b3 = box[3];
