@@ -452,3 +452,43 @@ def cull_flags(grid, cloud, ranges, thetas, ratios, min_range, margin=4.5, hw_sc
         inside = (u >= u0 - 0.01) & (u <= u1 + 0.01) & (np.abs(v) <= vm + 0.01)
         flags[b] = bool(zero[gy + apron, gx + apron][inside].all())
     return flags
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 8-bit class tile of the score-table pass (mcl_table.cuh, WIDE): classes 0..128 as in K; a cell with a table entry
+# holds 129 + its number within its 64-cell row segment, segments being aligned in (cell + bias_x), and the row's
+# segment bases complete the entry's index.
+# ---------------------------------------------------------------------------------------------------------------------
+def tab_nseg(tw):
+    bias = 127 * tw - 191
+    return ((bias + tw - 1) >> 6) - (bias >> 6) + 1
+
+
+def build_score_table_wide(K):
+    """From the 16-bit tile K (build_score_table): the 8-bit tile, the segment bases [h, nseg] and, per entry of the
+    wide numbering, the 16-bit tile's entry it must equal."""
+    h, w = K.shape
+    bias_x = 127 * w - 191
+    nseg = tab_nseg(w)
+    K8 = np.where(K < TAB_FIXED, K, 0).astype(np.int64)
+    base = np.zeros((h, nseg), np.int64)
+    entry_of = []                                    # wide entry index - TAB_FIXED -> K16 entry
+    for ty in range(h):
+        seg = ((np.arange(w) + bias_x) >> 6) - (bias_x >> 6)
+        assert seg.min() >= 0 and seg.max() < nseg
+        for sg in range(nseg):
+            cols = np.flatnonzero((seg == sg) & (K[ty] >= TAB_FIXED))
+            assert len(cols) <= 64
+            base[ty, sg] = TAB_FIXED + len(entry_of)
+            for i, tx in enumerate(cols):            # numbered in column order, as the ballots do
+                K8[ty, tx] = TAB_FIXED + i
+                entry_of.append(K[ty, tx])
+    assert K8.max() < 256
+    return K8, base, np.array(entry_of, np.int64), bias_x
+
+
+def wide_entry(K8, base, bias_x, cy, cx):
+    """Entry index of cell (cy, cx) as tab_eval<WIDE> forms it: K for the uniform classes, else segment base + K - 129."""
+    k = K8[cy, cx]
+    sg = ((cx + bias_x) >> 6) - (bias_x >> 6)
+    return np.where(k < TAB_FIXED, k, base[cy, sg] + k - TAB_FIXED)

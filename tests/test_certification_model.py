@@ -262,3 +262,24 @@ def test_the_culling_check_is_sensitive():
         per_ray = np.stack([port.ray_scores(pg, cloud[i], r, th, t) for i in range(len(cloud))])
         wrong += int((per_ray[:, flags] != 0).any(axis=0).sum())
     assert wrong > 0
+
+
+# ------------------------------------------------------------------------------------------------ 8-bit class tile (CPU)
+@pytest.mark.parametrize("case", [0, 1, 2, 5])
+def test_wide_tile_addresses_the_same_entries(case):
+    """The 8-bit class tile + segment bases (windows too large for 16-bit classes) resolve every window cell to the same
+    score-table entry as the 16-bit tile does."""
+    grid, cloud, r, th, t = make_case(case)
+    ratios = (t - int(cloud["parent_pose"]["utime"][0])).astype(np.float64) / float(
+        int(cloud["pose"]["utime"][0]) - int(cloud["parent_pose"]["utime"][0]))
+    plan = cm.TabPlan(grid, cloud, r, th, ratios, MIN_RANGE, smem_total=10 ** 7)
+    if not plan.ok:
+        pytest.skip("no table plan for this geometry")
+    K, T, n_entries = cm.build_score_table(grid, plan)
+    K8, base, entry_of, bias_x = cm.build_score_table_wide(K)
+    assert len(entry_of) == n_entries and cm.tab_nseg(plan.w) == base.shape[1]
+    cy, cx = np.meshgrid(np.arange(plan.h), np.arange(plan.w), indexing="ij")
+    e = cm.wide_entry(K8, base, bias_x, cy, cx)
+    k16 = np.where(e < cm.TAB_FIXED, e, entry_of[np.maximum(e - cm.TAB_FIXED, 0)])
+    assert np.array_equal(k16, K)
+    assert (T[k16] == T[K]).all()
